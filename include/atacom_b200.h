@@ -1,0 +1,152 @@
+/* atacom_b200.h — C ABI of libatacom_b200.so: batched ATACOM tangent-space projection on B200 (sm_100a).
+ *
+ * The reference (PuzeLiu/rl_on_manifold) has no FFI layer: its boundary is the Python method
+ * AtacomEnvWrapper.step_action_function(sim_state, alpha) (atacom/atacom.py:123-139) that a base
+ * environment calls back once per simulator sub-step, one environment at a time, on NumPy float64
+ * vectors.  Each entry point below replaces that call (and the helpers it reaches) for a BATCH of B
+ * independent environments of one family; INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - all array pointers are caller-owned DEVICE memory, fp32, contiguous row-major [B, dim];
+ *    `*_host` entry points take HOST pointers instead and do the copies themselves;
+ *  - `stream` is a cudaStream_t (NULL = default stream); calls are asynchronous on it; there is no
+ *    global mutable state, so calls on different streams are independent;
+ *  - s_in and s_out may alias (the reference integrates the slack in place, atacom.py:135);
+ *  - `status` (optional, may be NULL) receives one ATACOM_ST_* bit set per environment;
+ *  - `w_dbg` (optional, may be NULL) receives [B, 2*(n+G)]: the min-norm part -Jc^+(psi + K_c c)
+ *    (= _act_a + _act_err of the reference) followed by the null-space part Nc alpha (= _act_b);
+ *  - return value: ATACOM_OK or a negative ATACOM_ERR_* code; never throws, never aborts.
+ */
+#ifndef ATACOM_B200_H_
+#define ATACOM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATACOM_MAX_Q 8   /* dim_q                      */
+#define ATACOM_MAX_F 4   /* equality rows              */
+#define ATACOM_MAX_G 16  /* inequality rows / slacks   */
+#define ATACOM_MAX_C 20  /* F + G                      */
+#define ATACOM_ENV_PARAMS 24
+
+enum {
+  ATACOM_OK = 0,
+  ATACOM_ERR_NULL_POINTER = -1,
+  ATACOM_ERR_BAD_DIMS = -2,
+  ATACOM_ERR_BAD_PARAM = -3,
+  ATACOM_ERR_CUDA = -4,
+  ATACOM_ERR_NO_DEVICE = -5,
+  ATACOM_ERR_ALIGNMENT = -6
+};
+
+/* per-environment status bits */
+enum {
+  ATACOM_ST_RANK_DEFICIENT = 1, /* Jc lost row rank: pinv_null would cut a singular value           */
+  ATACOM_ST_COLUMN_DROPPED = 2, /* the tolerance branch of rref fired (null_space_coordinate.py:60) */
+  ATACOM_ST_SLACK_PIVOT = 4,    /* a slack column became a tangent coordinate                       */
+  ATACOM_ST_NONFINITE = 8,
+  ATACOM_ST_DENSE_PATH = 16     /* structured fast path deferred to the dense Householder path      */
+};
+
+enum { ATACOM_VARIANT_ATACOM = 0, ATACOM_VARIANT_ERROR_CORRECTION = 1 };
+enum { ATACOM_BIAS_JDOT_QDOT = 0, ATACOM_BIAS_OMEGA_X_V = 1 };
+
+/* Constructor arguments of AtacomEnvWrapper (atacom/atacom.py:10-71) resolved to arrays, plus the
+ * per-family constants the reference reads from its simulator / URDF. */
+typedef struct AtacomParams {
+  float K_f[ATACOM_MAX_F];     /* ViabilityConstraint.K of the equality rows   (constraints.py:26-29) */
+  float K_g[ATACOM_MAX_G];     /* ... of the inequality rows                                          */
+  float K_c[ATACOM_MAX_C];     /* error-correction gain                        (atacom.py:42-45)      */
+  float K_q[ATACOM_MAX_Q];     /* viability acceleration-bound gain            (atacom.py:65-69)      */
+  float vel_max[ATACOM_MAX_Q]; /* (atacom.py:53-57) */
+  float acc_max[ATACOM_MAX_Q]; /* (atacom.py:59-63) */
+  float dt;                    /* time_step                                    (atacom.py:28)         */
+  float rref_tol;              /* 0.05 in the wrapper                          (atacom.py:128)        */
+  int32_t variant;             /* ATACOM_VARIANT_*                                                    */
+  int32_t bias_mode;           /* ATACOM_BIAS_* for the Cartesian rows of planar / iiwa               */
+  int32_t clip_acc;            /* 1: apply acc_truncation (atacom.py:117-121)                         */
+  int32_t reserved;
+  float env[ATACOM_ENV_PARAMS]; /* planar: l1 l2 l3 base_x base_y qmax[3] half_len half_wid;
+                                   iiwa: base_x half_len half_wid height z4_min z7_min qmax[7];
+                                   point_reach: radius^2 K K_c                                         */
+} AtacomParams;
+
+const char* atacom_version(void);
+const char* atacom_error_string(int code);
+/* number of kernels this library has launched so far in this process (for benchmarks' bookkeeping) */
+int64_t atacom_launch_count(void);
+
+/* Fill `p` with the constructor defaults of the reference's env classes:
+ *  circle       CircleEnvAtacom            circle_atacom.py:8-18
+ *  planar       AirHockeyPlanarAtacom      atacom_air_hockey.py:28-43   (URDF constants unverified)
+ *  iiwa         AirHockeyIiwaAtacom        iiwa_hit_atacom.py:23-40, env_base.py:50,147-159, urdf/iiwa_1.urdf
+ *  point_reach  PointReachAtacom           collision_avoidance_atacom.py:9-16 */
+int atacom_circle_default_params(AtacomParams* p);
+int atacom_planar_default_params(AtacomParams* p);
+int atacom_iiwa_default_params(AtacomParams* p, int n_ctrl_joints /* 6 or 7 */);
+int atacom_point_reach_default_params(AtacomParams* p);
+
+/* ---- AtacomEnvWrapper.step_action_function (atacom.py:123-139) /
+ *      ErrorCorrectionEnvWrapper.step_action_function (error_correction_wrapper.py:117-134) ----
+ * q, dq: [B, n]; s_in, s_out: [B, G]; alpha: [B, k] (variant ATACOM; already scaled by alpha_max,
+ * atacom.py:107-108) or [B, n] (variant ERROR_CORRECTION); ddq: [B, n] clipped joint acceleration
+ * (the argument the reference hands to acc_to_ctrl_action, atacom.py:137-138).
+ *  circle: n=2 F=1 G=1 k=1     planar: n=3 F=0 G=6 k=3     iiwa: n=6|7 F=1 G=5+n k=n-1 */
+int atacom_circle_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq,
+                       float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                       void* stream);
+int atacom_planar_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq,
+                       float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                       void* stream);
+int atacom_iiwa_step(int n_ctrl_joints, const float* q, const float* dq, const float* s_in, const float* alpha,
+                     float* ddq, float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                     void* stream);
+
+/* ---- AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149): s = sqrt(max(-2 g~, 0)) ----
+ * mask (optional, may be NULL): uint8 [B]; only environments with mask != 0 are re-initialised. */
+int atacom_circle_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
+                             const AtacomParams* p, void* stream);
+int atacom_planar_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
+                             const AtacomParams* p, void* stream);
+int atacom_iiwa_slack_init(int n_ctrl_joints, const float* q, const float* dq, float* s, const uint8_t* mask,
+                           int64_t B, const AtacomParams* p, void* stream);
+
+/* ---- PointReachAtacom.step / reset (collision_avoidance_atacom.py:18-48) ----
+ * q, dq: [B, 2]; obs_p, obs_dp: [B, 2*n_objects]; s: [B, n_objects]; action: [B, 2] (unscaled,
+ * collision_avoidance_atacom.py:46); w: [B, 2] the projected action handed to PointGoalReach.step
+ * (before its clip and x10, collision_avoidance_base.py:44-45).  n_objects in {1,2,3,4,6,8}. */
+int atacom_point_reach_step(int n_objects, const float* q, const float* dq, const float* obs_p,
+                            const float* obs_dp, const float* s_in, const float* action, float* w,
+                            float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                            void* stream);
+int atacom_point_reach_slack_init(int n_objects, const float* q, const float* obs_p, float* s,
+                                  const uint8_t* mask, int64_t B, const AtacomParams* p, void* stream);
+
+/* ---- generic ConstraintsSet (atacom/constraints.py:46-82) ----
+ * For a user-defined ConstraintsSet whose callbacks were evaluated batched by the caller:
+ * c: [B, C] = fun(q) (origin), J: [B, C, n], b: [B, C] = b_state(q, dq); equality rows first.
+ * Supported (n, F, G): see atacom_generic_supported(). */
+int atacom_generic_supported(int n, int F, int G);
+int atacom_generic_step(int n, int F, int G, const float* c, const float* J, const float* b, const float* dq,
+                        const float* s_in, const float* alpha, float* ddq, float* s_out, uint8_t* status,
+                        float* w_dbg, int64_t B, const AtacomParams* p, void* stream);
+
+/* ---- host-buffer entry points (what a NumPy caller of the reference binds) ----
+ * Same semantics as atacom_iiwa_step but every array pointer is HOST memory (pinned memory makes
+ * the copies asynchronous).  The context owns the device staging buffers and streams; the batch is
+ * cut into `chunks` pieces whose H2D copy, kernel and D2H copy overlap. */
+typedef struct AtacomHostCtx AtacomHostCtx;
+int atacom_host_ctx_create(AtacomHostCtx** ctx, int64_t max_B, int chunks);
+int atacom_host_ctx_destroy(AtacomHostCtx* ctx);
+int atacom_iiwa_step_host(AtacomHostCtx* ctx, int n_ctrl_joints, const float* q, const float* dq,
+                          const float* s_in, const float* alpha, float* ddq, float* s_out, uint8_t* status,
+                          int64_t B, const AtacomParams* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATACOM_B200_H_ */

@@ -1,0 +1,622 @@
+// libatacom_b200.so — kernels and C ABI (include/atacom_b200.h).  sm_100a only.
+//
+// Mapping: one thread owns one environment; a block owns TPB consecutive environments, whose
+// rows of the AoS [B, dim] arrays form one contiguous slab per array.  Slabs move between HBM
+// and shared memory with coalesced 16-byte accesses; each thread then reads its row from shared
+// memory into registers, runs constraint evaluation (one FK pass) + projection, and writes its
+// results back through the same staging buffers.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <new>
+
+#include "../../include/atacom_b200.h"
+#include "atacom_envs.cuh"
+
+using namespace atacom;
+
+static_assert(sizeof(ParamsT<float>) == sizeof(AtacomParams), "ParamsT<float> must mirror AtacomParams");
+
+namespace {
+
+constexpr int TPB = 128;
+std::atomic<int64_t> g_launches{0};
+
+// ------------------------------------------------------------------ staging helpers
+template <int DIM>
+__device__ __forceinline__ void slab_load(const float* __restrict__ g, float* sm, int64_t env0, int nvalid) {
+  const float* src = g + env0 * DIM;
+  const int total = nvalid * DIM;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int nv = total >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(sm);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    for (int i = (nv << 2) + threadIdx.x; i < total; i += blockDim.x) sm[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = __ldg(src + i);
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void slab_store(float* __restrict__ g, const float* sm, int64_t env0, int nvalid) {
+  float* dst = g + env0 * DIM;
+  const int total = nvalid * DIM;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int nv = total >> 2;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* s4 = reinterpret_cast<const float4*>(sm);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) d4[i] = s4[i];
+    for (int i = (nv << 2) + threadIdx.x; i < total; i += blockDim.x) dst[i] = sm[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = sm[i];
+  }
+}
+
+template <int X> struct round4_t { static constexpr int value = (X + 3) & ~3; };
+
+struct StepArgs {
+  const float* q;
+  const float* dq;
+  const float* s_in;
+  const float* alpha;
+  float* ddq;
+  float* s_out;
+  uint8_t* status;
+  float* w_dbg;
+  int64_t B;
+};
+
+// ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
+template <class Env>
+__global__ void __launch_bounds__(TPB) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
+  using D = typename Env::D;
+  constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
+  constexpr int G1 = at_least_1<G>::value;
+  __shared__ __align__(16) float sq[round4_t<TPB * n>::value];
+  __shared__ __align__(16) float sdq[round4_t<TPB * n>::value];
+  __shared__ __align__(16) float ss[round4_t<TPB * G1>::value];
+  __shared__ __align__(16) float sa[round4_t<TPB * n>::value];
+
+  const int64_t env0 = static_cast<int64_t>(blockIdx.x) * TPB;
+  const int64_t left = a.B - env0;
+  const int nvalid = left < TPB ? static_cast<int>(left) : TPB;
+  const bool ec = P.variant == VARIANT_EC;
+
+  slab_load<n>(a.q, sq, env0, nvalid);
+  slab_load<n>(a.dq, sdq, env0, nvalid);
+  if (G > 0) slab_load<G1>(a.s_in, ss, env0, nvalid);
+  if (ec) slab_load<n>(a.alpha, sa, env0, nvalid);
+  else if (k > 0) slab_load<at_least_1<k>::value>(a.alpha, sa, env0, nvalid);
+  __syncthreads();
+
+  const int t = threadIdx.x;
+  if (t < nvalid) {
+    float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      q[j] = sq[t * n + j];
+      dq[j] = sdq[t * n + j];
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) s[i] = ss[t * G + i];
+    const int na = ec ? n : k;
+#pragma unroll
+    for (int j = 0; j < n; ++j) al[j] = j < na ? sa[t * na + j] : 0.f;
+
+    RawConstraints<float, D> R;
+    Env::template eval<float>(P, q, dq, R);
+    float* dbg = a.w_dbg ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
+    const uint8_t st = step_from_raw<float, D>(P, R, dq, s, al, ddq, so, dbg);
+    if (a.status) a.status[env0 + t] = st;
+#pragma unroll
+    for (int j = 0; j < n; ++j) sq[t * n + j] = ddq[j];
+#pragma unroll
+    for (int i = 0; i < G; ++i) ss[t * G + i] = so[i];
+  }
+  __syncthreads();
+  slab_store<n>(a.ddq, sq, env0, nvalid);
+  if (G > 0) slab_store<G1>(a.s_out, ss, env0, nvalid);
+}
+
+template <class Env>
+__global__ void __launch_bounds__(TPB) atacom_slack_init_kernel(const float* __restrict__ q,
+                                                                const float* __restrict__ dq, float* s,
+                                                                const uint8_t* __restrict__ mask, int64_t B,
+                                                                ParamsT<float> P) {
+  using D = typename Env::D;
+  constexpr int n = D::n, G = D::G;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  if (e >= B) return;
+  if (mask && !mask[e]) return;
+  float qq[n], dd[n], so[at_least_1<G>::value];
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    qq[j] = q[e * n + j];
+    dd[j] = dq[e * n + j];
+  }
+  RawConstraints<float, D> R;
+  Env::template eval<float>(P, qq, dd, R);
+  slack_from_raw<float, D>(P, R, dd, so);
+#pragma unroll
+  for (int i = 0; i < G; ++i) s[e * G + i] = so[i];
+}
+
+// ------------------------------------------------------------------ generic ConstraintsSet
+template <int n_, int F_, int G_>
+struct GenericDims { using D = Dims<n_, F_, G_>; };
+
+template <int n_, int F_, int G_>
+__global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __restrict__ c,
+                                                             const float* __restrict__ J,
+                                                             const float* __restrict__ b, StepArgs a,
+                                                             ParamsT<float> P) {
+  using D = Dims<n_, F_, G_>;
+  constexpr int n = D::n, G = D::G, k = D::k, C = D::C, N = D::N;
+  constexpr int G1 = at_least_1<G>::value;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  if (e >= a.B) return;
+  RawConstraints<float, D> R;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    R.c[i] = c[e * C + i];
+    R.b[i] = b[e * C + i];
+#pragma unroll
+    for (int j = 0; j < n; ++j) R.J[i][j] = J[(e * C + i) * n + j];
+  }
+  const bool ec = P.variant == VARIANT_EC;
+  const int na = ec ? n : k;
+  float dq[n], s[G1], al[n], ddq[n], so[G1];
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    dq[j] = a.dq[e * n + j];
+    al[j] = j < na ? a.alpha[e * na + j] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) s[i] = a.s_in[e * G + i];
+  float* dbg = a.w_dbg ? a.w_dbg + e * (2 * N) : nullptr;
+  const uint8_t st = step_from_raw<float, D>(P, R, dq, s, al, ddq, so, dbg);
+  if (a.status) a.status[e] = st;
+#pragma unroll
+  for (int j = 0; j < n; ++j) a.ddq[e * n + j] = ddq[j];
+#pragma unroll
+  for (int i = 0; i < G; ++i) a.s_out[e * G + i] = so[i];
+}
+
+// ------------------------------------------------------------------ PointReachAtacom.step
+struct PointArgs {
+  const float* q;
+  const float* dq;
+  const float* p;
+  const float* dp;
+  const float* s_in;
+  const float* action;
+  float* w;
+  float* s_out;
+  uint8_t* status;
+  float* w_dbg;
+  int64_t B;
+};
+
+template <int G_>
+__global__ void __launch_bounds__(TPB) point_reach_step_kernel(PointArgs a, ParamsT<float> P) {
+  using Env = PointReachEnv<G_>;
+  constexpr int G = G_, N = 2 + G_;
+  __shared__ __align__(16) float sq[round4_t<TPB * 2>::value];
+  __shared__ __align__(16) float sdq[round4_t<TPB * 2>::value];
+  __shared__ __align__(16) float sp[round4_t<TPB * 2 * G>::value];
+  __shared__ __align__(16) float sdp[round4_t<TPB * 2 * G>::value];
+  __shared__ __align__(16) float ss[round4_t<TPB * G>::value];
+  __shared__ __align__(16) float sa[round4_t<TPB * 2>::value];
+  const int64_t env0 = static_cast<int64_t>(blockIdx.x) * TPB;
+  const int64_t left = a.B - env0;
+  const int nvalid = left < TPB ? static_cast<int>(left) : TPB;
+  slab_load<2>(a.q, sq, env0, nvalid);
+  slab_load<2>(a.dq, sdq, env0, nvalid);
+  slab_load<2 * G>(a.p, sp, env0, nvalid);
+  slab_load<2 * G>(a.dp, sdp, env0, nvalid);
+  slab_load<G>(a.s_in, ss, env0, nvalid);
+  slab_load<2>(a.action, sa, env0, nvalid);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < nvalid) {
+    float q[2], dq[2], p[2 * G], dp[2 * G], s[G], act[2], w[2], so[G];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      q[j] = sq[t * 2 + j];
+      dq[j] = sdq[t * 2 + j];
+      act[j] = sa[t * 2 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * G; ++j) {
+      p[j] = sp[t * 2 * G + j];
+      dp[j] = sdp[t * 2 * G + j];
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) s[i] = ss[t * G + i];
+    float* dbg = a.w_dbg ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
+    const uint8_t st = Env::template step<float>(P, q, dq, p, dp, s, act, w, so, dbg);
+    if (a.status) a.status[env0 + t] = st;
+    sq[t * 2] = w[0];
+    sq[t * 2 + 1] = w[1];
+#pragma unroll
+    for (int i = 0; i < G; ++i) ss[t * G + i] = so[i];
+  }
+  __syncthreads();
+  slab_store<2>(a.w, sq, env0, nvalid);
+  slab_store<G>(a.s_out, ss, env0, nvalid);
+}
+
+template <int G_>
+__global__ void __launch_bounds__(TPB) point_reach_slack_init_kernel(const float* __restrict__ q,
+                                                                     const float* __restrict__ p, float* s,
+                                                                     const uint8_t* __restrict__ mask,
+                                                                     int64_t B, ParamsT<float> P) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  if (e >= B) return;
+  if (mask && !mask[e]) return;
+  float qq[2] = {q[e * 2], q[e * 2 + 1]}, pp[2 * G_], so[G_];
+#pragma unroll
+  for (int j = 0; j < 2 * G_; ++j) pp[j] = p[e * 2 * G_ + j];
+  PointReachEnv<G_>::template slack_init<float>(P, qq, pp, so);
+#pragma unroll
+  for (int i = 0; i < G_; ++i) s[e * G_ + i] = so[i];
+}
+
+// ------------------------------------------------------------------ host-side helpers
+inline const ParamsT<float>& as_params(const AtacomParams* p) {
+  return *reinterpret_cast<const ParamsT<float>*>(p);
+}
+
+inline int check_launch() {
+  const cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+}
+
+inline unsigned blocks_for(int64_t B) { return static_cast<unsigned>((B + TPB - 1) / TPB); }
+
+int check_common(int64_t B, const AtacomParams* p) {
+  if (!p) return ATACOM_ERR_NULL_POINTER;
+  if (B < 0 || B > (int64_t(1) << 31) * TPB) return ATACOM_ERR_BAD_DIMS;
+  if (p->variant != ATACOM_VARIANT_ATACOM && p->variant != ATACOM_VARIANT_ERROR_CORRECTION)
+    return ATACOM_ERR_BAD_PARAM;
+  if (!(p->rref_tol >= 0.f) || !(p->dt == p->dt)) return ATACOM_ERR_BAD_PARAM;
+  return ATACOM_OK;
+}
+
+template <class Env>
+int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
+                uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  using D = typename Env::D;
+  if (!q || !dq || !ddq || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
+  const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
+  if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
+  if (B == 0) return ATACOM_OK;
+  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B};
+  atacom_step_kernel<Env><<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(a, as_params(p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+template <class Env>
+int launch_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
+                      const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (!q || !dq || !s) return ATACOM_ERR_NULL_POINTER;
+  if (B == 0) return ATACOM_OK;
+  atacom_slack_init_kernel<Env><<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(q, dq, s, mask, B,
+                                                                                            as_params(p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+void fill_common(AtacomParams* p) {
+  for (size_t i = 0; i < sizeof(*p) / 4; ++i) reinterpret_cast<uint32_t*>(p)[i] = 0;
+  p->rref_tol = 0.05f;  // atacom.py:128
+  p->variant = ATACOM_VARIANT_ATACOM;
+  p->bias_mode = ATACOM_BIAS_JDOT_QDOT;
+  p->clip_acc = 1;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* atacom_version(void) { return "atacom_b200 0.1.0 (sm_100a)"; }
+
+const char* atacom_error_string(int code) {
+  switch (code) {
+    case ATACOM_OK: return "ok";
+    case ATACOM_ERR_NULL_POINTER: return "null pointer argument";
+    case ATACOM_ERR_BAD_DIMS: return "unsupported dimensions";
+    case ATACOM_ERR_BAD_PARAM: return "invalid AtacomParams field";
+    case ATACOM_ERR_CUDA: return "CUDA error";
+    case ATACOM_ERR_NO_DEVICE: return "no CUDA device";
+    case ATACOM_ERR_ALIGNMENT: return "pointer not 4-byte aligned";
+    default: return "unknown error";
+  }
+}
+
+int64_t atacom_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int atacom_circle_default_params(AtacomParams* p) {
+  if (!p) return ATACOM_ERR_NULL_POINTER;
+  fill_common(p);
+  p->K_f[0] = 0.1f;  // circle_atacom.py:10
+  p->K_g[0] = 2.f;   // circle_atacom.py:12
+  for (int i = 0; i < 2; ++i) {
+    p->K_c[i] = 100.f;  // circle_atacom.py:8 (Kc=100)
+    p->K_q[i] = 20.f;   // circle_atacom.py:18
+    p->vel_max[i] = 1.f;
+    p->acc_max[i] = 10.f;
+  }
+  p->dt = 0.01f;
+  return ATACOM_OK;
+}
+
+int atacom_planar_default_params(AtacomParams* p) {
+  if (!p) return ATACOM_ERR_NULL_POINTER;
+  fill_common(p);
+  const float vel[3] = {1.4835298641951802f, 1.4835298641951802f, 1.7453292519943295f};
+  const float qmax[3] = {2.9670597283903604f, 2.0943951023931953f, 2.0943951023931953f};
+  for (int i = 0; i < 3; ++i) {
+    p->K_g[i] = 0.5f;      // atacom_air_hockey.py:31
+    p->K_g[3 + i] = 1.f;   // atacom_air_hockey.py:33
+    p->acc_max[i] = 10.f;  // atacom_air_hockey.py:41
+    p->vel_max[i] = vel[i];
+    p->K_q[i] = 2.f * 10.f / vel[i];  // atacom_air_hockey.py:43
+    p->env[5 + i] = qmax[i];
+  }
+  for (int i = 0; i < 6; ++i) p->K_c[i] = 240.f;
+  p->dt = 1.f / 240.f;
+  p->env[0] = 0.55f;  // link lengths, base and table: recalled from mushroom-rl's planar URDF, unverified
+  p->env[1] = 0.44f;
+  p->env[2] = 0.44f;
+  p->env[3] = -1.51f;
+  p->env[4] = 0.f;
+  p->env[8] = 1.96f / 2 - 0.05f;
+  p->env[9] = 1.02f / 2 - 0.05f;
+  return ATACOM_OK;
+}
+
+int atacom_iiwa_default_params(AtacomParams* p, int n) {
+  if (!p) return ATACOM_ERR_NULL_POINTER;
+  if (n != 6 && n != 7) return ATACOM_ERR_BAD_DIMS;
+  fill_common(p);
+  const double vel[7] = {1.4835298641951802, 1.4835298641951802, 1.7453292519943295, 1.3089969389957472,
+                         2.2689280275926285, 2.356194490192345,  2.356194490192345};  // urdf/iiwa_1.urdf:74..297
+  const double qmax[7] = {2.9670597283903604, 2.0943951023931953, 2.9670597283903604, 2.0943951023931953,
+                          2.9670597283903604, 2.0943951023931953, 3.0543261909900763};
+  p->K_f[0] = 0.1f;  // iiwa_hit_atacom.py:26
+  for (int i = 0; i < 5; ++i) p->K_g[i] = 0.5f;      // :31
+  for (int i = 0; i < n; ++i) p->K_g[5 + i] = 1.f;   // :33
+  for (int i = 0; i < 6 + n; ++i) p->K_c[i] = 240.f;  // :13
+  for (int i = 0; i < n; ++i) {
+    p->acc_max[i] = 10.f;                               // :38
+    p->vel_max[i] = static_cast<float>(vel[i]);         // :39
+    p->K_q[i] = static_cast<float>(4.0 * 10.0 / vel[i]);  // :40
+  }
+  for (int i = 0; i < 7; ++i) p->env[6 + i] = static_cast<float>(qmax[i]);
+  p->dt = 1.f / 240.f;
+  p->env[0] = -1.51f;             // env_base.py:50
+  p->env[1] = 1.96f / 2 - 0.05f;  // env_base.py:156,158
+  p->env[2] = 1.02f / 2 - 0.05f;
+  p->env[3] = 0.1505f;            // env_base.py:159
+  p->env[4] = 0.36f;              // iiwa_hit_atacom.py:106
+  p->env[5] = 0.25f;              // iiwa_hit_atacom.py:107
+  return ATACOM_OK;
+}
+
+int atacom_point_reach_default_params(AtacomParams* p) {
+  if (!p) return ATACOM_ERR_NULL_POINTER;
+  fill_common(p);
+  p->clip_acc = 0;
+  p->dt = 0.01f;
+  // rref default tolerance max(m,n)*eps*||V||_inf (null_space_coordinate.py:48-49) restated for fp32
+  p->rref_tol = 8.f * 1.1920929e-07f * 2.5f;
+  p->env[0] = 0.36f;  // collision_avoidance_atacom.py:75
+  p->env[1] = 0.5f;   // :14
+  p->env[2] = 100.f;  // :13
+  return ATACOM_OK;
+}
+
+int atacom_circle_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq,
+                       float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                       void* stream) {
+  return launch_step<CircleEnv>(q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, p, stream);
+}
+
+int atacom_planar_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq,
+                       float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                       void* stream) {
+  return launch_step<PlanarEnv>(q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, p, stream);
+}
+
+int atacom_iiwa_step(int n, const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq,
+                     float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                     void* stream) {
+  if (n == 6) return launch_step<IiwaEnv<6>>(q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, p, stream);
+  if (n == 7) return launch_step<IiwaEnv<7>>(q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, p, stream);
+  return ATACOM_ERR_BAD_DIMS;
+}
+
+int atacom_circle_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
+                             const AtacomParams* p, void* stream) {
+  return launch_slack_init<CircleEnv>(q, dq, s, mask, B, p, stream);
+}
+
+int atacom_planar_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
+                             const AtacomParams* p, void* stream) {
+  return launch_slack_init<PlanarEnv>(q, dq, s, mask, B, p, stream);
+}
+
+int atacom_iiwa_slack_init(int n, const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
+                           const AtacomParams* p, void* stream) {
+  if (n == 6) return launch_slack_init<IiwaEnv<6>>(q, dq, s, mask, B, p, stream);
+  if (n == 7) return launch_slack_init<IiwaEnv<7>>(q, dq, s, mask, B, p, stream);
+  return ATACOM_ERR_BAD_DIMS;
+}
+
+#define ATACOM_POINT_DISPATCH(G_, CALL) \
+  case G_: CALL(G_); break;
+
+int atacom_point_reach_step(int n_objects, const float* q, const float* dq, const float* obs_p,
+                            const float* obs_dp, const float* s_in, const float* action, float* w,
+                            float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
+                            void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (!q || !dq || !obs_p || !obs_dp || !s_in || !action || !w || !s_out) return ATACOM_ERR_NULL_POINTER;
+  if (B == 0) return ATACOM_OK;
+  PointArgs a{q, dq, obs_p, obs_dp, s_in, action, w, s_out, status, w_dbg, B};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ATACOM_PR_STEP(G_) point_reach_step_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(a, as_params(p))
+  switch (n_objects) {
+    ATACOM_POINT_DISPATCH(1, ATACOM_PR_STEP)
+    ATACOM_POINT_DISPATCH(2, ATACOM_PR_STEP)
+    ATACOM_POINT_DISPATCH(3, ATACOM_PR_STEP)
+    ATACOM_POINT_DISPATCH(4, ATACOM_PR_STEP)
+    ATACOM_POINT_DISPATCH(6, ATACOM_PR_STEP)
+    ATACOM_POINT_DISPATCH(8, ATACOM_PR_STEP)
+    default: return ATACOM_ERR_BAD_DIMS;
+  }
+#undef ATACOM_PR_STEP
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+int atacom_point_reach_slack_init(int n_objects, const float* q, const float* obs_p, float* s,
+                                  const uint8_t* mask, int64_t B, const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (!q || !obs_p || !s) return ATACOM_ERR_NULL_POINTER;
+  if (B == 0) return ATACOM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ATACOM_PR_INIT(G_) \
+  point_reach_slack_init_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(q, obs_p, s, mask, B, as_params(p))
+  switch (n_objects) {
+    ATACOM_POINT_DISPATCH(1, ATACOM_PR_INIT)
+    ATACOM_POINT_DISPATCH(2, ATACOM_PR_INIT)
+    ATACOM_POINT_DISPATCH(3, ATACOM_PR_INIT)
+    ATACOM_POINT_DISPATCH(4, ATACOM_PR_INIT)
+    ATACOM_POINT_DISPATCH(6, ATACOM_PR_INIT)
+    ATACOM_POINT_DISPATCH(8, ATACOM_PR_INIT)
+    default: return ATACOM_ERR_BAD_DIMS;
+  }
+#undef ATACOM_PR_INIT
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+// generic ConstraintsSet: the (n, F, G) shapes compiled in
+#define ATACOM_GENERIC_SHAPES(X) \
+  X(2, 1, 1) X(3, 0, 6) X(6, 1, 11) X(7, 1, 12) X(2, 0, 4) X(4, 2, 3) X(3, 1, 0) X(2, 1, 2) X(3, 1, 3) X(4, 1, 4)
+
+int atacom_generic_supported(int n, int F, int G) {
+#define X(n_, F_, G_) if (n == n_ && F == F_ && G == G_) return 1;
+  ATACOM_GENERIC_SHAPES(X)
+#undef X
+  return 0;
+}
+
+int atacom_generic_step(int n, int F, int G, const float* c, const float* J, const float* b, const float* dq,
+                        const float* s_in, const float* alpha, float* ddq, float* s_out, uint8_t* status,
+                        float* w_dbg, int64_t B, const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (!atacom_generic_supported(n, F, G)) return ATACOM_ERR_BAD_DIMS;
+  if (!c || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
+  if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
+  if (B == 0) return ATACOM_OK;
+  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(n_, F_, G_)                                                                             \
+  if (n == n_ && F == F_ && G == G_)                                                              \
+    atacom_generic_kernel<n_, F_, G_><<<blocks_for(B), TPB, 0, st>>>(c, J, b, a, as_params(p));
+  ATACOM_GENERIC_SHAPES(X)
+#undef X
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+struct AtacomHostCtx {
+  int64_t max_B;
+  int chunks;
+  float *q, *dq, *s_in, *alpha, *ddq, *s_out;
+  uint8_t* status;
+  cudaStream_t streams[4];
+};
+
+int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
+  if (!out) return ATACOM_ERR_NULL_POINTER;
+  if (max_B <= 0 || chunks < 1 || chunks > 64) return ATACOM_ERR_BAD_DIMS;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ATACOM_ERR_NO_DEVICE;
+  AtacomHostCtx* c = new (std::nothrow) AtacomHostCtx();
+  if (!c) return ATACOM_ERR_CUDA;
+  c->max_B = max_B;
+  c->chunks = chunks;
+  const size_t q_bytes = sizeof(float) * ATACOM_MAX_Q * max_B, g_bytes = sizeof(float) * ATACOM_MAX_G * max_B;
+  bool ok = cudaMalloc(&c->q, q_bytes) == cudaSuccess && cudaMalloc(&c->dq, q_bytes) == cudaSuccess &&
+            cudaMalloc(&c->alpha, q_bytes) == cudaSuccess && cudaMalloc(&c->ddq, q_bytes) == cudaSuccess &&
+            cudaMalloc(&c->s_in, g_bytes) == cudaSuccess && cudaMalloc(&c->s_out, g_bytes) == cudaSuccess &&
+            cudaMalloc(&c->status, max_B) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    delete c;
+    return ATACOM_ERR_CUDA;
+  }
+  *out = c;
+  return ATACOM_OK;
+}
+
+int atacom_host_ctx_destroy(AtacomHostCtx* c) {
+  if (!c) return ATACOM_OK;
+  cudaFree(c->q); cudaFree(c->dq); cudaFree(c->alpha); cudaFree(c->ddq);
+  cudaFree(c->s_in); cudaFree(c->s_out); cudaFree(c->status);
+  for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->streams[i]);
+  delete c;
+  return ATACOM_OK;
+}
+
+int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* dq, const float* s_in,
+                          const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
+                          const AtacomParams* p) {
+  if (!c || !p || !q || !dq || !s_in || !alpha || !ddq || !s_out) return ATACOM_ERR_NULL_POINTER;
+  if (n != 6 && n != 7) return ATACOM_ERR_BAD_DIMS;
+  if (B < 0 || B > c->max_B) return ATACOM_ERR_BAD_DIMS;
+  if (B == 0) return ATACOM_OK;
+  const int G = 5 + n;
+  const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? n : n - 1;
+  // chunk boundaries are multiples of TPB so every chunk's slabs stay 16-byte aligned
+  int64_t per = (B + c->chunks - 1) / c->chunks;
+  per = (per + TPB - 1) / TPB * TPB;
+  int rc = ATACOM_OK;
+  int ci = 0;
+  for (int64_t e0 = 0; e0 < B && rc == ATACOM_OK; e0 += per, ++ci) {
+    const int64_t nb = (B - e0) < per ? (B - e0) : per;
+    cudaStream_t st = c->streams[ci & 3];
+    cudaMemcpyAsync(c->q + e0 * n, q + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->dq + e0 * n, dq + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->s_in + e0 * G, s_in + e0 * G, sizeof(float) * G * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->alpha + e0 * na, alpha + e0 * na, sizeof(float) * na * nb, cudaMemcpyHostToDevice, st);
+    rc = atacom_iiwa_step(n, c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
+                          c->ddq + e0 * n, c->s_out + e0 * G, status ? c->status + e0 : nullptr, nullptr, nb, p,
+                          st);
+    cudaMemcpyAsync(ddq + e0 * n, c->ddq + e0 * n, sizeof(float) * n * nb, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(s_out + e0 * G, c->s_out + e0 * G, sizeof(float) * G * nb, cudaMemcpyDeviceToHost, st);
+    if (status) cudaMemcpyAsync(status + e0, c->status + e0, nb, cudaMemcpyDeviceToHost, st);
+  }
+  for (int i = 0; i < 4; ++i)
+    if (cudaStreamSynchronize(c->streams[i]) != cudaSuccess) rc = ATACOM_ERR_CUDA;
+  if (rc == ATACOM_OK && cudaGetLastError() != cudaSuccess) rc = ATACOM_ERR_CUDA;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""Batched ATACOM projection step on CUDA tensors — thin typed layer over the C ABI.
+
+Every function takes contiguous float32 CUDA tensors shaped [B, dim] and launches
+one kernel of libatacom_b200.so on the current torch CUDA stream.  CPU tensors are
+rejected: there is no CPU fallback (the NumPy oracle lives in `oracle/` and is test
+infrastructure).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+FAMILY_DIMS = {
+    # family: (n, F, G)   reference: circle_atacom.py:9-18, atacom_air_hockey.py:28-43, iiwa_hit_atacom.py:23-40
+    "circle": (2, 1, 1),
+    "planar": (3, 0, 6),
+    "iiwa6": (6, 1, 11),
+    "iiwa7": (7, 1, 12),
+}
+
+
+def family_dims(family, n_ctrl_joints=None):
+    if family == "iiwa":
+        family = "iiwa%d" % (n_ctrl_joints or 6)
+    return FAMILY_DIMS[family]
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _check(t, name, B, dim, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    want = (B, dim) if dim is not None else (B,)
+    if tuple(t.shape) != want:
+        raise ValueError("%s: expected shape %s, got %s" % (name, want, tuple(t.shape)))
+
+
+def _stream(q):
+    return ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+
+
+def _alpha_dim(params, n, F):
+    return n if params.variant == _lib.VARIANT_ERROR_CORRECTION else n - F
+
+
+def step(family, q, dq, s, alpha, params, *, n_ctrl_joints=6, ddq=None, s_out=None, status=None, w_dbg=None):
+    """AtacomEnvWrapper.step_action_function for B environments (atacom.py:123-139).
+
+    Returns (ddq, s_out).  `s_out` may be `s` itself for the reference's in-place update."""
+    n, F, G = family_dims(family, n_ctrl_joints)
+    B = q.shape[0]
+    _check(q, "q", B, n)
+    _check(dq, "dq", B, n)
+    _check(s, "s", B, G)
+    _check(alpha, "alpha", B, _alpha_dim(params, n, F))
+    if ddq is None:
+        ddq = torch.empty_like(q)
+    if s_out is None:
+        s_out = torch.empty_like(s)
+    _check(ddq, "ddq", B, n)
+    _check(s_out, "s_out", B, G)
+    if status is not None:
+        _check(status, "status", B, None, torch.uint8)
+    if w_dbg is not None:
+        _check(w_dbg, "w_dbg", B, 2 * (n + G))
+    with torch.cuda.device(q.device):
+        common = (_ptr(q), _ptr(dq), _ptr(s), _ptr(alpha), _ptr(ddq), _ptr(s_out), _ptr(status), _ptr(w_dbg),
+                  B, ctypes.byref(params), _stream(q))
+        if family == "circle":
+            rc = _lib.lib.atacom_circle_step(*common)
+        elif family == "planar":
+            rc = _lib.lib.atacom_planar_step(*common)
+        elif family.startswith("iiwa"):
+            rc = _lib.lib.atacom_iiwa_step(n, *common)
+        else:
+            raise ValueError(family)
+    _lib.check(rc)
+    return ddq, s_out
+
+
+def slack_init(family, q, dq, params, *, n_ctrl_joints=6, s=None, mask=None):
+    """AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149)."""
+    n, F, G = family_dims(family, n_ctrl_joints)
+    B = q.shape[0]
+    _check(q, "q", B, n)
+    _check(dq, "dq", B, n)
+    if s is None:
+        s = torch.zeros(B, G, device=q.device, dtype=torch.float32)
+    _check(s, "s", B, G)
+    if mask is not None:
+        _check(mask, "mask", B, None, torch.uint8)
+    with torch.cuda.device(q.device):
+        common = (_ptr(q), _ptr(dq), _ptr(s), _ptr(mask), B, ctypes.byref(params), _stream(q))
+        if family == "circle":
+            rc = _lib.lib.atacom_circle_slack_init(*common)
+        elif family == "planar":
+            rc = _lib.lib.atacom_planar_slack_init(*common)
+        elif family.startswith("iiwa"):
+            rc = _lib.lib.atacom_iiwa_slack_init(n, *common)
+        else:
+            raise ValueError(family)
+    _lib.check(rc)
+    return s
+
+
+def point_reach_step(q, dq, obs_p, obs_dp, s, action, params, *, w=None, s_out=None, status=None, w_dbg=None):
+    """PointReachAtacom.step up to the base-env call (collision_avoidance_atacom.py:29-47)."""
+    B = q.shape[0]
+    G = s.shape[1]
+    _check(q, "q", B, 2)
+    _check(dq, "dq", B, 2)
+    _check(obs_p, "obs_p", B, 2 * G)
+    _check(obs_dp, "obs_dp", B, 2 * G)
+    _check(s, "s", B, G)
+    _check(action, "action", B, 2)
+    if w is None:
+        w = torch.empty_like(q)
+    if s_out is None:
+        s_out = torch.empty_like(s)
+    _check(w, "w", B, 2)
+    _check(s_out, "s_out", B, G)
+    if status is not None:
+        _check(status, "status", B, None, torch.uint8)
+    if w_dbg is not None:
+        _check(w_dbg, "w_dbg", B, 2 * (2 + G))
+    with torch.cuda.device(q.device):
+        rc = _lib.lib.atacom_point_reach_step(G, _ptr(q), _ptr(dq), _ptr(obs_p), _ptr(obs_dp), _ptr(s),
+                                              _ptr(action), _ptr(w), _ptr(s_out), _ptr(status), _ptr(w_dbg), B,
+                                              ctypes.byref(params), _stream(q))
+    _lib.check(rc)
+    return w, s_out
+
+
+def point_reach_slack_init(q, obs_p, params, *, s=None, mask=None):
+    """PointReachAtacom.reset slack (collision_avoidance_atacom.py:25)."""
+    B = q.shape[0]
+    G = obs_p.shape[1] // 2
+    _check(q, "q", B, 2)
+    _check(obs_p, "obs_p", B, 2 * G)
+    if s is None:
+        s = torch.zeros(B, G, device=q.device, dtype=torch.float32)
+    _check(s, "s", B, G)
+    if mask is not None:
+        _check(mask, "mask", B, None, torch.uint8)
+    with torch.cuda.device(q.device):
+        rc = _lib.lib.atacom_point_reach_slack_init(G, _ptr(q), _ptr(obs_p), _ptr(s), _ptr(mask), B,
+                                                    ctypes.byref(params), _stream(q))
+    _lib.check(rc)
+    return s
+
+
+def generic_supported(n, F, G):
+    return bool(_lib.lib.atacom_generic_supported(n, F, G))
+
+
+def generic_step(n, F, G, c, J, b, dq, s, alpha, params, *, ddq=None, s_out=None, status=None, w_dbg=None):
+    """Projection for a user-defined ConstraintsSet (constraints.py:46-82) whose callbacks were
+    evaluated batched: c [B,C] = fun(q), J [B,C,n], b [B,C] = b_state(q,dq); equality rows first."""
+    B = dq.shape[0]
+    C = F + G
+    _check(c, "c", B, C)
+    _check(b, "b", B, C)
+    if tuple(J.shape) != (B, C, n) or not J.is_contiguous() or not J.is_cuda or J.dtype != torch.float32:
+        raise ValueError("J must be a contiguous float32 CUDA tensor [B, C, n]")
+    _check(dq, "dq", B, n)
+    if G > 0:
+        _check(s, "s", B, G)
+    _check(alpha, "alpha", B, _alpha_dim(params, n, F))
+    if ddq is None:
+        ddq = torch.empty_like(dq)
+    if s_out is None:
+        s_out = torch.empty(B, G, device=dq.device, dtype=torch.float32)
+    if status is not None:
+        _check(status, "status", B, None, torch.uint8)
+    if w_dbg is not None:
+        _check(w_dbg, "w_dbg", B, 2 * (n + G))
+    with torch.cuda.device(dq.device):
+        rc = _lib.lib.atacom_generic_step(n, F, G, _ptr(c), _ptr(J), _ptr(b), _ptr(dq), _ptr(s) if G else None,
+                                          _ptr(alpha), _ptr(ddq), _ptr(s_out) if G else None, _ptr(status),
+                                          _ptr(w_dbg), B, ctypes.byref(params), _stream(dq))
+    _lib.check(rc)
+    return ddq, s_out
+
+
+class HostContext:
+    """Host-buffer entry point (`atacom_iiwa_step_host`): NumPy / pinned-tensor in, NumPy out,
+    copies inside the call — what a caller of the NumPy reference binds."""
+
+    def __init__(self, max_B, chunks=4):
+        self._ctx = ctypes.c_void_p()
+        _lib.check(_lib.lib.atacom_host_ctx_create(ctypes.byref(self._ctx), max_B, chunks))
+        self.max_B = max_B
+
+    def iiwa_step(self, n, q, dq, s, alpha, ddq, s_out, params, status=None):
+        B = q.shape[0]
+        ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() if hasattr(t, "data_ptr")
+                                                               else t.ctypes.data)
+        _lib.check(_lib.lib.atacom_iiwa_step_host(self._ctx, n, ptr(q), ptr(dq), ptr(s), ptr(alpha), ptr(ddq),
+                                                  ptr(s_out), ptr(status), B, ctypes.byref(params)))
+        return ddq, s_out
+
+    def close(self):
+        if self._ctx:
+            _lib.lib.atacom_host_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,144 @@
+// Host-side test harness: compiles the DEVICE algebra headers of the product
+// (rl_on_manifold_b200/csrc/*.cuh, all __host__ __device__) with g++ so the
+// `-m "not gpu"` tests can check the very same source against the NumPy oracle on
+// a box without a GPU.  Test infrastructure only: never linked into the product
+// library, never a fallback.
+#include <cstdint>
+#include "../../rl_on_manifold_b200/csrc/atacom_envs.cuh"
+
+using namespace atacom;
+
+template <typename T, int n, int F, int G>
+static void run_dense(int64_t B, const T* Af, const T* Ag, const T* s, const T* r, const T* alpha, T tol,
+                      T* w_mn, T* w_null, uint8_t* status) {
+  using D = Dims<n, F, G>;
+  for (int64_t b = 0; b < B; ++b) {
+    status[b] = project_dense<T, D>(Af + b * F * n, Ag + b * G * n, s + b * G, r + b * D::C,
+                                    alpha + b * D::k, tol, true, w_mn + b * D::N, w_null + b * D::N);
+  }
+}
+
+#define DISPATCH(T, FN)                                                                      \
+  if (n == 2 && F == 1 && G == 1) { FN<T, 2, 1, 1>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 3 && F == 0 && G == 6) { FN<T, 3, 0, 6>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 6 && F == 1 && G == 11) { FN<T, 6, 1, 11>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 7 && F == 1 && G == 12) { FN<T, 7, 1, 12>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 2 && F == 0 && G == 4) { FN<T, 2, 0, 4>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 4 && F == 2 && G == 3) { FN<T, 4, 2, 3>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 3 && F == 1 && G == 0) { FN<T, 3, 1, 0>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  return -1;
+
+extern "C" {
+int harness_dense_f32(int n, int F, int G, int64_t B, const float* Af, const float* Ag, const float* s,
+                      const float* r, const float* alpha, float tol, float* w_mn, float* w_null,
+                      uint8_t* status) {
+  DISPATCH(float, run_dense)
+}
+int harness_dense_f64(int n, int F, int G, int64_t B, const double* Af, const double* Ag, const double* s,
+                      const double* r, const double* alpha, double tol, double* w_mn, double* w_null,
+                      uint8_t* status) {
+  DISPATCH(double, run_dense)
+}
+}
+
+// ---- full step: env functor + viability terms + projection + slack integration + clipping
+// params: the ParamsT<T> fields flattened in declaration order with the four int32 fields as T.
+template <typename T>
+static ParamsT<T> unpack(const T* f) {
+  ParamsT<T> P;
+  const T* p = f;
+  for (int i = 0; i < 4; ++i) P.K_f[i] = *p++;
+  for (int i = 0; i < 16; ++i) P.K_g[i] = *p++;
+  for (int i = 0; i < 20; ++i) P.K_c[i] = *p++;
+  for (int i = 0; i < 8; ++i) P.K_q[i] = *p++;
+  for (int i = 0; i < 8; ++i) P.vel_max[i] = *p++;
+  for (int i = 0; i < 8; ++i) P.acc_max[i] = *p++;
+  P.dt = *p++;
+  P.rref_tol = *p++;
+  P.variant = (int32_t)*p++;
+  P.bias_mode = (int32_t)*p++;
+  P.clip_acc = (int32_t)*p++;
+  P.reserved = (int32_t)*p++;
+  for (int i = 0; i < 24; ++i) P.env[i] = *p++;
+  return P;
+}
+
+template <typename T, class Env>
+static void run_step(int64_t B, const T* params, const T* q, const T* dq, const T* s, const T* alpha, T* ddq,
+                     T* s_out, T* w_dbg, uint8_t* status, int init_only) {
+  using D = typename Env::D;
+  const ParamsT<T> P = unpack<T>(params);
+  const int na = P.variant == VARIANT_EC ? D::n : D::k;
+  for (int64_t b = 0; b < B; ++b) {
+    RawConstraints<T, D> R;
+    Env::template eval<T>(P, q + b * D::n, dq + b * D::n, R);
+    if (init_only) {
+      slack_from_raw<T, D>(P, R, dq + b * D::n, s_out + b * D::G);
+      continue;
+    }
+    T al[D::n];
+    for (int j = 0; j < D::n; ++j) al[j] = j < na ? alpha[b * na + j] : T(0);
+    status[b] = step_from_raw<T, D>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n, s_out + b * D::G,
+                                    w_dbg + b * 2 * D::N);
+  }
+}
+
+template <typename T>
+static int step_dispatch(int env, int64_t B, const T* params, const T* q, const T* dq, const T* s, const T* alpha,
+                         T* ddq, T* s_out, T* w_dbg, uint8_t* status, int init_only) {
+  switch (env) {
+    case 0: run_step<T, CircleEnv>(B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only); return 0;
+    case 1: run_step<T, PlanarEnv>(B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only); return 0;
+    case 2: run_step<T, IiwaEnv<6>>(B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only); return 0;
+    case 3: run_step<T, IiwaEnv<7>>(B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only); return 0;
+  }
+  return -1;
+}
+
+template <typename T, int G>
+static void run_point(int64_t B, const T* params, const T* q, const T* dq, const T* p, const T* dp, const T* s,
+                      const T* act, T* w, T* s_out, T* w_dbg, uint8_t* status, int init_only) {
+  const ParamsT<T> P = unpack<T>(params);
+  for (int64_t b = 0; b < B; ++b) {
+    if (init_only) {
+      PointReachEnv<G>::template slack_init<T>(P, q + 2 * b, p + 2 * G * b, s_out + G * b);
+      continue;
+    }
+    status[b] = PointReachEnv<G>::template step<T>(P, q + 2 * b, dq + 2 * b, p + 2 * G * b, dp + 2 * G * b,
+                                                  s + G * b, act + 2 * b, w + 2 * b, s_out + G * b,
+                                                  w_dbg + b * 2 * (2 + G));
+  }
+}
+
+template <typename T>
+static int point_dispatch(int G, int64_t B, const T* params, const T* q, const T* dq, const T* p, const T* dp,
+                          const T* s, const T* act, T* w, T* s_out, T* w_dbg, uint8_t* status, int init_only) {
+  switch (G) {
+    case 1: run_point<T, 1>(B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only); return 0;
+    case 2: run_point<T, 2>(B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only); return 0;
+    case 4: run_point<T, 4>(B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only); return 0;
+  }
+  return -1;
+}
+
+extern "C" {
+int harness_step_f32(int env, int64_t B, const float* params, const float* q, const float* dq, const float* s,
+                     const float* alpha, float* ddq, float* s_out, float* w_dbg, uint8_t* status, int init_only) {
+  return step_dispatch<float>(env, B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only);
+}
+int harness_step_f64(int env, int64_t B, const double* params, const double* q, const double* dq, const double* s,
+                     const double* alpha, double* ddq, double* s_out, double* w_dbg, uint8_t* status,
+                     int init_only) {
+  return step_dispatch<double>(env, B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only);
+}
+int harness_point_f32(int G, int64_t B, const float* params, const float* q, const float* dq, const float* p,
+                      const float* dp, const float* s, const float* act, float* w, float* s_out, float* w_dbg,
+                      uint8_t* status, int init_only) {
+  return point_dispatch<float>(G, B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only);
+}
+int harness_point_f64(int G, int64_t B, const double* params, const double* q, const double* dq, const double* p,
+                      const double* dp, const double* s, const double* act, double* w, double* s_out,
+                      double* w_dbg, uint8_t* status, int init_only) {
+  return point_dispatch<double>(G, B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only);
+}
+}
