@@ -9,6 +9,8 @@
  *
  * Conventions
  *  - all array pointers are caller-owned DEVICE memory, fp32, contiguous row-major [B, dim];
+ *    arithmetic: constraint values / kinematics in FP64 (the reference multiplies the residual
+ *    c + K J dq + s^2/2, a cancellation of O(1) terms, by K_c ~ 100-240), projection algebra in FP32;
  *    `*_host` entry points take HOST pointers instead and do the copies themselves;
  *  - `stream` is a cudaStream_t (NULL = default stream); calls are asynchronous on it; there is no
  *    global mutable state, so calls on different streams are independent;
@@ -70,9 +72,10 @@ typedef struct AtacomParams {
   int32_t bias_mode;           /* ATACOM_BIAS_* for the Cartesian rows of planar / iiwa               */
   int32_t clip_acc;            /* 1: apply acc_truncation (atacom.py:117-121)                         */
   int32_t reserved;
-  float env[ATACOM_ENV_PARAMS]; /* planar: l1 l2 l3 base_x base_y qmax[3] half_len half_wid;
-                                   iiwa: base_x half_len half_wid height z4_min z7_min qmax[7];
-                                   point_reach: radius^2 K K_c                                         */
+  double env[ATACOM_ENV_PARAMS]; /* geometry constants, double because K_c amplifies their rounding:
+                                    planar: l1 l2 l3 base_x base_y qmax[3] half_len half_wid;
+                                    iiwa: base_x half_len half_wid height z4_min z7_min qmax[7];
+                                    point_reach: radius^2 K K_c                                        */
 } AtacomParams;
 
 const char* atacom_version(void);

@@ -33,7 +33,7 @@ class AtacomParams(ctypes.Structure):
         ("bias_mode", ctypes.c_int32),
         ("clip_acc", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
-        ("env", ctypes.c_float * ENV_PARAMS),
+        ("env", ctypes.c_double * ENV_PARAMS),
     ]
 
     def copy(self):

@@ -5,6 +5,13 @@
 // equality rows first.  The reference evaluates J three times per step per constraint and
 // crosses into pinocchio ~30 times; here one forward-kinematics pass
 // serves all rows.
+//
+// Precision: two scalar types.  HP (double on the device) carries the geometry and everything
+// that enters the residual  c(q) + K J dq + s^2/2 : the reference multiplies that residual, a
+// cancellation of O(1) terms that is ~0 on the constraint manifold, by K_c = 100..240
+// (atacom.py:181), so fp32 rounding of any term shows up at 1e-4 in the output.  T (float on the
+// device) carries the Jacobian entries of Jc, the velocity-product terms b(q,dq) and the whole
+// projection algebra, where fp32 is backward stable to ~2e-6.
 #pragma once
 
 #include "atacom_core.cuh"
@@ -26,45 +33,67 @@ struct ParamsT {
   int32_t bias_mode;
   int32_t clip_acc;
   int32_t reserved;
-  T env[24];
+  double env[24];
 };
 
 enum { VARIANT_ATACOM = 0, VARIANT_EC = 1 };
 enum { BIAS_JDOT_QDOT = 0, BIAS_OMEGA_X_V = 1 };
 
-template <typename T, class D>
+template <typename T, typename HP, class D>
 struct RawConstraints {
   static constexpr int C1 = at_least_1<D::C>::value;
-  T c[C1];
-  T J[C1][D::n];
-  T b[C1];
+  HP c[C1];       // c(q)
+  HP Jdq[C1];     // J(q) dq
+  T J[C1][D::n];  // J(q)
+  T b[C1];        // b(q, dq)
 };
 
-template <typename T> ATACOM_HD void sincos_t(T x, T* s, T* c);
-template <> ATACOM_HD void sincos_t<float>(float x, float* s, float* c) {
-#if defined(__CUDA_ARCH__)
-  sincosf(x, s, c);
-#else
-  *s = ::sinf(x);
-  *c = ::cosf(x);
-#endif
-}
-template <> ATACOM_HD void sincos_t<double>(double x, double* s, double* c) {
-  *s = ::sin(x);
-  *c = ::cos(x);
+// sin and cos of a joint angle in double precision, ~1e-16 absolute: Cody-Waite reduction by
+// multiples of pi/2 and Taylor polynomials on [-pi/4, pi/4] (|x| < ~1e5; joint angles are < 3.1).
+// About 30 FP64 operations, a fraction of the library sincos(double).
+ATACOM_HD void sincos_hp(double x, double* sn, double* cs) {
+  const double kd = ::rint(x * 0.63661977236758134308);  // 2/pi
+  double r = ::fma(-kd, 1.57079632679489655800e+00, x);  // pi/2 high
+  r = ::fma(-kd, 6.12323399573676603587e-17, r);         // pi/2 low
+  const double r2 = r * r;
+  double ps = -7.64716373181981647590e-13;  // -1/15!
+  ps = ::fma(ps, r2, 1.60590438368216145994e-10);
+  ps = ::fma(ps, r2, -2.50521083854417187751e-08);
+  ps = ::fma(ps, r2, 2.75573192239858906526e-06);
+  ps = ::fma(ps, r2, -1.98412698412698412698e-04);
+  ps = ::fma(ps, r2, 8.33333333333333333333e-03);
+  ps = ::fma(ps, r2, -1.66666666666666666667e-01);
+  const double sr = ::fma(ps * r2, r, r);
+  double pc = 4.77947733238738529744e-14;  // 1/16!
+  pc = ::fma(pc, r2, -1.14707455977297247139e-11);
+  pc = ::fma(pc, r2, 2.08767569878680989792e-09);
+  pc = ::fma(pc, r2, -2.75573192239858906526e-07);
+  pc = ::fma(pc, r2, 2.48015873015873015873e-05);
+  pc = ::fma(pc, r2, -1.38888888888888888889e-03);
+  pc = ::fma(pc, r2, 4.16666666666666666667e-02);
+  pc = ::fma(pc, r2, -0.5);
+  const double cr = ::fma(pc, r2, 1.0);
+  const int k = static_cast<int>(kd) & 3;
+  const double s0 = (k & 1) ? cr : sr;
+  const double c0 = (k & 1) ? sr : cr;
+  *sn = (k & 2) ? -s0 : s0;
+  *cs = ((k + 1) & 2) ? -c0 : c0;
 }
 
 // ----------------------------------------------------------------------------- circle (env A / E)
 // circle_atacom.py:47-69: f = q0^2 + q1^2 - 1, g = -q1 - 0.5
 struct CircleEnv {
   using D = Dims<2, 1, 1>;
-  template <typename T>
-  static ATACOM_HD void eval(const ParamsT<T>&, const T* q, const T* dq, RawConstraints<T, D>& R) {
-    R.c[0] = q[0] * q[0] + q[1] * q[1] - T(1);
+  template <typename T, typename HP>
+  static ATACOM_HD void eval(const ParamsT<T>&, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
+    const HP q0 = q[0], q1 = q[1], d0 = dq[0], d1 = dq[1];
+    R.c[0] = q0 * q0 + q1 * q1 - HP(1);
+    R.Jdq[0] = HP(2) * (q0 * d0 + q1 * d1);
     R.J[0][0] = T(2) * q[0];
     R.J[0][1] = T(2) * q[1];
     R.b[0] = T(2) * dq[0] * dq[0] + T(2) * dq[1] * dq[1];
-    R.c[1] = -q[1] - T(0.5);
+    R.c[1] = -q1 - HP(0.5);
+    R.Jdq[1] = -d1;
     R.J[1][0] = T(0);
     R.J[1][1] = T(-1);
     R.b[1] = T(0);
@@ -75,53 +104,57 @@ struct CircleEnv {
 // atacom_air_hockey.py:78-107.  env[] = l1 l2 l3 base_x base_y qmax[3] half_len half_wid
 struct PlanarEnv {
   using D = Dims<3, 0, 6>;
-  template <typename T>
-  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, D>& R) {
-    T th = T(0), om = T(0);
-    T lc[3], ls[3], w[3];
+  template <typename T, typename HP>
+  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
+    HP th = HP(0), om = HP(0);
+    HP lc[3], ls[3], w[3];
     ATACOM_UNROLL
     for (int i = 0; i < 3; ++i) {
-      th += q[i];
-      om += dq[i];
-      T sn, cs;
-      sincos_t<T>(th, &sn, &cs);
-      lc[i] = P.env[i] * cs;
-      ls[i] = P.env[i] * sn;
+      th += HP(q[i]);
+      om += HP(dq[i]);
+      double sn, cs;
+      sincos_hp(static_cast<double>(th), &sn, &cs);
+      lc[i] = HP(P.env[i] * cs);
+      ls[i] = HP(P.env[i] * sn);
       w[i] = om;
     }
-    const T x = P.env[3] + lc[0] + lc[1] + lc[2];
-    const T y = P.env[4] + ls[0] + ls[1] + ls[2];
-    T Jx[3], Jy[3];
+    const HP x = HP(P.env[3]) + lc[0] + lc[1] + lc[2];
+    const HP y = HP(P.env[4]) + ls[0] + ls[1] + ls[2];
+    HP Jx[3], Jy[3];
     Jx[2] = -ls[2];
     Jy[2] = lc[2];
     Jx[1] = Jx[2] - ls[1];
     Jy[1] = Jy[2] + lc[1];
     Jx[0] = Jx[1] - ls[0];
     Jy[0] = Jy[1] + lc[0];
+    const HP vx = Jx[0] * HP(dq[0]) + Jx[1] * HP(dq[1]) + Jx[2] * HP(dq[2]);
+    const HP vy = Jy[0] * HP(dq[0]) + Jy[1] * HP(dq[1]) + Jy[2] * HP(dq[2]);
     T bx, by;
     if (P.bias_mode == BIAS_JDOT_QDOT) {
-      bx = -(lc[0] * w[0] * w[0] + lc[1] * w[1] * w[1] + lc[2] * w[2] * w[2]);
-      by = -(ls[0] * w[0] * w[0] + ls[1] * w[1] * w[1] + ls[2] * w[2] * w[2]);
+      bx = -T(lc[0] * w[0] * w[0] + lc[1] * w[1] * w[1] + lc[2] * w[2] * w[2]);
+      by = -T(ls[0] * w[0] * w[0] + ls[1] * w[1] * w[1] + ls[2] * w[2] * w[2]);
     } else {  // pinocchio classical acceleration with zero spatial acceleration: omega x v
-      const T vx = Jx[0] * dq[0] + Jx[1] * dq[1] + Jx[2] * dq[2];
-      const T vy = Jy[0] * dq[0] + Jy[1] * dq[1] + Jy[2] * dq[2];
-      bx = -om * vy;
-      by = om * vx;
+      bx = -T(om * vy);
+      by = T(om * vx);
     }
-    const T hl = P.env[8], hw = P.env[9];
+    const HP hl = HP(P.env[8]), hw = HP(P.env[9]);
     R.c[0] = -x - hl;
     R.c[1] = -y - hw;
     R.c[2] = y - hw;
+    R.Jdq[0] = -vx;
+    R.Jdq[1] = -vy;
+    R.Jdq[2] = vy;
     R.b[0] = -bx;
     R.b[1] = -by;
     R.b[2] = by;
     ATACOM_UNROLL
     for (int j = 0; j < 3; ++j) {
-      R.J[0][j] = -Jx[j];
-      R.J[1][j] = -Jy[j];
-      R.J[2][j] = Jy[j];
-      const T qm = P.env[5 + j];
-      R.c[3 + j] = q[j] * q[j] - qm * qm;
+      R.J[0][j] = -T(Jx[j]);
+      R.J[1][j] = -T(Jy[j]);
+      R.J[2][j] = T(Jy[j]);
+      const HP qm = HP(P.env[5 + j]), qj = q[j];
+      R.c[3 + j] = qj * qj - qm * qm;
+      R.Jdq[3 + j] = HP(2) * qj * HP(dq[j]);
       R.b[3 + j] = T(2) * dq[j] * dq[j];
       ATACOM_UNROLL
       for (int i = 0; i < 3; ++i) R.J[3 + j][i] = (i == j) ? T(2) * q[j] : T(0);
@@ -142,37 +175,37 @@ template <typename T> ATACOM_HD Vec3<T> cross(const Vec3<T>& a, const Vec3<T>& b
 template <typename T> ATACOM_HD Vec3<T> operator+(const Vec3<T>& a, const Vec3<T>& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 template <typename T> ATACOM_HD Vec3<T> operator-(const Vec3<T>& a, const Vec3<T>& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 template <typename T> ATACOM_HD Vec3<T> operator*(T s, const Vec3<T>& a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename T, typename U> ATACOM_HD Vec3<T> vcast(const Vec3<U>& a) { return {T(a.x), T(a.y), T(a.z)}; }
+template <typename T> ATACOM_HD T dot(const Vec3<T>& a, const Vec3<T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 template <int NJ>
 struct IiwaEnv {
   static_assert(NJ == 6 || NJ == 7, "iiwa: 6 (isolated joint 7) or 7 controlled joints");
   using D = Dims<NJ, 1, 5 + NJ>;
 
-  template <typename T>
-  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, D>& R) {
-    // joint placement in the parent frame: translation along z (kind 0) or along y (kind 1)
+  template <typename T, typename HP>
+  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
+    // joint placement in the parent frame: translation along z or along y
     constexpr double len[7] = {0.1575, 0.2025, 0.2045, 0.2155, 0.1845, 0.2155, 0.081};
     constexpr int along_y[7] = {0, 0, 1, 0, 1, 0, 1};
     constexpr int rot_kind[7] = {0, 1, 1, 2, 1, 2, 1};  // 0: I, 1: A, 2: Bm (see header comment)
     constexpr double tip_len = 0.585;                   // env_base.py:148-149
 
-    // frame axes as columns ex, ey, ez and origin o, all in the robot base frame
-    Vec3<T> ex{T(1), T(0), T(0)}, ey{T(0), T(1), T(0)}, ez{T(0), T(0), T(1)}, o{T(0), T(0), T(0)};
-    Vec3<T> zax[7], org[7];
+    // ---- geometry in HP: frame axes ex, ey, ez and origin o in the robot base frame
+    Vec3<HP> ex{HP(1), HP(0), HP(0)}, ey{HP(0), HP(1), HP(0)}, ez{HP(0), HP(0), HP(1)}, o{HP(0), HP(0), HP(0)};
+    Vec3<HP> zax[7], org[7];
     ATACOM_UNROLL
     for (int i = 0; i < 7; ++i) {
-      o = o + T(len[i]) * (along_y[i] ? ey : ez);
-      // R <- R * Rc: columns of the new frame expressed with the old ones
-      Vec3<T> nx, ny, nz;
+      o = o + HP(len[i]) * (along_y[i] ? ey : ez);
+      Vec3<HP> nx, ny, nz;  // R <- R * Rc
       if (rot_kind[i] == 0) { nx = ex; ny = ey; nz = ez; }
-      else if (rot_kind[i] == 1) { nx = T(-1) * ex; ny = ez; nz = ey; }
-      else { nx = ex; ny = ez; nz = T(-1) * ey; }
-      // R <- R * Rz(q_i)
-      if (i < NJ) {
-        T sn, cs;
-        sincos_t<T>(q[i], &sn, &cs);
-        ex = cs * nx + sn * ny;
-        ey = cs * ny - sn * nx;
+      else if (rot_kind[i] == 1) { nx = HP(-1) * ex; ny = ez; nz = ey; }
+      else { nx = ex; ny = ez; nz = HP(-1) * ey; }
+      if (i < NJ) {         // R <- R * Rz(q_i)
+        double sn, cs;
+        sincos_hp(static_cast<double>(q[i < NJ ? i : 0]), &sn, &cs);
+        ex = HP(cs) * nx + HP(sn) * ny;
+        ey = HP(cs) * ny - HP(sn) * nx;
       } else {
         ex = nx;
         ey = ny;
@@ -181,63 +214,64 @@ struct IiwaEnv {
       zax[i] = ez;
       org[i] = o;
     }
-    const Vec3<T> tip = o + T(tip_len) * ez;
+    const Vec3<HP> tip = o + HP(tip_len) * ez;
 
-    // velocity-product recursion (zero joint acceleration): angular velocity w, angular
-    // acceleration al, acceleration of each joint origin; sampled at link 4, link 7 and the tip
+    // world-aligned linear Jacobians, column j = z_j x (p - o_j); J dq accumulated in HP
+    Vec3<HP> vt{HP(0), HP(0), HP(0)}, v4 = vt, v7 = vt;
+    T Jt[3][NJ], J4z[NJ], J7z[NJ];
+    ATACOM_UNROLL
+    for (int j = 0; j < NJ; ++j) {
+      const HP dqj = dq[j];
+      const Vec3<HP> ct = cross(zax[j], tip - org[j]);
+      Jt[0][j] = T(ct.x); Jt[1][j] = T(ct.y); Jt[2][j] = T(ct.z);
+      vt = vt + dqj * ct;
+      Vec3<HP> c4{HP(0), HP(0), HP(0)}, c7 = c4;
+      if (j < 3) c4 = cross(zax[j], org[3] - org[j]);
+      if (j < 6) c7 = cross(zax[j], org[6] - org[j]);
+      J4z[j] = T(c4.z);
+      J7z[j] = T(c7.z);
+      v4 = v4 + dqj * c4;
+      v7 = v7 + dqj * c7;
+    }
+
+    // ---- velocity-product terms in T (not amplified by K_c): zero-joint-acceleration recursion
+    // for the acceleration of the link-4 / link-7 origins and the tip
     Vec3<T> w{T(0), T(0), T(0)}, al = w, ao = w, oprev = w;
     Vec3<T> acc4 = w, acc7 = w, w4 = w, w7 = w;
     ATACOM_UNROLL
     for (int i = 0; i < 7; ++i) {
-      const Vec3<T> rr = org[i] - oprev;
+      const Vec3<T> oi = vcast<T>(org[i]);
+      const Vec3<T> rr = oi - oprev;
       ao = ao + cross(al, rr) + cross(w, cross(w, rr));
       if (i == 3) { acc4 = ao; w4 = w; }
       if (i == 6) { acc7 = ao; w7 = w; }
       if (i < NJ) {
-        const Vec3<T> zq = dq[i] * zax[i];
+        const Vec3<T> zq = dq[i < NJ ? i : 0] * vcast<T>(zax[i]);
         al = al + cross(w, zq);
         w = w + zq;
       }
-      oprev = org[i];
+      oprev = oi;
     }
-    const Vec3<T> rt = tip - oprev;
+    const Vec3<T> rt = vcast<T>(tip) - oprev;
     Vec3<T> acct = ao + cross(al, rt) + cross(w, cross(w, rt));
-
-    // world-aligned linear Jacobians: column j = z_j x (p - o_j)
-    T Jt[3][NJ], J4z[NJ], J7z[NJ];
-    Vec3<T> vt{T(0), T(0), T(0)}, v4 = vt, v7 = vt;
-    ATACOM_UNROLL
-    for (int j = 0; j < NJ; ++j) {
-      const Vec3<T> ct = cross(zax[j], tip - org[j]);
-      Jt[0][j] = ct.x; Jt[1][j] = ct.y; Jt[2][j] = ct.z;
-      vt = vt + dq[j] * ct;
-      Vec3<T> c4{T(0), T(0), T(0)}, c7 = c4;
-      if (j < 3) c4 = cross(zax[j], org[3] - org[j]);
-      if (j < 6) c7 = cross(zax[j], org[6] - org[j]);
-      J4z[j] = c4.z;
-      J7z[j] = c7.z;
-      v4 = v4 + dq[j] * c4;
-      v7 = v7 + dq[j] * c7;
-    }
     if (P.bias_mode == BIAS_OMEGA_X_V) {
       // link-4 / link-7 frames are the child frames of joints 4 / 7: their angular velocity
       // includes that joint's own rate
-      const Vec3<T> w4f = w4 + dq[3] * zax[3];
-      const Vec3<T> w7f = (NJ == 7) ? w7 + dq[NJ == 7 ? 6 : 0] * zax[6] : w7;
-      acct = cross(w, vt);
-      acc4 = cross(w4f, v4);
-      acc7 = cross(w7f, v7);
+      const Vec3<T> w4f = w4 + dq[3] * vcast<T>(zax[3]);
+      const Vec3<T> w7f = (NJ == 7) ? w7 + dq[NJ == 7 ? 6 : 0] * vcast<T>(zax[6]) : w7;
+      acct = cross(w, vcast<T>(vt));
+      acc4 = cross(w4f, vcast<T>(v4));
+      acc7 = cross(w7f, vcast<T>(v7));
     }
 
-    const T xw = tip.x + P.env[0];
-    const T hl = P.env[1], hw = P.env[2];
-    R.c[0] = tip.z - P.env[3];
-    R.b[0] = acct.z;
-    R.c[1] = -xw - hl;      R.b[1] = -acct.x;
-    R.c[2] = -tip.y - hw;   R.b[2] = -acct.y;
-    R.c[3] = tip.y - hw;    R.b[3] = acct.y;
-    R.c[4] = P.env[4] - org[3].z;  R.b[4] = -acc4.z;
-    R.c[5] = P.env[5] - org[6].z;  R.b[5] = -acc7.z;
+    const HP xw = tip.x + HP(P.env[0]);
+    const HP hl = HP(P.env[1]), hw = HP(P.env[2]);
+    R.c[0] = tip.z - HP(P.env[3]);     R.Jdq[0] = vt.z;    R.b[0] = acct.z;
+    R.c[1] = -xw - hl;                 R.Jdq[1] = -vt.x;   R.b[1] = -acct.x;
+    R.c[2] = -tip.y - hw;              R.Jdq[2] = -vt.y;   R.b[2] = -acct.y;
+    R.c[3] = tip.y - hw;               R.Jdq[3] = vt.y;    R.b[3] = acct.y;
+    R.c[4] = HP(P.env[4]) - org[3].z;  R.Jdq[4] = -v4.z;   R.b[4] = -acc4.z;
+    R.c[5] = HP(P.env[5]) - org[6].z;  R.Jdq[5] = -v7.z;   R.b[5] = -acc7.z;
     ATACOM_UNROLL
     for (int j = 0; j < NJ; ++j) {
       R.J[0][j] = Jt[2][j];
@@ -246,8 +280,9 @@ struct IiwaEnv {
       R.J[3][j] = Jt[1][j];
       R.J[4][j] = -J4z[j];
       R.J[5][j] = -J7z[j];
-      const T qm = P.env[6 + j];
-      R.c[6 + j] = q[j] * q[j] - qm * qm;
+      const HP qm = HP(P.env[6 + j]), qj = q[j];
+      R.c[6 + j] = qj * qj - qm * qm;
+      R.Jdq[6 + j] = HP(2) * qj * HP(dq[j]);
       R.b[6 + j] = T(2) * dq[j] * dq[j];
       ATACOM_UNROLL
       for (int i = 0; i < NJ; ++i) R.J[6 + j][i] = (i == j) ? T(2) * q[j] : T(0);
@@ -258,8 +293,8 @@ struct IiwaEnv {
 // ----------------------------------------------------------------------------- shared tail
 // constraints.py:33-43 (fun / K_J / b), atacom.py:151-196 (Jc, psi, c), :130-137 (assembly,
 // slack integration, acceleration truncation); error_correction_wrapper.py:117-134 for VARIANT_EC.
-template <typename T, class D>
-ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, D>& R, const T* dq, const T* s,
+template <typename T, typename HP, class D>
+ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP, D>& R, const T* dq, const T* s,
                                 const T* alpha, T* ddq, T* s_out, T* w_dbg) {
   constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
   constexpr int C1 = at_least_1<C>::value;
@@ -268,16 +303,15 @@ ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, D>&
   ATACOM_UNROLL
   for (int i = 0; i < C; ++i) {
     const T K = i < F ? P.K_f[i < F ? i : 0] : P.K_g[i >= F ? i - F : 0];
-    T Jdq = T(0);
     ATACOM_UNROLL
-    for (int j = 0; j < n; ++j) {
-      Jdq += R.J[i][j] * dq[j];
-      A[i][j] = K * R.J[i][j];
+    for (int j = 0; j < n; ++j) A[i][j] = K * R.J[i][j];        // constraints.py:39-40
+    HP ct = R.c[i] + HP(K) * R.Jdq[i];                          // constraints.py:37
+    if (i >= F) {
+      const HP si = s[i >= F ? i - F : 0];
+      ct += HP(0.5) * si * si;                                  // atacom.py:195
     }
-    T ct = R.c[i] + K * Jdq;                                    // constraints.py:37
-    if (i >= F) ct += T(0.5) * s[i >= F ? i - F : 0] * s[i >= F ? i - F : 0];   // atacom.py:195
-    const T psi = Jdq + K * R.b[i];                             // constraints.py:43
-    r[i] = (ec ? T(0) : psi) + P.K_c[i] * ct;
+    const HP psi = R.Jdq[i] + HP(K) * HP(R.b[i]);               // constraints.py:43
+    r[i] = T((ec ? HP(0) : psi) + HP(P.K_c[i]) * ct);           // atacom.py:130,132,181
   }
   T w_mn[N], w_null[N];
   uint8_t st = project_dense<T, D>(&A[0][0], &A[F < C ? F : 0][0], s, r, alpha, P.rref_tol, !ec, w_mn, w_null);
@@ -322,17 +356,13 @@ ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, D>&
 }
 
 // atacom.py:145-149
-template <typename T, class D>
-ATACOM_HD void slack_from_raw(const ParamsT<T>& P, const RawConstraints<T, D>& R, const T* dq, T* s) {
-  constexpr int n = D::n, F = D::F, G = D::G;
+template <typename T, typename HP, class D>
+ATACOM_HD void slack_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP, D>& R, T* s) {
+  constexpr int F = D::F, G = D::G;
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) {
-    T Jdq = T(0);
-    ATACOM_UNROLL
-    for (int j = 0; j < n; ++j) Jdq += R.J[F + i][j] * dq[j];
-    const T ct = R.c[F + i] + P.K_g[i] * Jdq;
-    const T v = T(-2) * ct;
-    s[i] = v > T(0) ? num<T>::sqrt(v) : T(0);
+    const HP v = HP(-2) * (R.c[F + i] + HP(P.K_g[i]) * R.Jdq[F + i]);
+    s[i] = v > HP(0) ? T(::sqrt(static_cast<double>(v))) : T(0);
   }
 }
 
@@ -342,24 +372,26 @@ ATACOM_HD void slack_from_raw(const ParamsT<T>& P, const RawConstraints<T, D>& R
 template <int G_>
 struct PointReachEnv {
   using D = Dims<2, 0, G_>;
-  template <typename T>
+  template <typename T, typename HP>
   static ATACOM_HD uint8_t step(const ParamsT<T>& P, const T* q, const T* dq, const T* p, const T* dp,
                                 const T* s, const T* action, T* w_out, T* s_out, T* w_dbg) {
     constexpr int G = G_, N = 2 + G_;
-    const T rad2 = P.env[0], K = P.env[1], Kc = P.env[2];
+    const HP rad2 = HP(P.env[0]), K = HP(P.env[1]), Kc = HP(P.env[2]);
+    const HP qx = q[0], qy = q[1];
     T A[G][2], r[G];
     ATACOM_UNROLL
     for (int i = 0; i < G; ++i) {
-      const T px = p[2 * i], py = p[2 * i + 1];
-      const T dx = q[0] - px, dy = q[1] - py;
-      const T c_o = rad2 - (dx * dx + dy * dy);
-      A[i][0] = T(-2) * dx;
-      A[i][1] = T(-2) * dy;
-      const T dc = T(2) * (dx * dp[2 * i] + dy * dp[2 * i + 1]) + A[i][0] * dq[0] + A[i][1] * dq[1];
-      const T bp = (T(-2) * px + T(2) * q[0]) * px + (T(-2) * py + T(2) * q[1]) * py;
-      const T bq = (T(-2) * q[0] + T(2) * px) * q[0] + (T(-2) * q[1] + T(2) * py) * q[1];
-      const T c = c_o + T(0.5) * s[i] * s[i] + K * dc;
-      r[i] = dc + K * (bp + bq) + Kc * c;
+      const HP px = p[2 * i], py = p[2 * i + 1];
+      const HP dx = qx - px, dy = qy - py;
+      const HP c_o = rad2 - (dx * dx + dy * dy);
+      A[i][0] = T(HP(-2) * dx);
+      A[i][1] = T(HP(-2) * dy);
+      const HP dc = HP(2) * (dx * HP(dp[2 * i]) + dy * HP(dp[2 * i + 1])) - HP(2) * (dx * HP(dq[0]) + dy * HP(dq[1]));
+      const HP bp = (HP(-2) * px + HP(2) * qx) * px + (HP(-2) * py + HP(2) * qy) * py;
+      const HP bq = (HP(-2) * qx + HP(2) * px) * qx + (HP(-2) * qy + HP(2) * py) * qy;
+      const HP si = s[i];
+      const HP c = c_o + HP(0.5) * si * si + K * dc;
+      r[i] = T(dc + K * (bp + bq) + Kc * c);
     }
     T w_mn[N], w_null[N];
     uint8_t st = project_dense<T, D>((const T*)nullptr, &A[0][0], s, r, action, P.rref_tol, true, w_mn, w_null);
@@ -375,13 +407,13 @@ struct PointReachEnv {
     if (!finite) st |= ST_NONFINITE;
     return st;
   }
-  template <typename T>
+  template <typename T, typename HP>
   static ATACOM_HD void slack_init(const ParamsT<T>& P, const T* q, const T* p, T* s) {
     ATACOM_UNROLL
     for (int i = 0; i < G_; ++i) {
-      const T dx = q[0] - p[2 * i], dy = q[1] - p[2 * i + 1];
-      const T v = T(-2) * (P.env[0] - (dx * dx + dy * dy));
-      s[i] = v > T(0) ? num<T>::sqrt(v) : T(0);
+      const HP dx = HP(q[0]) - HP(p[2 * i]), dy = HP(q[1]) - HP(p[2 * i + 1]);
+      const HP v = HP(-2) * (HP(P.env[0]) - (dx * dx + dy * dy));
+      s[i] = v > HP(0) ? T(::sqrt(static_cast<double>(v))) : T(0);
     }
   }
 };

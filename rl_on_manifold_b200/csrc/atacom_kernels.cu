@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(TPB) atacom_step_kernel(StepArgs a, ParamsT<fl
 #pragma unroll
     for (int j = 0; j < n; ++j) al[j] = j < na ? sa[t * na + j] : 0.f;
 
-    RawConstraints<float, D> R;
-    Env::template eval<float>(P, q, dq, R);
+    RawConstraints<float, double, D> R;
+    Env::template eval<float, double>(P, q, dq, R);
     float* dbg = a.w_dbg ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
-    const uint8_t st = step_from_raw<float, D>(P, R, dq, s, al, ddq, so, dbg);
+    const uint8_t st = step_from_raw<float, double, D>(P, R, dq, s, al, ddq, so, dbg);
     if (a.status) a.status[env0 + t] = st;
 #pragma unroll
     for (int j = 0; j < n; ++j) sq[t * n + j] = ddq[j];
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(TPB) atacom_slack_init_kernel(const float* __r
     qq[j] = q[e * n + j];
     dd[j] = dq[e * n + j];
   }
-  RawConstraints<float, D> R;
-  Env::template eval<float>(P, qq, dd, R);
-  slack_from_raw<float, D>(P, R, dd, so);
+  RawConstraints<float, double, D> R;
+  Env::template eval<float, double>(P, qq, dd, R);
+  slack_from_raw<float, double, D>(P, R, so);
 #pragma unroll
   for (int i = 0; i < G; ++i) s[e * G + i] = so[i];
 }
@@ -156,14 +156,6 @@ __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __rest
   constexpr int G1 = at_least_1<G>::value;
   const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
   if (e >= a.B) return;
-  RawConstraints<float, D> R;
-#pragma unroll
-  for (int i = 0; i < C; ++i) {
-    R.c[i] = c[e * C + i];
-    R.b[i] = b[e * C + i];
-#pragma unroll
-    for (int j = 0; j < n; ++j) R.J[i][j] = J[(e * C + i) * n + j];
-  }
   const bool ec = P.variant == VARIANT_EC;
   const int na = ec ? n : k;
   float dq[n], s[G1], al[n], ddq[n], so[G1];
@@ -172,10 +164,23 @@ __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __rest
     dq[j] = a.dq[e * n + j];
     al[j] = j < na ? a.alpha[e * na + j] : 0.f;
   }
+  RawConstraints<float, double, D> R;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    R.c[i] = c[e * C + i];
+    R.b[i] = b[e * C + i];
+    double jdq = 0.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      R.J[i][j] = J[(e * C + i) * n + j];
+      jdq += static_cast<double>(R.J[i][j]) * static_cast<double>(dq[j]);
+    }
+    R.Jdq[i] = jdq;
+  }
 #pragma unroll
   for (int i = 0; i < G; ++i) s[i] = a.s_in[e * G + i];
   float* dbg = a.w_dbg ? a.w_dbg + e * (2 * N) : nullptr;
-  const uint8_t st = step_from_raw<float, D>(P, R, dq, s, al, ddq, so, dbg);
+  const uint8_t st = step_from_raw<float, double, D>(P, R, dq, s, al, ddq, so, dbg);
   if (a.status) a.status[e] = st;
 #pragma unroll
   for (int j = 0; j < n; ++j) a.ddq[e * n + j] = ddq[j];
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(TPB) point_reach_step_kernel(PointArgs a, Para
 #pragma unroll
     for (int i = 0; i < G; ++i) s[i] = ss[t * G + i];
     float* dbg = a.w_dbg ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
-    const uint8_t st = Env::template step<float>(P, q, dq, p, dp, s, act, w, so, dbg);
+    const uint8_t st = Env::template step<float, double>(P, q, dq, p, dp, s, act, w, so, dbg);
     if (a.status) a.status[env0 + t] = st;
     sq[t * 2] = w[0];
     sq[t * 2 + 1] = w[1];
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(TPB) point_reach_slack_init_kernel(const float
   float qq[2] = {q[e * 2], q[e * 2 + 1]}, pp[2 * G_], so[G_];
 #pragma unroll
   for (int j = 0; j < 2 * G_; ++j) pp[j] = p[e * 2 * G_ + j];
-  PointReachEnv<G_>::template slack_init<float>(P, qq, pp, so);
+  PointReachEnv<G_>::template slack_init<float, double>(P, qq, pp, so);
 #pragma unroll
   for (int i = 0; i < G_; ++i) s[e * G_ + i] = so[i];
 }
@@ -362,7 +367,7 @@ int atacom_planar_default_params(AtacomParams* p) {
   if (!p) return ATACOM_ERR_NULL_POINTER;
   fill_common(p);
   const float vel[3] = {1.4835298641951802f, 1.4835298641951802f, 1.7453292519943295f};
-  const float qmax[3] = {2.9670597283903604f, 2.0943951023931953f, 2.0943951023931953f};
+  const double qmax[3] = {2.9670597283903604, 2.0943951023931953, 2.0943951023931953};
   for (int i = 0; i < 3; ++i) {
     p->K_g[i] = 0.5f;      // atacom_air_hockey.py:31
     p->K_g[3 + i] = 1.f;   // atacom_air_hockey.py:33
@@ -373,13 +378,13 @@ int atacom_planar_default_params(AtacomParams* p) {
   }
   for (int i = 0; i < 6; ++i) p->K_c[i] = 240.f;
   p->dt = 1.f / 240.f;
-  p->env[0] = 0.55f;  // link lengths, base and table: recalled from mushroom-rl's planar URDF, unverified
-  p->env[1] = 0.44f;
-  p->env[2] = 0.44f;
-  p->env[3] = -1.51f;
-  p->env[4] = 0.f;
-  p->env[8] = 1.96f / 2 - 0.05f;
-  p->env[9] = 1.02f / 2 - 0.05f;
+  p->env[0] = 0.55;  // link lengths, base and table: recalled from mushroom-rl's planar URDF, unverified
+  p->env[1] = 0.44;
+  p->env[2] = 0.44;
+  p->env[3] = -1.51;
+  p->env[4] = 0.0;
+  p->env[8] = 1.96 / 2 - 0.05;
+  p->env[9] = 1.02 / 2 - 0.05;
   return ATACOM_OK;
 }
 
@@ -400,14 +405,14 @@ int atacom_iiwa_default_params(AtacomParams* p, int n) {
     p->vel_max[i] = static_cast<float>(vel[i]);         // :39
     p->K_q[i] = static_cast<float>(4.0 * 10.0 / vel[i]);  // :40
   }
-  for (int i = 0; i < 7; ++i) p->env[6 + i] = static_cast<float>(qmax[i]);
+  for (int i = 0; i < 7; ++i) p->env[6 + i] = qmax[i];
   p->dt = 1.f / 240.f;
-  p->env[0] = -1.51f;             // env_base.py:50
-  p->env[1] = 1.96f / 2 - 0.05f;  // env_base.py:156,158
-  p->env[2] = 1.02f / 2 - 0.05f;
-  p->env[3] = 0.1505f;            // env_base.py:159
-  p->env[4] = 0.36f;              // iiwa_hit_atacom.py:106
-  p->env[5] = 0.25f;              // iiwa_hit_atacom.py:107
+  p->env[0] = -1.51;              // env_base.py:50
+  p->env[1] = 1.96 / 2 - 0.05;    // env_base.py:156,158
+  p->env[2] = 1.02 / 2 - 0.05;
+  p->env[3] = 0.1505;             // env_base.py:159
+  p->env[4] = 0.36;               // iiwa_hit_atacom.py:106
+  p->env[5] = 0.25;               // iiwa_hit_atacom.py:107
   return ATACOM_OK;
 }
 
@@ -418,9 +423,9 @@ int atacom_point_reach_default_params(AtacomParams* p) {
   p->dt = 0.01f;
   // rref default tolerance max(m,n)*eps*||V||_inf (null_space_coordinate.py:48-49) restated for fp32
   p->rref_tol = 8.f * 1.1920929e-07f * 2.5f;
-  p->env[0] = 0.36f;  // collision_avoidance_atacom.py:75
-  p->env[1] = 0.5f;   // :14
-  p->env[2] = 100.f;  // :13
+  p->env[0] = 0.36;   // collision_avoidance_atacom.py:75
+  p->env[1] = 0.5;    // :14
+  p->env[2] = 100.0;  // :13
   return ATACOM_OK;
 }
 

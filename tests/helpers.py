@@ -35,7 +35,8 @@ def harness_step(lib, family, params_flat, q, dq, s, alpha, dtype=np.float32, in
     n, F, G = DIMS[family]
     B = q.shape[0]
     fn = lib.harness_step_f32 if dtype == np.float32 else lib.harness_step_f64
-    arrs = [np.ascontiguousarray(a, dtype=dtype) for a in (params_flat, q, dq, s, alpha)]
+    arrs = [np.ascontiguousarray(params_flat, dtype=np.float64)] + \
+        [np.ascontiguousarray(a, dtype=dtype) for a in (q, dq, s, alpha)]
     ddq = np.zeros((B, n), dtype)
     s_out = np.zeros((B, G), dtype)
     dbg = np.zeros((B, 2 * (n + G)), dtype)
@@ -61,7 +62,8 @@ def harness_dense(lib, n, F, G, Af, Ag, s, r, alpha, tol, dtype=np.float32):
 def harness_point(lib, G, params_flat, q, dq, p, dp, s, act, dtype=np.float32, init_only=False):
     B = q.shape[0]
     fn = lib.harness_point_f32 if dtype == np.float32 else lib.harness_point_f64
-    arrs = [np.ascontiguousarray(a, dtype=dtype) for a in (params_flat, q, dq, p, dp, s, act)]
+    arrs = [np.ascontiguousarray(params_flat, dtype=np.float64)] + \
+        [np.ascontiguousarray(a, dtype=dtype) for a in (q, dq, p, dp, s, act)]
     w, s_out, dbg, st = np.zeros((B, 2), dtype), np.zeros((B, G), dtype), np.zeros((B, 2 * (2 + G)), dtype), \
         np.zeros(B, np.uint8)
     rc = fn(G, ctypes.c_int64(B), *[_p(a) for a in arrs], _p(w), _p(s_out), _p(dbg), _p(st), int(init_only))
@@ -117,14 +119,16 @@ def oracle_batch(family, q, dq, s, alpha, basis="canonical", variant="atacom", b
     return out
 
 
-def rel_err(x, ref):
-    """Per-env max-norm error relative to max(1, max|ref|)."""
+def rel_err(x, ref, scale=None):
+    """Per-env max-norm error relative to max(1, max|ref|) — or to max(1, max|scale|) when the
+    compared quantity was clipped from a larger one (ddq is w[:n] clipped to +-acc_max)."""
     x, ref = np.asarray(x, np.float64), np.asarray(ref, np.float64)
     if x.ndim == 1:
         x, ref = x[:, None], ref[:, None]
     if x.shape[1] == 0:
         return np.zeros(x.shape[0])
-    return np.abs(x - ref).max(1) / np.maximum(1.0, np.abs(ref).max(1))
+    sc = np.abs(ref if scale is None else np.asarray(scale, np.float64)).max(1)
+    return np.abs(x - ref).max(1) / np.maximum(1.0, sc)
 
 
 def synthetic_cpu(family, B, seed):
@@ -138,3 +142,29 @@ def synthetic_cpu(family, B, seed):
                                 dq[i].double().numpy()) for i in range(B)]).astype(np.float32)
     s = synthetic.slack_mix(torch.from_numpy(s), seed).numpy()
     return q.numpy(), dq.numpy(), s, alpha.numpy()
+
+
+def exact_params_flat(family, params):
+    """`params.flat()` with every constant replaced by the oracle's float64 value, for the float64 host
+    build (the C struct stores fp32, e.g. 0.1f != 0.1)."""
+    spec = oracle_spec(family)
+    f = params.flat()
+    off = 0
+    for arr, size in ((spec.K_f, 4), (spec.K_g, 16), (spec.K_c, 20), (spec.K_q, 8), (spec.vel_max, 8),
+                      (spec.acc_max, 8)):
+        f[off:off + len(arr)] = list(arr)
+        off += size
+    f[off] = spec.dt
+    f[off + 1] = spec.tol
+    env0 = off + 6
+    if family.startswith("iiwa"):
+        env = [oenv.IIWA_BASE_X, oenv.TABLE_LENGTH / 2 - oenv.MALLET_RADIUS, oenv.TABLE_WIDTH / 2 - oenv.MALLET_RADIUS,
+               oenv.UNIVERSAL_HEIGHT, oenv.Z_LINK4_MIN, oenv.Z_LINK7_MIN] + list(oenv.IIWA_Q_MAX)
+    elif family == "planar":
+        d = oenv.PLANAR_DEFAULTS
+        env = list(d["links"]) + [d["base_x"], d["base_y"]] + list(d["q_max"]) + \
+            [d["table_length"] / 2 - d["mallet_radius"], d["table_width"] / 2 - d["mallet_radius"]]
+    else:
+        env = []
+    f[env0:env0 + len(env)] = env
+    return f

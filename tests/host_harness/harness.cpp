@@ -25,6 +25,7 @@ static void run_dense(int64_t B, const T* Af, const T* Ag, const T* s, const T* 
   if (n == 7 && F == 1 && G == 12) { FN<T, 7, 1, 12>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
   if (n == 2 && F == 0 && G == 4) { FN<T, 2, 0, 4>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
   if (n == 4 && F == 2 && G == 3) { FN<T, 4, 2, 3>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
+  if (n == 3 && F == 1 && G == 3) { FN<T, 3, 1, 3>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
   if (n == 3 && F == 1 && G == 0) { FN<T, 3, 1, 0>(B, Af, Ag, s, r, alpha, tol, w_mn, w_null, status); return 0; } \
   return -1;
 
@@ -44,17 +45,17 @@ int harness_dense_f64(int n, int F, int G, int64_t B, const double* Af, const do
 // ---- full step: env functor + viability terms + projection + slack integration + clipping
 // params: the ParamsT<T> fields flattened in declaration order with the four int32 fields as T.
 template <typename T>
-static ParamsT<T> unpack(const T* f) {
+static ParamsT<T> unpack(const double* f) {
   ParamsT<T> P;
-  const T* p = f;
-  for (int i = 0; i < 4; ++i) P.K_f[i] = *p++;
-  for (int i = 0; i < 16; ++i) P.K_g[i] = *p++;
-  for (int i = 0; i < 20; ++i) P.K_c[i] = *p++;
-  for (int i = 0; i < 8; ++i) P.K_q[i] = *p++;
-  for (int i = 0; i < 8; ++i) P.vel_max[i] = *p++;
-  for (int i = 0; i < 8; ++i) P.acc_max[i] = *p++;
-  P.dt = *p++;
-  P.rref_tol = *p++;
+  const double* p = f;
+  for (int i = 0; i < 4; ++i) P.K_f[i] = static_cast<T>(*p++);
+  for (int i = 0; i < 16; ++i) P.K_g[i] = static_cast<T>(*p++);
+  for (int i = 0; i < 20; ++i) P.K_c[i] = static_cast<T>(*p++);
+  for (int i = 0; i < 8; ++i) P.K_q[i] = static_cast<T>(*p++);
+  for (int i = 0; i < 8; ++i) P.vel_max[i] = static_cast<T>(*p++);
+  for (int i = 0; i < 8; ++i) P.acc_max[i] = static_cast<T>(*p++);
+  P.dt = static_cast<T>(*p++);
+  P.rref_tol = static_cast<T>(*p++);
   P.variant = (int32_t)*p++;
   P.bias_mode = (int32_t)*p++;
   P.clip_acc = (int32_t)*p++;
@@ -64,27 +65,27 @@ static ParamsT<T> unpack(const T* f) {
 }
 
 template <typename T, class Env>
-static void run_step(int64_t B, const T* params, const T* q, const T* dq, const T* s, const T* alpha, T* ddq,
+static void run_step(int64_t B, const double* params, const T* q, const T* dq, const T* s, const T* alpha, T* ddq,
                      T* s_out, T* w_dbg, uint8_t* status, int init_only) {
   using D = typename Env::D;
   const ParamsT<T> P = unpack<T>(params);
   const int na = P.variant == VARIANT_EC ? D::n : D::k;
   for (int64_t b = 0; b < B; ++b) {
-    RawConstraints<T, D> R;
-    Env::template eval<T>(P, q + b * D::n, dq + b * D::n, R);
+    RawConstraints<T, double, D> R;
+    Env::template eval<T, double>(P, q + b * D::n, dq + b * D::n, R);
     if (init_only) {
-      slack_from_raw<T, D>(P, R, dq + b * D::n, s_out + b * D::G);
+      slack_from_raw<T, double, D>(P, R, s_out + b * D::G);
       continue;
     }
     T al[D::n];
     for (int j = 0; j < D::n; ++j) al[j] = j < na ? alpha[b * na + j] : T(0);
-    status[b] = step_from_raw<T, D>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n, s_out + b * D::G,
+    status[b] = step_from_raw<T, double, D>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n, s_out + b * D::G,
                                     w_dbg + b * 2 * D::N);
   }
 }
 
 template <typename T>
-static int step_dispatch(int env, int64_t B, const T* params, const T* q, const T* dq, const T* s, const T* alpha,
+static int step_dispatch(int env, int64_t B, const double* params, const T* q, const T* dq, const T* s, const T* alpha,
                          T* ddq, T* s_out, T* w_dbg, uint8_t* status, int init_only) {
   switch (env) {
     case 0: run_step<T, CircleEnv>(B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only); return 0;
@@ -96,22 +97,22 @@ static int step_dispatch(int env, int64_t B, const T* params, const T* q, const 
 }
 
 template <typename T, int G>
-static void run_point(int64_t B, const T* params, const T* q, const T* dq, const T* p, const T* dp, const T* s,
+static void run_point(int64_t B, const double* params, const T* q, const T* dq, const T* p, const T* dp, const T* s,
                       const T* act, T* w, T* s_out, T* w_dbg, uint8_t* status, int init_only) {
   const ParamsT<T> P = unpack<T>(params);
   for (int64_t b = 0; b < B; ++b) {
     if (init_only) {
-      PointReachEnv<G>::template slack_init<T>(P, q + 2 * b, p + 2 * G * b, s_out + G * b);
+      PointReachEnv<G>::template slack_init<T, double>(P, q + 2 * b, p + 2 * G * b, s_out + G * b);
       continue;
     }
-    status[b] = PointReachEnv<G>::template step<T>(P, q + 2 * b, dq + 2 * b, p + 2 * G * b, dp + 2 * G * b,
+    status[b] = PointReachEnv<G>::template step<T, double>(P, q + 2 * b, dq + 2 * b, p + 2 * G * b, dp + 2 * G * b,
                                                   s + G * b, act + 2 * b, w + 2 * b, s_out + G * b,
                                                   w_dbg + b * 2 * (2 + G));
   }
 }
 
 template <typename T>
-static int point_dispatch(int G, int64_t B, const T* params, const T* q, const T* dq, const T* p, const T* dp,
+static int point_dispatch(int G, int64_t B, const double* params, const T* q, const T* dq, const T* p, const T* dp,
                           const T* s, const T* act, T* w, T* s_out, T* w_dbg, uint8_t* status, int init_only) {
   switch (G) {
     case 1: run_point<T, 1>(B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only); return 0;
@@ -122,7 +123,7 @@ static int point_dispatch(int G, int64_t B, const T* params, const T* q, const T
 }
 
 extern "C" {
-int harness_step_f32(int env, int64_t B, const float* params, const float* q, const float* dq, const float* s,
+int harness_step_f32(int env, int64_t B, const double* params, const float* q, const float* dq, const float* s,
                      const float* alpha, float* ddq, float* s_out, float* w_dbg, uint8_t* status, int init_only) {
   return step_dispatch<float>(env, B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only);
 }
@@ -131,7 +132,7 @@ int harness_step_f64(int env, int64_t B, const double* params, const double* q, 
                      int init_only) {
   return step_dispatch<double>(env, B, params, q, dq, s, alpha, ddq, s_out, w_dbg, status, init_only);
 }
-int harness_point_f32(int G, int64_t B, const float* params, const float* q, const float* dq, const float* p,
+int harness_point_f32(int G, int64_t B, const double* params, const float* q, const float* dq, const float* p,
                       const float* dp, const float* s, const float* act, float* w, float* s_out, float* w_dbg,
                       uint8_t* status, int init_only) {
   return point_dispatch<float>(G, B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only);

@@ -1,0 +1,259 @@
+"""Parity tests proper: the CUDA kernels, called through the C ABI (ctypes -> libatacom_b200.so),
+against the NumPy oracle on identical seeded inputs, the reference's golden vectors, and
+size-independent properties at BASELINE.json's full batch sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import atacom_oracle as ao
+from rl_on_manifold_b200 import _lib, projection, synthetic
+from tests import helpers
+from tests.test_host_core import TOL32, tol32
+from tests.test_oracle import GENERIC, generic_spec
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(family):
+    if family.startswith("iiwa"):
+        return _lib.default_params("iiwa", int(family[-1]))
+    return _lib.default_params(family)
+
+
+def _fam(family):
+    return ("iiwa", int(family[-1])) if family.startswith("iiwa") else (family, 6)
+
+
+def _run(family, q, dq, s, alpha, params, dev, dbg=True):
+    fam, nj = _fam(family)
+    t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (q, dq, s, alpha)]
+    B = q.shape[0]
+    n, F, G = helpers.DIMS[family]
+    status = torch.zeros(B, dtype=torch.uint8, device=dev)
+    w_dbg = torch.zeros(B, 2 * (n + G), device=dev) if dbg else None
+    ddq, s_out = projection.step(fam, *t, params, n_ctrl_joints=nj, status=status, w_dbg=w_dbg)
+    torch.cuda.synchronize()
+    return ddq.cpu().numpy(), s_out.cpu().numpy(), (w_dbg.cpu().numpy() if dbg else None), status.cpu().numpy()
+
+
+@pytest.mark.parametrize("family,B", [("circle", 4096), ("planar", 2048), ("iiwa6", 2048), ("iiwa7", 512)])
+def test_step_vs_oracle(cuda_device, family, B):
+    q, dq, s, alpha = helpers.synthetic_cpu(family, B, seed=1234)
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
+    ddq, s_out, dbg, st = _run(family, q, dq, s, alpha, _params(family), cuda_device)
+    N = ref["w"].shape[1]
+    ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
+    assert ok.mean() > 0.9
+    tol = tol32(ref["cond"])
+    errs = dict(w_mn=helpers.rel_err(dbg[:, :N], ref["w_mn"]), w_null=helpers.rel_err(dbg[:, N:], ref["w_null"]),
+                ddq=helpers.rel_err(ddq, ref["ddq"], ref["w"]), s=helpers.rel_err(s_out, ref["s_new"]))
+    for name, e in errs.items():
+        assert (e < tol)[ok].all(), "%s: max %g" % (name, e[ok].max())
+        assert (e[ok] < TOL32).mean() > 0.95, name
+    assert ((st & _lib.ST_NONFINITE) == 0).all()
+    dropped = (st & _lib.ST_COLUMN_DROPPED) != 0
+    assert (dropped[ok] >= ref["fired"][ok]).all()
+    print("\n[%s] B=%d parity domain %d, tolerance-branch fired in %d; max rel err ddq %.2e s %.2e; "
+          "share under 1e-5: %.4f" % (family, B, ok.sum(), ref["fired"][ok].sum(), errs["ddq"][ok].max(),
+                                      errs["s"][ok].max(), (errs["ddq"][ok] < TOL32).mean()))
+
+
+@pytest.mark.parametrize("family", ["circle", "planar", "iiwa6"])
+def test_stratum_one_equals_reference_svd_basis(cuda_device, family):
+    q, dq, s, alpha = helpers.synthetic_cpu(family, 512, seed=99)
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="svd")
+    can = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
+    ddq, s_out, _, _ = _run(family, q, dq, s, alpha, _params(family), cuda_device, dbg=False)
+    stratum1 = ~ref["fired"] & ~can["fired"] & ~ref["rank_def"]
+    assert stratum1.mean() > 0.5
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[stratum1].all()
+    assert (helpers.rel_err(s_out, ref["s_new"]) < tol32(ref["cond"]))[stratum1].all()
+
+
+@pytest.mark.parametrize("family", ["circle", "iiwa6"])
+def test_error_correction_variant(cuda_device, family):
+    q, dq, s, _ = helpers.synthetic_cpu(family, 512, seed=7)
+    alpha = np.random.default_rng(0).uniform(-10, 10, q.shape).astype(np.float32)
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, variant="ec")
+    p = _params(family)
+    p.variant = _lib.VARIANT_ERROR_CORRECTION
+    ddq, s_out, _, _ = _run(family, q, dq, s, alpha, p, cuda_device, dbg=False)
+    ok = ~ref["rank_def"]
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
+    assert (helpers.rel_err(s_out, ref["s_new"]) < tol32(ref["cond"]))[ok].all()
+
+
+@pytest.mark.parametrize("family", ["planar", "iiwa6"])
+def test_bias_mode_omega_cross_v(cuda_device, family):
+    q, dq, s, alpha = helpers.synthetic_cpu(family, 256, seed=3)
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, bias="omega_x_v")
+    p = _params(family)
+    p.bias_mode = _lib.BIAS_OMEGA_X_V
+    ddq, s_out, _, _ = _run(family, q, dq, s, alpha, p, cuda_device, dbg=False)
+    ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
+
+
+@pytest.mark.parametrize("family", ["circle", "planar", "iiwa6", "iiwa7"])
+def test_slack_init_vs_oracle(cuda_device, family):
+    fam, nj = _fam(family)
+    q, dq, _ = synthetic.state_batch(fam, 1000, 5, nj)
+    spec = helpers.oracle_spec(family)
+    ref = np.stack([ao.slack_init(spec, helpers.oracle_eval(family, q[i].double().numpy(), dq[i].double().numpy()),
+                                  dq[i].double().numpy()) for i in range(q.shape[0])])
+    s = projection.slack_init(fam, q.to(cuda_device), dq.to(cuda_device), _params(family), n_ctrl_joints=nj)
+    np.testing.assert_allclose(s.cpu().numpy(), ref, rtol=2e-6, atol=1e-7)
+    # masked re-initialisation leaves unmasked rows untouched
+    mask = (torch.arange(1000, device=cuda_device) % 3 == 0).to(torch.uint8)
+    s2 = torch.full_like(s, -1.0)
+    projection.slack_init(fam, q.to(cuda_device), dq.to(cuda_device), _params(family), n_ctrl_joints=nj, s=s2, mask=mask)
+    m = mask.bool().cpu().numpy()
+    np.testing.assert_array_equal(s2.cpu().numpy()[m], s.cpu().numpy()[m])
+    assert (s2.cpu().numpy()[~m] == -1.0).all()
+
+
+def test_circle_reference_trajectory_golden(cuda_device, golden):
+    """One-step parity along the 500-step CircleEnvAtacom trajectory recorded from the reference,
+    including the start state where the tolerance branch drops column 0 (Nc = [0,1,2])."""
+    spec = helpers.oracle_spec("circle")
+    acts, states, s_ref = golden["circleA_actions"], golden["circleA_states"], golden["circleA_s"]
+    alpha = np.clip(acts, -1, 1) * spec.alpha_max
+    q, dq = states[:-1, :2], states[:-1, 2:]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    ddq, s_out, dbg, st = _run("circle", f32(q), f32(dq), f32(s_ref[:-1]), f32(alpha), _params("circle"), cuda_device)
+    # inputs are rounded to fp32 here, so compare against the oracle on the rounded inputs ...
+    ref = helpers.oracle_batch("circle", f32(q), f32(dq), f32(s_ref[:-1]), f32(alpha), basis="svd")
+    ok = ref["margin"] > 1e-3
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
+    # ... and against the float64 trajectory itself at the accuracy of the fp32 rounding of its inputs
+    assert np.abs(dbg[0, 3:] - golden["circleA_act_b"][0]).max() < 1e-5          # [0, 7, 14]
+    assert np.median(np.abs(s_out - s_ref[1:])) < 1e-6
+
+
+def test_circle_single_projection_golden(cuda_device, golden):
+    g = {k: np.ascontiguousarray(golden["circleP_" + k], dtype=np.float32) for k in ("q", "dq", "s", "alpha")}
+    ddq, s_out, _, st = _run("circle", g["q"], g["dq"], g["s"], g["alpha"], _params("circle"), cuda_device, dbg=False)
+    ref = helpers.oracle_batch("circle", g["q"], g["dq"], g["s"], g["alpha"], basis="svd")
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"])).all()
+    # the recorded fp64 outputs (u = ddq / acc_max) at fp32-input accuracy
+    assert np.median(np.abs(ddq / 10.0 - golden["circleP_u"])) < 1e-5
+    assert (s_out[golden["circleP_s"][:, 0] == 0.0] != 0).all()      # active constraint (s = 0) handled
+
+
+@pytest.mark.parametrize("tag", GENERIC)
+def test_generic_constraint_set_golden(cuda_device, golden, tag):
+    spec = generic_spec(golden[tag + "_meta"])
+    n, F, G = spec.n, spec.F, spec.G
+    assert projection.generic_supported(n, F, G)
+    p = _lib.AtacomParams()
+    p.K_f[:F] = list(spec.K_f); p.K_g[:G] = list(spec.K_g); p.K_c[:F + G] = list(spec.K_c)
+    p.K_q[:n] = list(spec.K_q); p.vel_max[:n] = list(spec.vel_max); p.acc_max[:n] = list(spec.acc_max)
+    p.dt, p.rref_tol, p.clip_acc = spec.dt, 0.05, 1
+    dev = cuda_device
+    t = {k: torch.from_numpy(np.ascontiguousarray(golden["%s_%s" % (tag, k)], dtype=np.float32)).to(dev)
+         for k in ("c", "J", "b", "dq", "s", "alpha")}
+    B = t["c"].shape[0]
+    w_dbg = torch.zeros(B, 2 * (n + G), device=dev)
+    ddq, s_out = projection.generic_step(n, F, G, t["c"], t["J"], t["b"], t["dq"], t["s"], t["alpha"], p, w_dbg=w_dbg)
+    torch.cuda.synchronize()
+    N = n + G
+    ref_mn = golden[tag + "_act_a"] + golden[tag + "_act_err"]
+    # inputs and gains were rounded to fp32 on the way in: 5e-5 covers K_c * eps32 on the O(1) residual
+    assert helpers.rel_err(w_dbg[:, :N].cpu().numpy(), ref_mn).max() < 5e-5
+    fired = []
+    for i in range(B):
+        g = {k: golden["%s_%s" % (tag, k)][i] for k in ("c", "J", "b", "dq", "s", "alpha")}
+        ev = ao.ConstraintEval(c_f=g["c"][:F], J_f=g["J"][:F], b_f=g["b"][:F], c_g=g["c"][F:], J_g=g["J"][F:],
+                               b_g=g["b"][F:])
+        tr = [ao.atacom_step(spec, ev, g["dq"], g["s"], g["alpha"], basis=bs)["trace"] for bs in ("svd", "canonical")]
+        fired.append(any(pv > 1e-9 for t_ in tr for (_, _, pv) in t_["dropped"]))
+    keep = ~np.array(fired)
+    assert helpers.rel_err(w_dbg[:, N:].cpu().numpy()[keep], golden[tag + "_act_b"][keep]).max() < 5e-5
+    assert helpers.rel_err(ddq.cpu().numpy()[keep], golden[tag + "_ddq"][keep]).max() < 5e-5
+
+
+def test_point_reach_golden_and_oracle(cuda_device, golden):
+    dev = cuda_device
+    p = _lib.default_params("point_reach")
+    pre, acts, s_ref, u_ref = (golden["collC_" + k] for k in ("pre", "actions", "s", "u"))
+    T = len(acts)
+    ob = pre[:, 4:].reshape(T, 4, 4)
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    q, dq, P, DP = f(pre[:, :2]), f(pre[:, 2:4]), f(ob[:, :, :2].reshape(T, 8)), f(ob[:, :, 2:].reshape(T, 8))
+    w, s_out = projection.point_reach_step(q, dq, P, DP, f(s_ref[:-1]), f(acts), p)
+    u = np.clip(w.cpu().numpy(), -1, 1) * 10
+    assert helpers.rel_err(s_out.cpu().numpy(), s_ref[1:]).max() < TOL32
+    assert helpers.rel_err(u, u_ref).max() < 1e-4
+    s0 = projection.point_reach_slack_init(q[:1], P[:1], p)
+    np.testing.assert_allclose(s0.cpu().numpy()[0], s_ref[0], rtol=1e-6)
+
+
+# ------------------------------------------------------------------ full-size properties
+
+@pytest.mark.parametrize("family,B", [("planar", 16384), ("iiwa6", 65536), ("iiwa7", 65536)])
+def test_full_batch_properties(cuda_device, family, B):
+    """BASELINE.json batch sizes: constraint-space identities that hold for every environment
+    (Jc w_mn = -r cannot be checked without r, so use the null-space identity and batch invariance):
+      * Jc (Nc alpha) = 0 wherever no column was dropped,
+      * a ragged sub-batch gives bit-identical results to the same environments inside the full batch,
+      * in-place slack update == out-of-place, and repeated launches are bit-identical."""
+    dev = cuda_device
+    fam, nj = _fam(family)
+    params = _params(family)
+    n, F, G = helpers.DIMS[family]
+    q, dq, s, alpha = synthetic.device_batch(fam, B, 4321, dev, nj, params)
+    status = torch.zeros(B, dtype=torch.uint8, device=dev)
+    w_dbg = torch.zeros(B, 2 * (n + G), device=dev)
+    ddq, s_out = projection.step(fam, q, dq, s, alpha, params, n_ctrl_joints=nj, status=status, w_dbg=w_dbg)
+    ddq2, s_out2 = projection.step(fam, q, dq, s, alpha, params, n_ctrl_joints=nj)
+    assert torch.equal(ddq, ddq2) and torch.equal(s_out, s_out2)
+    s_inplace = s.clone()
+    projection.step(fam, q, dq, s_inplace, alpha, params, n_ctrl_joints=nj, s_out=s_inplace)
+    assert torch.equal(s_inplace, s_out)
+    lo, hi = 777, 777 + 1001                                    # ragged, unaligned slice
+    sl = [t[lo:hi].contiguous() for t in (q, dq, s, alpha)]
+    ddq_s, s_s = projection.step(fam, *sl, params, n_ctrl_joints=nj)
+    assert torch.equal(ddq_s, ddq[lo:hi]) and torch.equal(s_s, s_out[lo:hi])
+    assert torch.isfinite(ddq).all() and torch.isfinite(s_out).all()
+    # acceleration limits hold (atacom.py:117-121)
+    am = torch.tensor(list(params.acc_max[:n]), device=dev)
+    assert (ddq.abs() <= am + 1e-6).all()
+    # null-space identity on environments without dropped columns: A_g x + s z = 0 cannot be formed
+    # without A; use the slack rows of joint-limit constraints, whose Jacobian is 2 K q_j e_j
+    clean = (status & (_lib.ST_COLUMN_DROPPED | _lib.ST_RANK_DEFICIENT)) == 0
+    N = n + G
+    wn = w_dbg[:, N:]
+    j0 = G - n                                                   # first joint-limit row
+    lhs = 2.0 * q * wn[:, :n] + s[:, j0:] * wn[:, n + j0:]
+    scale = 1.0 + wn.abs().max(1).values
+    assert ((lhs.abs().max(1).values / scale)[clean] < 2e-4).all()
+    print("\n[%s] B=%d: dropped %.3f, slack pivot %.3f, rank-deficient %.5f" % (
+        family, B, ((status & 2) != 0).float().mean(), ((status & 4) != 0).float().mean(),
+        ((status & 1) != 0).float().mean()))
+
+
+def test_empty_and_tiny_batches(cuda_device):
+    dev = cuda_device
+    p = _lib.default_params("iiwa", 6)
+    z = lambda d: torch.zeros(0, d, device=dev)
+    ddq, s_out = projection.step("iiwa", z(6), z(6), z(11), z(5), p)
+    assert ddq.shape == (0, 6) and s_out.shape == (0, 11)
+    for B in (1, 2, 127, 129):
+        q, dq, s, alpha = synthetic.device_batch("iiwa", B, 11, dev, 6, p)
+        ddq, s_out = projection.step("iiwa", q, dq, s, alpha, p)
+        q2, dq2, s2, a2 = synthetic.device_batch("iiwa", 129, 11, dev, 6, p)
+        assert torch.isfinite(ddq).all()
+
+
+def test_host_buffer_entry_point(cuda_device):
+    p = _lib.default_params("iiwa", 6)
+    B = 5000
+    q, dq, s, alpha = synthetic.device_batch("iiwa", B, 77, cuda_device, 6, p)
+    ddq, s_out = projection.step("iiwa", q, dq, s, alpha, p)
+    ctx = projection.HostContext(B, chunks=4)
+    h = [t.cpu().pin_memory() for t in (q, dq, s, alpha)]
+    ddq_h = torch.empty(B, 6).pin_memory()
+    s_h = torch.empty(B, 11).pin_memory()
+    ctx.iiwa_step(6, *h, ddq_h, s_h, p)
+    assert torch.equal(ddq_h, ddq.cpu()) and torch.equal(s_h, s_out.cpu())
+    ctx.close()
