@@ -47,7 +47,7 @@ def workload_name(n_gpus):
 
 def _cpu_worker(args):
     """Per-environment float64 NumPy path, the way the reference runs it (SVD + rref per call)."""
-    q, dq, s, alpha = args
+    q, dq, s, alpha, reps = args
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(1)
@@ -62,9 +62,10 @@ def _cpu_worker(args):
     evs = [oenv.iiwa_eval(q[i], dq[i]) for i in range(q.shape[0])]
     t0 = time.perf_counter()
     acc = 0.0
-    for i in range(q.shape[0]):
-        out = ao.atacom_step(spec, evs[i], dq[i], s[i], alpha[i], basis="svd")
-        acc += out["ddq"][0]
+    for _ in range(reps):
+        for i in range(q.shape[0]):
+            out = ao.atacom_step(spec, evs[i], dq[i], s[i], alpha[i], basis="svd")
+            acc += out["ddq"][0]
     dt = time.perf_counter() - t0
     del limiter
     return dt, acc
@@ -84,27 +85,28 @@ def _cpu_sample(n_envs, seed):
     return q, dq, s, alpha
 
 
-def cpu_env_steps_per_sec(pool, cores, sample):
-    """Run one bounded sample split over `cores` processes; returns (env-steps/s, wall seconds)."""
+def cpu_env_steps_per_sec(pool, cores, sample, reps=1):
+    """Run one bounded sample (`reps` passes over it) split over `cores` processes; returns
+    (env-steps/s, seconds of the slowest worker's timed loop)."""
     import numpy as np
     q, dq, s, alpha = sample
     idx = np.array_split(np.arange(q.shape[0]), cores)
-    res = pool.map(_cpu_worker, [(q[i], dq[i], s[i], alpha[i]) for i in idx])
-    wall = max(r[0] for r in res)                     # slowest worker's timed loop
-    return q.shape[0] / wall, wall
+    res = pool.map(_cpu_worker, [(q[i], dq[i], s[i], alpha[i], reps) for i in idx])
+    wall = max(r[0] for r in res)
+    return reps * q.shape[0] / wall, wall
 
 
-def run_cpu_baseline(envs_per_core=384):
+def run_cpu_baseline(envs_per_core=256, reps=24):
     cores = os.cpu_count() or 1
     sample = _cpu_sample(envs_per_core * cores, 1234)
     with mp.get_context("fork").Pool(cores) as pool:
         cpu_env_steps_per_sec(pool, cores, tuple(a[:8 * cores] for a in sample))     # warm the workers
-        value, wall = cpu_env_steps_per_sec(pool, cores, sample)
+        value, wall = cpu_env_steps_per_sec(pool, cores, sample, reps)
     return dict(value=value, unit=UNIT, cores=cores, kind="port",
-                sample="first %d envs of the seed-1234 IiwaAirHockey-7H batch, float64 oracle port of "
-                       "atacom.py:123-139 (SciPy SVD + rref per env; constraint callbacks precomputed, pinocchio absent), "
-                       "%d processes x 1 thread, %.1f s timed"
-                       % (envs_per_core * cores, cores, wall))
+                sample="%d passes over the first %d envs of the seed-1234 IiwaAirHockey-7H batch, float64 oracle "
+                       "port of atacom.py:123-139 (SciPy SVD + rref per env; constraint callbacks precomputed, "
+                       "pinocchio absent), %d processes x 1 thread, %.1f s timed"
+                       % (reps, envs_per_core * cores, cores, wall))
 
 
 def reference_arm(args):
@@ -113,15 +115,16 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 256 * cores                              # bounded sample per step
+    per_step = 128 * cores                              # distinct envs; 4 passes per step
     sample = _cpu_sample(per_step, 1234)
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(max(args.warmup, 1)):
             cpu_env_steps_per_sec(pool, cores, tuple(a[:16 * cores] for a in sample))
         walls = []
         for _ in range(args.steps):
-            walls.append(cpu_env_steps_per_sec(pool, cores, sample)[1])
+            walls.append(cpu_env_steps_per_sec(pool, cores, sample, 4)[1])
     total = sum(walls)
+    per_step *= 4
     value = per_step * args.steps / total
     desc = ("%d envs per step (bounded sample of the %d-env batch), float64 oracle port of atacom.py:123-139 "
             "(SciPy SVD + rref per env; constraint callbacks precomputed, pinocchio absent), "

@@ -295,10 +295,10 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   int rc = check_common(B, p);
   if (rc) return rc;
   using D = typename Env::D;
+  if (B == 0) return ATACOM_OK;
   if (!q || !dq || !ddq || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
-  if (B == 0) return ATACOM_OK;
   StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B};
   atacom_step_kernel<Env><<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(a, as_params(p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -310,8 +310,8 @@ int launch_slack_init(const float* q, const float* dq, float* s, const uint8_t* 
                       const AtacomParams* p, void* stream) {
   int rc = check_common(B, p);
   if (rc) return rc;
-  if (!q || !dq || !s) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
+  if (!q || !dq || !s) return ATACOM_ERR_NULL_POINTER;
   atacom_slack_init_kernel<Env><<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(q, dq, s, mask, B,
                                                                                             as_params(p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -475,8 +475,8 @@ int atacom_point_reach_step(int n_objects, const float* q, const float* dq, cons
                             void* stream) {
   int rc = check_common(B, p);
   if (rc) return rc;
-  if (!q || !dq || !obs_p || !obs_dp || !s_in || !action || !w || !s_out) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
+  if (!q || !dq || !obs_p || !obs_dp || !s_in || !action || !w || !s_out) return ATACOM_ERR_NULL_POINTER;
   PointArgs a{q, dq, obs_p, obs_dp, s_in, action, w, s_out, status, w_dbg, B};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define ATACOM_PR_STEP(G_) point_reach_step_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(a, as_params(p))
@@ -498,8 +498,8 @@ int atacom_point_reach_slack_init(int n_objects, const float* q, const float* ob
                                   const uint8_t* mask, int64_t B, const AtacomParams* p, void* stream) {
   int rc = check_common(B, p);
   if (rc) return rc;
-  if (!q || !obs_p || !s) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
+  if (!q || !obs_p || !s) return ATACOM_ERR_NULL_POINTER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define ATACOM_PR_INIT(G_) \
   point_reach_slack_init_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(q, obs_p, s, mask, B, as_params(p))
@@ -534,6 +534,7 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   int rc = check_common(B, p);
   if (rc) return rc;
   if (!atacom_generic_supported(n, F, G)) return ATACOM_ERR_BAD_DIMS;
+  if (B == 0) return ATACOM_OK;
   if (!c || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;

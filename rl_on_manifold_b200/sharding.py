@@ -1,0 +1,52 @@
+"""Multi-GPU layout of the environment batch: independent shards, one gather per roll-out step.
+
+The projection has no cross-environment term (atacom.py:123-139), so rank r of W owns the contiguous
+block [lo_r, hi_r) of the environment index and its slices of q, dq, s, alpha, ddq; the slack state `s`
+never leaves its rank.  The only exchange is one all-gather of the projected accelerations
+ddq[B/W, n] per step, issued on the stream the kernel ran on."""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_B, rank, world):
+    """Contiguous block of rank `rank`: sizes differ by at most one when W does not divide B."""
+    base, rem = divmod(global_B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class EnvShard:
+    def __init__(self, global_B, rank=None, world=None, group=None):
+        self.group = group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.global_B = global_B
+        self.lo, self.hi = shard_bounds(global_B, self.rank, self.world)
+        self.max_local = -(-global_B // self.world)
+
+    @property
+    def local_B(self):
+        return self.hi - self.lo
+
+    def take(self, t):
+        """This rank's rows of a [global_B, ...] tensor."""
+        return t[self.lo:self.hi].contiguous()
+
+    def gather(self, local, out=None):
+        """All-gather [local_B, d] rows into [global_B, d] (every rank gets the full array)."""
+        if self.world == 1:
+            return local if out is None else out.copy_(local)
+        d = local.shape[1:]
+        if out is None:
+            out = torch.empty((self.global_B,) + tuple(d), dtype=local.dtype, device=local.device)
+        if self.global_B % self.world == 0:
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            return out
+        pad = torch.zeros((self.max_local,) + tuple(d), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad, group=self.group)
+        for r, part in enumerate(parts):
+            lo, hi = shard_bounds(self.global_B, r, self.world)
+            out[lo:hi] = part[:hi - lo]
+        return out

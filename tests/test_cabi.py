@@ -53,6 +53,7 @@ def test_argument_validation_without_gpu():
     assert _lib.lib.atacom_circle_step(one, one, one, one, one, one, null, null, 0, ctypes.byref(p), null) == 0
     assert _lib.lib.atacom_circle_step(null, one, one, one, one, one, null, null, 4, ctypes.byref(p), null) == -1
     assert _lib.lib.atacom_circle_step(one, one, one, one, one, one, null, null, 4, None, null) == -1
+    assert _lib.lib.atacom_circle_step(null, null, null, null, null, null, null, null, 0, ctypes.byref(p), null) == 0
     bad = p.copy()
     bad.variant = 7
     assert _lib.lib.atacom_circle_step(one, one, one, one, one, one, null, null, 4, ctypes.byref(bad), null) == -3
