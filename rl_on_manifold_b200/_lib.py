@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libatacom_b200.so")
+LIB_PATH = os.environ.get("ATACOM_B200_LIB") or os.path.join(_HERE, "libatacom_b200.so")   # override: kernel experiments
 
 MAX_Q, MAX_F, MAX_G, MAX_C, ENV_PARAMS = 8, 4, 16, 20, 24
 

@@ -37,6 +37,17 @@
 
 namespace atacom {
 
+// The per-environment code is one long fully unrolled instruction stream (> 100 KB of SASS); warps
+// that drift apart each stream it through the instruction cache on their own.  Kernels in which every
+// thread of the block runs the projection place block barriers between its phases (SYNC = true) so
+// the resident warps stay in the same code region and share instruction-cache lines.
+template <bool SYNC>
+ATACOM_HD void phase_sync() {
+#if defined(__CUDA_ARCH__)
+  if (SYNC) __syncthreads();
+#endif
+}
+
 // status bits written per environment
 enum : uint8_t {
   ST_RANK_DEFICIENT = 1,   // Jc lost row rank (pinv_null would cut a singular value)
@@ -51,11 +62,27 @@ template <> struct num<float> {
   static ATACOM_HD float eps() { return 1.1920929e-07f; }
   static ATACOM_HD float sqrt(float x) { return ::sqrtf(x); }
   static ATACOM_HD float abs(float x) { return ::fabsf(x); }
+  static ATACOM_HD float div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);      // MUFU.RCP + FMUL, <= 2 ulp: far below eps32 * cond(Jc)
+#else
+    return a / b;
+#endif
+  }
+  static ATACOM_HD float rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return ::rsqrtf(x);
+#else
+    return 1.0f / ::sqrtf(x);
+#endif
+  }
 };
 template <> struct num<double> {
   static ATACOM_HD double eps() { return 2.220446049250313e-16; }
   static ATACOM_HD double sqrt(double x) { return ::sqrt(x); }
   static ATACOM_HD double abs(double x) { return ::fabs(x); }
+  static ATACOM_HD double div(double a, double b) { return a / b; }
+  static ATACOM_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
 };
 
 template <int N_, int F_, int G_>
@@ -69,18 +96,6 @@ struct Dims {
 };
 
 template <int V> struct at_least_1 { static constexpr int value = V > 0 ? V : 1; };
-
-// Householder reflector for x[0..len): overwrites x with v (H = I - beta v v^T),
-// returns the image H x = diag * e_0.  beta = 0 marks a vanishing vector.
-template <typename T>
-ATACOM_HD void make_reflector(T* x, int len, T sigma, T& beta, T& diag) {
-  const T x0 = x[0];
-  const T sg = x0 >= T(0) ? T(1) : T(-1);
-  x[0] = x0 + sg * sigma;
-  beta = T(1) / (sigma * (sigma + num<T>::abs(x0)));
-  diag = -sg * sigma;
-  (void)len;
-}
 
 // ---------------------------------------------------------------------------------------
 // Dense path: Householder QR of Jc^T (N x C), exactly the orthogonal route the reference's

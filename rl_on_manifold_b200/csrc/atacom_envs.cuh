@@ -15,6 +15,7 @@
 #pragma once
 
 #include "atacom_core.cuh"
+#include "atacom_structured.cuh"
 
 namespace atacom {
 
@@ -84,6 +85,7 @@ ATACOM_HD void sincos_hp(double x, double* sn, double* cs) {
 // circle_atacom.py:47-69: f = q0^2 + q1^2 - 1, g = -q1 - 0.5
 struct CircleEnv {
   using D = Dims<2, 1, 1>;
+  static constexpr int NDIAG = 0;   // trailing inequality rows with a diagonal Jacobian
   template <typename T, typename HP>
   static ATACOM_HD void eval(const ParamsT<T>&, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
     const HP q0 = q[0], q1 = q[1], d0 = dq[0], d1 = dq[1];
@@ -104,6 +106,7 @@ struct CircleEnv {
 // atacom_air_hockey.py:78-107.  env[] = l1 l2 l3 base_x base_y qmax[3] half_len half_wid
 struct PlanarEnv {
   using D = Dims<3, 0, 6>;
+  static constexpr int NDIAG = 3;   // joint-limit rows q_j^2 - qmax_j^2
   template <typename T, typename HP>
   static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
     HP th = HP(0), om = HP(0);
@@ -182,6 +185,7 @@ template <int NJ>
 struct IiwaEnv {
   static_assert(NJ == 6 || NJ == 7, "iiwa: 6 (isolated joint 7) or 7 controlled joints");
   using D = Dims<NJ, 1, 5 + NJ>;
+  static constexpr int NDIAG = NJ;  // joint-limit rows q_j^2 - qmax_j^2
 
   template <typename T, typename HP>
   static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
@@ -290,10 +294,62 @@ struct IiwaEnv {
   }
 };
 
+// ----------------------------------------------------------------------------- projection dispatch
+// Dense Householder path, kept out of line: it is the rarely taken fallback of the structured path and
+// must not set the register budget of the kernels that inline the fast path.
+#if defined(__CUDACC__)
+#define ATACOM_NOINLINE __host__ __device__ __noinline__
+#else
+#define ATACOM_NOINLINE __attribute__((noinline))
+#endif
+template <typename T, class D>
+ATACOM_NOINLINE uint8_t project_dense_outlined(const T* Af, const T* Ag, const T* s, const T* r, const T* alpha,
+                                               T tol, bool want_null, T* w_mn, T* w_null) {
+  return project_dense<T, D>(Af, Ag, s, r, alpha, tol, want_null, w_mn, w_null);
+}
+
+constexpr int STRUCTURED_TMAX = 2;      // stiff inequality rows handled by the fast path
+#define ATACOM_STIFF_TAU 25             // row i is stiff when |a_i|^2 > tau s_i^2
+
+// A: C x n row-major (equality rows first, all K-scaled), the last NDIAG inequality rows diagonal.
+template <typename T, class D, int NDIAG, bool SYNC = false>
+ATACOM_HD uint8_t project(const T* A, const T* s, const T* r, const T* alpha, T tol, bool want_null, T* w_mn,
+                          T* w_null) {
+  constexpr int n = D::n, F = D::F, G = D::G, C = D::C, GD = G - NDIAG;
+  T dg[at_least_1<NDIAG>::value];
+  ATACOM_UNROLL
+  for (int j = 0; j < NDIAG; ++j) dg[j] = A[(F + GD + j) * n + j];
+  const T* Ag = A + (F < C ? F : 0) * n;
+  uint8_t st = Structured<T, D, NDIAG, STRUCTURED_TMAX, SYNC>::project(A, Ag, dg, s, r, alpha, tol, T(ATACOM_STIFF_TAU),
+                                                                 want_null, w_mn, w_null);
+  if (st & ST_DENSE_PATH) {
+    // private copies: only these (not the register-resident operands of the fast path) are addressable
+    constexpr int N = D::N, k = D::k;
+    T A2[at_least_1<C * n>::value], s2[at_least_1<G>::value], r2[at_least_1<C>::value];
+    T al2[at_least_1<k>::value], wm2[N], wn2[N];
+    ATACOM_UNROLL
+    for (int i = 0; i < C * n; ++i) A2[i] = A[i];
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) s2[i] = s[i];
+    ATACOM_UNROLL
+    for (int i = 0; i < C; ++i) r2[i] = r[i];
+    ATACOM_UNROLL
+    for (int i = 0; i < k; ++i) al2[i] = alpha[i];
+    st = ST_DENSE_PATH | project_dense_outlined<T, D>(A2, A2 + (F < C ? F : 0) * n, s2, r2, al2, tol, want_null,
+                                                      wm2, wn2);
+    ATACOM_UNROLL
+    for (int i = 0; i < N; ++i) {
+      w_mn[i] = wm2[i];
+      w_null[i] = wn2[i];
+    }
+  }
+  return st;
+}
+
 // ----------------------------------------------------------------------------- shared tail
 // constraints.py:33-43 (fun / K_J / b), atacom.py:151-196 (Jc, psi, c), :130-137 (assembly,
 // slack integration, acceleration truncation); error_correction_wrapper.py:117-134 for VARIANT_EC.
-template <typename T, typename HP, class D>
+template <typename T, typename HP, class D, int NDIAG, bool SYNC = false>
 ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP, D>& R, const T* dq, const T* s,
                                 const T* alpha, T* ddq, T* s_out, T* w_dbg) {
   constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
@@ -314,7 +370,8 @@ ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP,
     r[i] = T((ec ? HP(0) : psi) + HP(P.K_c[i]) * ct);           // atacom.py:130,132,181
   }
   T w_mn[N], w_null[N];
-  uint8_t st = project_dense<T, D>(&A[0][0], &A[F < C ? F : 0][0], s, r, alpha, P.rref_tol, !ec, w_mn, w_null);
+  phase_sync<SYNC>();
+  uint8_t st = project<T, D, NDIAG, SYNC>(&A[0][0], s, r, alpha, P.rref_tol, !ec, w_mn, w_null);
   if (ec) {
     ATACOM_UNROLL
     for (int j = 0; j < n; ++j) w_null[j] = alpha[j];           // error_correction_wrapper.py:127
@@ -394,7 +451,7 @@ struct PointReachEnv {
       r[i] = T(dc + K * (bp + bq) + Kc * c);
     }
     T w_mn[N], w_null[N];
-    uint8_t st = project_dense<T, D>((const T*)nullptr, &A[0][0], s, r, action, P.rref_tol, true, w_mn, w_null);
+    uint8_t st = project<T, D, 0>(&A[0][0], s, r, action, P.rref_tol, true, w_mn, w_null);
     bool finite = true;
     ATACOM_UNROLL
     for (int i = 0; i < N; ++i) {

@@ -19,7 +19,13 @@ static_assert(sizeof(ParamsT<float>) == sizeof(AtacomParams), "ParamsT<float> mu
 
 namespace {
 
-constexpr int TPB = 128;
+#ifndef ATACOM_TPB
+#define ATACOM_TPB 128   // environments (threads) per block
+#endif
+#ifndef ATACOM_MINB
+#define ATACOM_MINB 1    // min resident blocks per SM asked of ptxas for the step kernels
+#endif
+constexpr int TPB = ATACOM_TPB;
 std::atomic<int64_t> g_launches{0};
 
 // ------------------------------------------------------------------ staging helpers
@@ -69,7 +75,7 @@ struct StepArgs {
 
 // ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
 template <class Env>
-__global__ void __launch_bounds__(TPB) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
+__global__ void __launch_bounds__(TPB, ATACOM_MINB) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value;
@@ -90,29 +96,36 @@ __global__ void __launch_bounds__(TPB) atacom_step_kernel(StepArgs a, ParamsT<fl
   else if (k > 0) slab_load<at_least_1<k>::value>(a.alpha, sa, env0, nvalid);
   __syncthreads();
 
+  // every thread runs the projection (threads past the end of a ragged last block recompute row 0
+  // and discard the result) so that the phase barriers inside it are reached by the whole block
   const int t = threadIdx.x;
-  if (t < nvalid) {
+  const bool valid = t < nvalid;
+  const int tr = valid ? t : 0;
+  {
     float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
 #pragma unroll
     for (int j = 0; j < n; ++j) {
-      q[j] = sq[t * n + j];
-      dq[j] = sdq[t * n + j];
+      q[j] = sq[tr * n + j];
+      dq[j] = sdq[tr * n + j];
     }
 #pragma unroll
-    for (int i = 0; i < G; ++i) s[i] = ss[t * G + i];
+    for (int i = 0; i < G; ++i) s[i] = ss[tr * G + i];
     const int na = ec ? n : k;
 #pragma unroll
-    for (int j = 0; j < n; ++j) al[j] = j < na ? sa[t * na + j] : 0.f;
+    for (int j = 0; j < n; ++j) al[j] = j < na ? sa[tr * na + j] : 0.f;
+    __syncthreads();                       // all rows are in registers: the staging buffers can be reused
 
     RawConstraints<float, double, D> R;
     Env::template eval<float, double>(P, q, dq, R);
-    float* dbg = a.w_dbg ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
-    const uint8_t st = step_from_raw<float, double, D>(P, R, dq, s, al, ddq, so, dbg);
-    if (a.status) a.status[env0 + t] = st;
+    float* dbg = (a.w_dbg && valid) ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
+    const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, true>(P, R, dq, s, al, ddq, so, dbg);
+    if (valid) {
+      if (a.status) a.status[env0 + t] = st;
 #pragma unroll
-    for (int j = 0; j < n; ++j) sq[t * n + j] = ddq[j];
+      for (int j = 0; j < n; ++j) sq[t * n + j] = ddq[j];
 #pragma unroll
-    for (int i = 0; i < G; ++i) ss[t * G + i] = so[i];
+      for (int i = 0; i < G; ++i) ss[t * G + i] = so[i];
+    }
   }
   __syncthreads();
   slab_store<n>(a.ddq, sq, env0, nvalid);
@@ -180,7 +193,7 @@ __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __rest
 #pragma unroll
   for (int i = 0; i < G; ++i) s[i] = a.s_in[e * G + i];
   float* dbg = a.w_dbg ? a.w_dbg + e * (2 * N) : nullptr;
-  const uint8_t st = step_from_raw<float, double, D>(P, R, dq, s, al, ddq, so, dbg);
+  const uint8_t st = step_from_raw<float, double, D, 0>(P, R, dq, s, al, ddq, so, dbg);
   if (a.status) a.status[e] = st;
 #pragma unroll
   for (int j = 0; j < n; ++j) a.ddq[e * n + j] = ddq[j];

@@ -59,6 +59,18 @@ def harness_dense(lib, n, F, G, Af, Ag, s, r, alpha, tol, dtype=np.float32):
     return wmn, wn, st
 
 
+def harness_structured(lib, n, F, G, Af, Ag, s, r, alpha, tol, tau, dtype=np.float32):
+    B = s.shape[0] if G else alpha.shape[0]
+    N = n + G
+    fn = lib.harness_structured_f32 if dtype == np.float32 else lib.harness_structured_f64
+    arrs = [np.ascontiguousarray(a, dtype=dtype) for a in (Af, Ag, s, r, alpha)]
+    wmn, wn, st = np.zeros((B, N), dtype), np.zeros((B, N), dtype), np.zeros(B, np.uint8)
+    ct = ctypes.c_float if dtype == np.float32 else ctypes.c_double
+    rc = fn(n, F, G, ctypes.c_int64(B), *[_p(a) for a in arrs], ct(tol), ct(tau), _p(wmn), _p(wn), _p(st))
+    assert rc == 0, "shape not compiled into the harness"
+    return wmn, wn, st
+
+
 def harness_point(lib, G, params_flat, q, dq, p, dp, s, act, dtype=np.float32, init_only=False):
     B = q.shape[0]
     fn = lib.harness_point_f32 if dtype == np.float32 else lib.harness_point_f64

@@ -5,6 +5,7 @@
 // library, never a fallback.
 #include <cstdint>
 #include "../../rl_on_manifold_b200/csrc/atacom_envs.cuh"
+#include "../../rl_on_manifold_b200/csrc/atacom_structured.cuh"
 
 using namespace atacom;
 
@@ -79,7 +80,7 @@ static void run_step(int64_t B, const double* params, const T* q, const T* dq, c
     }
     T al[D::n];
     for (int j = 0; j < D::n; ++j) al[j] = j < na ? alpha[b * na + j] : T(0);
-    status[b] = step_from_raw<T, double, D>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n, s_out + b * D::G,
+    status[b] = step_from_raw<T, double, D, Env::NDIAG>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n, s_out + b * D::G,
                                     w_dbg + b * 2 * D::N);
   }
 }
@@ -141,5 +142,48 @@ int harness_point_f64(int G, int64_t B, const double* params, const double* q, c
                       const double* dp, const double* s, const double* act, double* w, double* s_out,
                       double* w_dbg, uint8_t* status, int init_only) {
   return point_dispatch<double>(G, B, params, q, dq, p, dp, s, act, w, s_out, w_dbg, status, init_only);
+}
+}
+
+// ---- structured path (with the dense fallback the kernels use when it defers)
+template <typename T, int n, int F, int G, int NDIAG, int TMAX>
+static void run_structured(int64_t B, const T* Af, const T* Ag, const T* s, const T* r, const T* alpha, T tol, T tau,
+                           T* w_mn, T* w_null, uint8_t* status) {
+  using D = Dims<n, F, G>;
+  constexpr int GD = G - NDIAG;
+  for (int64_t b = 0; b < B; ++b) {
+    T dg[NDIAG > 0 ? NDIAG : 1];
+    for (int j = 0; j < NDIAG; ++j) dg[j] = Ag[(b * G + GD + j) * n + j];
+    uint8_t st = Structured<T, D, NDIAG, TMAX>::project(Af + b * F * n, Ag + b * G * n, dg, s + b * G, r + b * D::C,
+                                                        alpha + b * D::k, tol, tau, true, w_mn + b * D::N,
+                                                        w_null + b * D::N);
+    if (st & ST_DENSE_PATH)
+      st = ST_DENSE_PATH | project_dense<T, D>(Af + b * F * n, Ag + b * G * n, s + b * G, r + b * D::C,
+                                               alpha + b * D::k, tol, true, w_mn + b * D::N, w_null + b * D::N);
+    status[b] = st;
+  }
+}
+
+#define SDISPATCH(T)                                                                                                 \
+  if (n == 2 && F == 1 && G == 1) { run_structured<T, 2, 1, 1, 0, 1>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 3 && F == 0 && G == 6) { run_structured<T, 3, 0, 6, 3, 2>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 6 && F == 1 && G == 11) { run_structured<T, 6, 1, 11, 6, 2>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 7 && F == 1 && G == 12) { run_structured<T, 7, 1, 12, 7, 2>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 2 && F == 0 && G == 4) { run_structured<T, 2, 0, 4, 0, 2>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 4 && F == 2 && G == 3) { run_structured<T, 4, 2, 3, 0, 2>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 3 && F == 1 && G == 3) { run_structured<T, 3, 1, 3, 0, 2>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  if (n == 3 && F == 1 && G == 0) { run_structured<T, 3, 1, 0, 0, 0>(B, Af, Ag, s, r, alpha, tol, tau, w_mn, w_null, status); return 0; } \
+  return -1;
+
+extern "C" {
+int harness_structured_f32(int n, int F, int G, int64_t B, const float* Af, const float* Ag, const float* s,
+                           const float* r, const float* alpha, float tol, float tau, float* w_mn, float* w_null,
+                           uint8_t* status) {
+  SDISPATCH(float)
+}
+int harness_structured_f64(int n, int F, int G, int64_t B, const double* Af, const double* Ag, const double* s,
+                           const double* r, const double* alpha, double tol, double tau, double* w_mn,
+                           double* w_null, uint8_t* status) {
+  SDISPATCH(double)
 }
 }
