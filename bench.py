@@ -254,9 +254,40 @@ def ours(args):
         time.sleep(0.3)
 
     launches0 = _lib.launch_count()
-    total_ms = timed(step, args.steps, args.warmup)
+    eager_ms = timed(step, args.steps, args.warmup)
     launches = _lib.launch_count() - launches0 - args.warmup
-    kernel_ms = total_ms if world == 1 else timed(kernel_only, args.steps, args.warmup)
+    total_ms, launch_mode = eager_ms, "eager launches from Python (ctypes)"
+    kernel_ms = eager_ms if world == 1 else timed(kernel_only, args.steps, args.warmup)
+
+    def timed_graph(fn, steps):
+        """The same K steps captured once in a CUDA graph and replayed: removes the per-launch host cost."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                fn(i)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(steps):
+                fn(i)
+        graph.replay()                                   # warm-up replay
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    if world == 1 and not args.no_graph:
+        try:
+            graph_ms = timed_graph(kernel_only, args.steps)
+            if graph_ms < total_ms:
+                total_ms = kernel_ms = graph_ms
+                launch_mode = "CUDA graph of %d launches, one replay" % args.steps
+        except Exception as exc:                         # pragma: no cover
+            launch_mode += " (graph capture failed: %s)" % type(exc).__name__
 
     # end to end through the host-buffer entry point: pinned host arrays in, pinned host arrays out
     ctx = projection.HostContext(B, chunks=args.chunks)
@@ -308,7 +339,8 @@ def ours(args):
                         else "single GPU",
                         cold_inputs="ring of %d distinct batches (%.0f MB > 2x L2) rotated every step"
                                     % (ring, ring * B * BYTES_PER_ENV_STEP / 1e6),
-                        bytes_per_env_step=BYTES_PER_ENV_STEP),
+                        bytes_per_env_step=BYTES_PER_ENV_STEP, launch=launch_mode,
+                        eager_ms_per_step=eager_ms / args.steps),
             e2e=dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * BYTES_IN,
                      d2h_bytes_per_step=B * BYTES_OUT, api="atacom_iiwa_step_host (pinned host buffers)",
                      chunks=args.chunks),
@@ -334,6 +366,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--chunks", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

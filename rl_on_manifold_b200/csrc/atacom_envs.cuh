@@ -309,7 +309,7 @@ ATACOM_NOINLINE uint8_t project_dense_outlined(const T* Af, const T* Ag, const T
 }
 
 constexpr int STRUCTURED_TMAX = 2;      // stiff inequality rows handled by the fast path
-#define ATACOM_STIFF_TAU 25             // row i is stiff when |a_i|^2 > tau s_i^2
+#define ATACOM_STIFF_TAU 400            // row i is stiff when |a_i|^2 > tau s_i^2
 
 // A: C x n row-major (equality rows first, all K-scaled), the last NDIAG inequality rows diagonal.
 template <typename T, class D, int NDIAG, bool SYNC = false>

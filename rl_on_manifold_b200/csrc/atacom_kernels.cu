@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <new>
 
 #include "../../include/atacom_b200.h"
@@ -20,12 +21,16 @@ static_assert(sizeof(ParamsT<float>) == sizeof(AtacomParams), "ParamsT<float> mu
 namespace {
 
 #ifndef ATACOM_TPB
-#define ATACOM_TPB 128   // environments (threads) per block
+#define ATACOM_TPB 128   // environments (threads) per block of the auxiliary kernels
+#endif
+#ifndef ATACOM_STEP_MAX_TPB
+#define ATACOM_STEP_MAX_TPB 448   // largest block of the step kernels: 448 x 144 registers fill one SM
 #endif
 #ifndef ATACOM_MINB
 #define ATACOM_MINB 1    // min resident blocks per SM asked of ptxas for the step kernels
 #endif
 constexpr int TPB = ATACOM_TPB;
+constexpr int STEP_MAX_TPB = ATACOM_STEP_MAX_TPB;
 std::atomic<int64_t> g_launches{0};
 
 // ------------------------------------------------------------------ staging helpers
@@ -73,63 +78,78 @@ struct StepArgs {
   int64_t B;
 };
 
+// ------------------------------------------------------------------ row access
+// One thread moves its own rows.  A warp's 32 rows of a [B, DIM] array are one contiguous piece of
+// 32*DIM*4 bytes, so its DIM loads touch exactly the lines of that piece (the first load brings them
+// to L1, the others hit): DRAM traffic is the algorithmic minimum without a shared-memory round trip,
+// and the loads of all arrays are in flight together.  Rows are 8-byte aligned when DIM is even.
+template <int DIM>
+__device__ __forceinline__ void row_load(const float* __restrict__ g, int64_t e, float* dst) {
+  const float* src = g + e * DIM;
+  if (DIM % 2 == 0 && (reinterpret_cast<uintptr_t>(g) & 7) == 0) {
+#pragma unroll
+    for (int j = 0; j < DIM / 2; ++j) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src) + j);
+      dst[2 * j] = v.x;
+      dst[2 * j + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) dst[j] = __ldg(src + j);
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void row_store(float* __restrict__ g, int64_t e, const float* src) {
+  float* dst = g + e * DIM;
+  if (DIM % 2 == 0 && (reinterpret_cast<uintptr_t>(g) & 7) == 0) {
+#pragma unroll
+    for (int j = 0; j < DIM / 2; ++j) reinterpret_cast<float2*>(dst)[j] = make_float2(src[2 * j], src[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) dst[j] = src[j];
+  }
+}
+
 // ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
+// One thread = one environment.  The block size is chosen at launch (<= STEP_MAX_TPB) so that the batch
+// spreads evenly over the SMs, ideally one block per SM: the body is a long fully unrolled instruction
+// stream and the block barriers between its phases keep all warps of the SM in the same code region,
+// so each instruction line is fetched once per SM rather than once per warp.
 template <class Env>
-__global__ void __launch_bounds__(TPB, ATACOM_MINB) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
+__global__ void __launch_bounds__(STEP_MAX_TPB, ATACOM_MINB) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
-  constexpr int G1 = at_least_1<G>::value;
-  __shared__ __align__(16) float sq[round4_t<TPB * n>::value];
-  __shared__ __align__(16) float sdq[round4_t<TPB * n>::value];
-  __shared__ __align__(16) float ss[round4_t<TPB * G1>::value];
-  __shared__ __align__(16) float sa[round4_t<TPB * n>::value];
-
-  const int64_t env0 = static_cast<int64_t>(blockIdx.x) * TPB;
-  const int64_t left = a.B - env0;
-  const int nvalid = left < TPB ? static_cast<int>(left) : TPB;
+  constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
+  const int64_t e_raw = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = e_raw < a.B;
+  // threads past the end recompute the last environment and discard it, so that every thread of the
+  // block reaches the phase barriers inside the projection
+  const int64_t e = valid ? e_raw : a.B - 1;
   const bool ec = P.variant == VARIANT_EC;
 
-  slab_load<n>(a.q, sq, env0, nvalid);
-  slab_load<n>(a.dq, sdq, env0, nvalid);
-  if (G > 0) slab_load<G1>(a.s_in, ss, env0, nvalid);
-  if (ec) slab_load<n>(a.alpha, sa, env0, nvalid);
-  else if (k > 0) slab_load<at_least_1<k>::value>(a.alpha, sa, env0, nvalid);
-  __syncthreads();
-
-  // every thread runs the projection (threads past the end of a ragged last block recompute row 0
-  // and discard the result) so that the phase barriers inside it are reached by the whole block
-  const int t = threadIdx.x;
-  const bool valid = t < nvalid;
-  const int tr = valid ? t : 0;
-  {
-    float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
+  float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
+  row_load<n>(a.q, e, q);
+  row_load<n>(a.dq, e, dq);
+  if (G > 0) row_load<G1>(a.s_in, e, s);
+  if (ec) {
+    row_load<n>(a.alpha, e, al);
+  } else {
+    float ak[K1];
+    if (k > 0) row_load<K1>(a.alpha, e, ak);
 #pragma unroll
-    for (int j = 0; j < n; ++j) {
-      q[j] = sq[tr * n + j];
-      dq[j] = sdq[tr * n + j];
-    }
-#pragma unroll
-    for (int i = 0; i < G; ++i) s[i] = ss[tr * G + i];
-    const int na = ec ? n : k;
-#pragma unroll
-    for (int j = 0; j < n; ++j) al[j] = j < na ? sa[tr * na + j] : 0.f;
-    __syncthreads();                       // all rows are in registers: the staging buffers can be reused
-
-    RawConstraints<float, double, D> R;
-    Env::template eval<float, double>(P, q, dq, R);
-    float* dbg = (a.w_dbg && valid) ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
-    const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, true>(P, R, dq, s, al, ddq, so, dbg);
-    if (valid) {
-      if (a.status) a.status[env0 + t] = st;
-#pragma unroll
-      for (int j = 0; j < n; ++j) sq[t * n + j] = ddq[j];
-#pragma unroll
-      for (int i = 0; i < G; ++i) ss[t * G + i] = so[i];
-    }
+    for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
   }
-  __syncthreads();
-  slab_store<n>(a.ddq, sq, env0, nvalid);
-  if (G > 0) slab_store<G1>(a.s_out, ss, env0, nvalid);
+
+  RawConstraints<float, double, D> R;
+  Env::template eval<float, double>(P, q, dq, R);
+  float* dbg = (a.w_dbg && valid) ? a.w_dbg + e * (2 * N) : nullptr;
+  const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, true>(P, R, dq, s, al, ddq, so, dbg);
+  if (valid) {
+    if (a.status) a.status[e] = st;
+    row_store<n>(a.ddq, e, ddq);
+    if (G > 0) row_store<G1>(a.s_out, e, so);
+  }
 }
 
 template <class Env>
@@ -293,6 +313,30 @@ inline int check_launch() {
 
 inline unsigned blocks_for(int64_t B) { return static_cast<unsigned>((B + TPB - 1) / TPB); }
 
+// Block size of the step kernels: spread B environments over the SMs in as few equal waves as possible.
+int step_block_size(int64_t B) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sm_count = v;
+    else
+      sm_count = 148;
+  }
+  if (const char* f = getenv("ATACOM_STEP_TPB")) {   // experiments only
+    const int v = atoi(f);
+    if (v >= 32 && v <= STEP_MAX_TPB) return v / 32 * 32;
+  }
+  const int64_t waves = (B + static_cast<int64_t>(sm_count) * STEP_MAX_TPB - 1) / (static_cast<int64_t>(sm_count) * STEP_MAX_TPB);
+  const int64_t blocks = waves * sm_count;                       // one block per SM per wave
+  int64_t tpb = (B + blocks - 1) / blocks;
+  tpb = (tpb + 31) / 32 * 32;
+  if (tpb < 64) tpb = 64;
+  if (tpb > STEP_MAX_TPB) tpb = STEP_MAX_TPB;
+  return static_cast<int>(tpb);
+}
+
 int check_common(int64_t B, const AtacomParams* p) {
   if (!p) return ATACOM_ERR_NULL_POINTER;
   if (B < 0 || B > (int64_t(1) << 31) * TPB) return ATACOM_ERR_BAD_DIMS;
@@ -313,7 +357,9 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
   StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B};
-  atacom_step_kernel<Env><<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(a, as_params(p));
+  const int tpb = step_block_size(B);
+  const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
+  atacom_step_kernel<Env><<<grid, tpb, 0, static_cast<cudaStream_t>(stream)>>>(a, as_params(p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
 }

@@ -87,11 +87,11 @@ struct Structured {
       ATACOM_UNROLL
       for (int j = 0; j < n; ++j) sa[t][j] = T(0);
     }
-    // A row is a stiff CANDIDATE when |a_i|^2 > tau s_i^2 and MUST be stiff when |a_i|^2 > tau_hi s_i^2
-    // (tau_hi = 16 tau).  Must rows take slots first, candidates fill what is left; a candidate without
-    // a slot stays soft (cond(M) then grows to at most 1 + tau_hi G); a must row without a slot overflows.
+    // Row i is stiff when |a_i|^2 > tau s_i^2 (tau = 400: |a_i| / |s_i| > 20, the regime in which the rref
+    // tolerance 0.05 starts dropping x columns).  Soft rows then keep cond(M) <= 1 + tau G, measured fp32
+    // error <= 1e-5; a stiff row that finds no free slot overflows to the dense path.
     int nst = 0;
-    bool soft[G1], cand[G1], must[G1];
+    bool soft[G1];
     T tinv[G1];
     bool overflow = false;
     ATACOM_UNROLL
@@ -106,34 +106,28 @@ struct Structured {
       const T s2 = s[i] * s[i];
       const bool zero_row = !(nrm2 > T(0)) && !(s2 > T(0));
       if (zero_row) status |= ST_RANK_DEFICIENT;
-      cand[i] = !(nrm2 <= tau * s2) && !zero_row;
-      must[i] = !(nrm2 <= T(16) * tau * s2) && !zero_row;
-      soft[i] = true;
-      tinv[i] = (s2 > T(0)) ? num<T>::div(T(1), s2) : T(0);
+      const bool stiff = !(nrm2 <= tau * s2) && !zero_row;
+      const bool takes = stiff && nst < TMAX;
+      overflow = overflow || (stiff && !takes);
+      soft[i] = !takes;
+      ATACOM_UNROLL
+      for (int t2 = 0; t2 < TMAX; ++t2) srow[t2] = (takes && t2 == nst) ? i : srow[t2];
+      nst += takes ? 1 : 0;
+      tinv[i] = (soft[i] && s2 > T(0)) ? num<T>::div(T(1), s2) : T(0);
     }
+    // copy the chosen rows into their slots (zeros of a diagonal row are compile-time constants)
     ATACOM_UNROLL
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int t = 0; t < TMAX; ++t) {
       ATACOM_UNROLL
       for (int i = 0; i < G; ++i) {
-        const bool want = soft[i] && (pass == 0 ? must[i] : cand[i]);
-        if (want) {
-          if (nst < TMAX) {
-            soft[i] = false;
+        if (srow[t] == i) {
+          ss[t] = s[i];
+          sr[t] = r[F + i];
+          if (i < GD) {
             ATACOM_UNROLL
-            for (int t2 = 0; t2 < TMAX; ++t2) {
-              if (t2 == nst) {
-                ss[t2] = s[i];
-                sr[t2] = r[F + i];
-                srow[t2] = i;
-                ATACOM_UNROLL
-                for (int j = 0; j < n; ++j)
-                  sa[t2][j] = (i < GD) ? Ad[(i < GD ? i : 0) * n + j]
-                                       : ((j == i - GD) ? dg[i >= GD ? i - GD : 0] : T(0));
-              }
-            }
-            ++nst;
-          } else if (pass == 0) {
-            overflow = true;
+            for (int j = 0; j < n; ++j) sa[t][j] = Ad[(i < GD ? i : 0) * n + j];
+          } else {
+            sa[t][i >= GD ? i - GD : 0] = dg[i >= GD ? i - GD : 0];
           }
         }
       }
@@ -143,7 +137,7 @@ struct Structured {
     phase_sync<SYNC>();
     ATACOM_UNROLL
     for (int i = 0; i < G; ++i) {
-      const T t = soft[i] ? tinv[i] : T(0);
+      const T t = tinv[i];
       const T tr = t * r[F + i];
       if (i < GD) {
         ATACOM_UNROLL
@@ -521,68 +515,115 @@ struct Structured {
             Zr[j][t] = acc;
           }
         }
+        // slack columns in order
+#ifndef ATACOM_ROLL_SLACK
+#define ATACOM_ROLL_SLACK 0
+#endif
+        unsigned softmask = 0u, testmask = 0u;
+        T zloc[G1];
+        ATACOM_UNROLL
+        for (int i = 0; i < G; ++i) {
+          zloc[i] = T(0);
+          softmask |= soft[i] ? (1u << i) : 0u;
+        }
+#if ATACOM_ROLL_SLACK
+        // rolled: the body stays in the instruction cache; what it indexes dynamically lives in private arrays
+        T Aloc[GD1 * n], dloc[ND1], sloc[G1];
+        ATACOM_UNROLL
+        for (int i = 0; i < GD * n; ++i) Aloc[i] = Ad[i];
+        ATACOM_UNROLL
+        for (int j = 0; j < NDIAG; ++j) dloc[j] = dg[j];
+        ATACOM_UNROLL
+        for (int i = 0; i < G; ++i) sloc[i] = s[i];
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+        for (int i = 0; i < G && rem > 0; ++i) {
+#else
+        const T* Aloc = Ad;
+        const T* dloc = dg;
+        const T* sloc = s;
         ATACOM_UNROLL
         for (int i = 0; i < G; ++i) {
           if (rem > 0) {
-            int slot = -1;
-            ATACOM_UNROLL
-            for (int t = 0; t < TMAX; ++t) slot = (srow[t] == i) ? t : slot;
-            const T ninv_s = soft[i] ? ((s[i] * s[i] > T(0)) ? num<T>::div(T(-1), s[i]) : T(0)) : T(0);
-            T e[RMAX];
-            T s2 = T(0);
-            ATACOM_UNROLL
-            for (int j = 0; j < RMAX; ++j) {
-              T v;
-              if (soft[i]) {
-                v = gdot(Ad, dg, i, Xr[j]) * ninv_s;
-              } else {
-                v = T(0);
-                ATACOM_UNROLL
-                for (int t = 0; t < TMAX; ++t) v = (t == slot) ? Zr[j][t] : v;
-              }
-              e[j] = v;
-              s2 += v * v;
-            }
-            T part;
-            if (soft[i]) {
-              part = gdot(Ad, dg, i, xl) * ninv_s;
-            } else {
-              part = T(0);
-              ATACOM_UNROLL
-              for (int t = 0; t < TMAX; ++t) part = (t == slot) ? zl[t] : part;
-            }
-            const T sigma = num<T>::sqrt(s2);
-            ztested[i] = true;
-            if (!(sigma > tol)) {
-              zval[i] = part;
-              status |= ST_COLUMN_DROPPED;
-            } else {
-              status |= ST_SLACK_PIVOT;
-              T al = T(0);
-              ATACOM_UNROLL
-              for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
-              zval[i] = al;
-              const T inv = num<T>::div(T(1), sigma);
-              const T bnew = (al - part) * inv;
-              const T c0 = e[0] * inv, c1 = e[1] * inv;  // direction of the new row inside the remaining subspace
+#endif
+          const bool is_soft = (softmask >> i) & 1u;
+          int slot = -1;
+          ATACOM_UNROLL
+          for (int t = 0; t < TMAX; ++t) slot = (srow[t] == i) ? t : slot;
+          const T si = sloc[i];
+          const T ninv_s = (is_soft && si * si > T(0)) ? num<T>::div(T(-1), si) : T(0);
+          // entries of this slack column on the remaining directions (e) and on the pivoted rows (part)
+          T e[RMAX], part;
+          if (is_soft) {
+            T d0 = T(0), d1 = T(0), dp = T(0);
+            if (i < GD) {
               ATACOM_UNROLL
               for (int j = 0; j < n; ++j) {
-                const T d = c0 * Xr[0][j] + c1 * Xr[1][j];
-                xl[j] += bnew * d;
-                Xr[0][j] = c0 * Xr[1][j] - c1 * Xr[0][j];  // what is left: the in-plane normal of the direction
-                Xr[1][j] = T(0);
+                const T a = Aloc[i * n + j];
+                d0 += a * Xr[0][j];
+                d1 += a * Xr[1][j];
+                dp += a * xl[j];
               }
+            } else {
+              const int jd = i - GD;
+              const T a = dloc[jd];
               ATACOM_UNROLL
-              for (int t = 0; t < TMAX; ++t) {
-                const T d = c0 * Zr[0][t] + c1 * Zr[1][t];
-                zl[t] += bnew * d;
-                Zr[0][t] = c0 * Zr[1][t] - c1 * Zr[0][t];
-                Zr[1][t] = T(0);
+              for (int j = 0; j < n; ++j) {
+                d0 += (j == jd) ? a * Xr[0][j] : T(0);
+                d1 += (j == jd) ? a * Xr[1][j] : T(0);
+                dp += (j == jd) ? a * xl[j] : T(0);
               }
-              ++npiv;
-              --rem;
+            }
+            e[0] = d0 * ninv_s;
+            e[1] = d1 * ninv_s;
+            part = dp * ninv_s;
+          } else {
+            e[0] = e[1] = part = T(0);
+            ATACOM_UNROLL
+            for (int t = 0; t < TMAX; ++t) {
+              e[0] = (t == slot) ? Zr[0][t] : e[0];
+              e[1] = (t == slot) ? Zr[1][t] : e[1];
+              part = (t == slot) ? zl[t] : part;
             }
           }
+          const T sigma = num<T>::sqrt(e[0] * e[0] + e[1] * e[1]);
+          testmask |= 1u << i;
+          const bool take = sigma > tol;
+          T al = T(0);
+          ATACOM_UNROLL
+          for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
+          zloc[i] = take ? al : part;
+          status |= take ? ST_SLACK_PIVOT : ST_COLUMN_DROPPED;
+          const T inv = take ? num<T>::div(T(1), sigma) : T(0);
+          const T bnew = (al - part) * inv;
+          // direction of the new row inside the remaining subspace (c0, c1); what is left of the subspace is
+          // its in-plane normal.  Nothing changes when the column is dropped (c = (0, 1) rotation skipped).
+          const T c0 = e[0] * inv, c1 = e[1] * inv;
+          ATACOM_UNROLL
+          for (int j = 0; j < n; ++j) {
+            const T x0 = Xr[0][j], x1 = Xr[1][j];
+            xl[j] += bnew * (c0 * x0 + c1 * x1);
+            Xr[0][j] = take ? (c0 * x1 - c1 * x0) : x0;
+            Xr[1][j] = take ? T(0) : x1;
+          }
+          ATACOM_UNROLL
+          for (int t = 0; t < TMAX; ++t) {
+            const T z0 = Zr[0][t], z1 = Zr[1][t];
+            zl[t] += bnew * (c0 * z0 + c1 * z1);
+            Zr[0][t] = take ? (c0 * z1 - c1 * z0) : z0;
+            Zr[1][t] = take ? T(0) : z1;
+          }
+          npiv += take ? 1 : 0;
+          rem -= take ? 1 : 0;
+#if !ATACOM_ROLL_SLACK
+          }
+#endif
+        }
+        ATACOM_UNROLL
+        for (int i = 0; i < G; ++i) {
+          ztested[i] = (testmask >> i) & 1u;
+          zval[i] = zloc[i];
         }
       }
     }
