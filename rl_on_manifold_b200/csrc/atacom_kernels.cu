@@ -26,8 +26,11 @@ namespace {
 #ifndef ATACOM_STEP_MAX_TPB
 #define ATACOM_STEP_MAX_TPB 448   // largest block of the step kernels: 448 x 144 registers fill one SM
 #endif
-#ifndef ATACOM_MINB
-#define ATACOM_MINB 1    // min resident blocks per SM asked of ptxas for the step kernels
+#ifndef ATACOM_PHASE_BARRIERS
+#define ATACOM_PHASE_BARRIERS 0   // 1: block barriers between the phases of the projection (measured: no gain)
+#endif
+#ifndef ATACOM_STEP_MAXNREG
+#define ATACOM_STEP_MAXNREG 128   // a 448-thread block is allocated as 16 warps: 16 x 32 x 128 = the SM register file
 #endif
 constexpr int TPB = ATACOM_TPB;
 constexpr int STEP_MAX_TPB = ATACOM_STEP_MAX_TPB;
@@ -117,7 +120,7 @@ __device__ __forceinline__ void row_store(float* __restrict__ g, int64_t e, cons
 // stream and the block barriers between its phases keep all warps of the SM in the same code region,
 // so each instruction line is fetched once per SM rather than once per warp.
 template <class Env>
-__global__ void __launch_bounds__(STEP_MAX_TPB, ATACOM_MINB) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
+__global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(STEP_MAX_TPB, ATACOM_MINB) atacom_step_kernel(
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
   float* dbg = (a.w_dbg && valid) ? a.w_dbg + e * (2 * N) : nullptr;
-  const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, true>(P, R, dq, s, al, ddq, so, dbg);
+  const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, ATACOM_PHASE_BARRIERS != 0>(P, R, dq, s, al, ddq, so, dbg);
   if (valid) {
     if (a.status) a.status[e] = st;
     row_store<n>(a.ddq, e, ddq);

@@ -515,110 +515,94 @@ struct Structured {
             Zr[j][t] = acc;
           }
         }
-        // slack columns in order
-#ifndef ATACOM_ROLL_SLACK
-#define ATACOM_ROLL_SLACK 0
-#endif
-        unsigned softmask = 0u, testmask = 0u;
-        T zloc[G1];
+        // Slack columns in order.  Straight-line code (no per-column branches): each of the <= RMAX passes
+        // evaluates every slack column on the remaining directions, takes the first one past the previous
+        // pivot whose remainder exceeds the tolerance, and marks the columns it skipped as dropped.
+        unsigned testmask = 0u;
+        T zloc[G1], ninv[G1];
+        int slot_of[G1];
         ATACOM_UNROLL
         for (int i = 0; i < G; ++i) {
           zloc[i] = T(0);
-          softmask |= soft[i] ? (1u << i) : 0u;
-        }
-#if ATACOM_ROLL_SLACK
-        // rolled: the body stays in the instruction cache; what it indexes dynamically lives in private arrays
-        T Aloc[GD1 * n], dloc[ND1], sloc[G1];
-        ATACOM_UNROLL
-        for (int i = 0; i < GD * n; ++i) Aloc[i] = Ad[i];
-        ATACOM_UNROLL
-        for (int j = 0; j < NDIAG; ++j) dloc[j] = dg[j];
-        ATACOM_UNROLL
-        for (int i = 0; i < G; ++i) sloc[i] = s[i];
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-        for (int i = 0; i < G && rem > 0; ++i) {
-#else
-        const T* Aloc = Ad;
-        const T* dloc = dg;
-        const T* sloc = s;
-        ATACOM_UNROLL
-        for (int i = 0; i < G; ++i) {
-          if (rem > 0) {
-#endif
-          const bool is_soft = (softmask >> i) & 1u;
-          int slot = -1;
+          ninv[i] = (soft[i] && s[i] * s[i] > T(0)) ? num<T>::div(T(-1), s[i]) : T(0);
+          slot_of[i] = -1;
           ATACOM_UNROLL
-          for (int t = 0; t < TMAX; ++t) slot = (srow[t] == i) ? t : slot;
-          const T si = sloc[i];
-          const T ninv_s = (is_soft && si * si > T(0)) ? num<T>::div(T(-1), si) : T(0);
-          // entries of this slack column on the remaining directions (e) and on the pivoted rows (part)
-          T e[RMAX], part;
-          if (is_soft) {
-            T d0 = T(0), d1 = T(0), dp = T(0);
-            if (i < GD) {
-              ATACOM_UNROLL
-              for (int j = 0; j < n; ++j) {
-                const T a = Aloc[i * n + j];
-                d0 += a * Xr[0][j];
-                d1 += a * Xr[1][j];
-                dp += a * xl[j];
+          for (int t = 0; t < TMAX; ++t) slot_of[i] = (srow[t] == i) ? t : slot_of[i];
+        }
+        const T tol2 = tol * tol;
+        int last = -1;
+        ATACOM_UNROLL
+        for (int it = 0; it < RMAX; ++it) {
+          if (rem > 0) {
+            T e0[G1], e1[G1], part[G1];
+            int piv = G;
+            ATACOM_UNROLL
+            for (int i = G - 1; i >= 0; --i) {
+              T a0, a1, ap;
+              if (i < GD) {
+                a0 = gdot(Ad, dg, i, Xr[0]);
+                a1 = gdot(Ad, dg, i, Xr[1]);
+                ap = gdot(Ad, dg, i, xl);
+              } else {
+                const T d = dg[i >= GD ? i - GD : 0];
+                a0 = d * Xr[0][i >= GD ? i - GD : 0];
+                a1 = d * Xr[1][i >= GD ? i - GD : 0];
+                ap = d * xl[i >= GD ? i - GD : 0];
               }
-            } else {
-              const int jd = i - GD;
-              const T a = dloc[jd];
+              T z0 = T(0), z1 = T(0), zp = T(0);
               ATACOM_UNROLL
-              for (int j = 0; j < n; ++j) {
-                d0 += (j == jd) ? a * Xr[0][j] : T(0);
-                d1 += (j == jd) ? a * Xr[1][j] : T(0);
-                dp += (j == jd) ? a * xl[j] : T(0);
+              for (int t = 0; t < TMAX; ++t) {
+                z0 = (t == slot_of[i]) ? Zr[0][t] : z0;
+                z1 = (t == slot_of[i]) ? Zr[1][t] : z1;
+                zp = (t == slot_of[i]) ? zl[t] : zp;
               }
+              e0[i] = soft[i] ? a0 * ninv[i] : z0;
+              e1[i] = soft[i] ? a1 * ninv[i] : z1;
+              part[i] = soft[i] ? ap * ninv[i] : zp;
+              const bool ok = (i > last) && (e0[i] * e0[i] + e1[i] * e1[i] > tol2);
+              piv = ok ? i : piv;
             }
-            e[0] = d0 * ninv_s;
-            e[1] = d1 * ninv_s;
-            part = dp * ninv_s;
-          } else {
-            e[0] = e[1] = part = T(0);
+            T pe0 = T(0), pe1 = T(0), pp = T(0);
+            ATACOM_UNROLL
+            for (int i = 0; i < G; ++i) {
+              const bool skipped = (i > last) && (i < piv);
+              zloc[i] = skipped ? part[i] : zloc[i];
+              testmask |= (skipped || i == piv) ? (1u << i) : 0u;
+              if (skipped) status |= ST_COLUMN_DROPPED;
+              pe0 = (i == piv) ? e0[i] : pe0;
+              pe1 = (i == piv) ? e1[i] : pe1;
+              pp = (i == piv) ? part[i] : pp;
+            }
+            const bool take = piv < G;
+            const T sigma = num<T>::sqrt(pe0 * pe0 + pe1 * pe1);
+            T al = T(0);
+            ATACOM_UNROLL
+            for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
+            ATACOM_UNROLL
+            for (int i = 0; i < G; ++i) zloc[i] = (i == piv) ? al : zloc[i];
+            if (take) status |= ST_SLACK_PIVOT;
+            const T inv = take ? num<T>::div(T(1), sigma) : T(0);
+            const T bnew = (al - pp) * inv;
+            // direction of the new row inside the remaining subspace; what is left is its in-plane normal
+            const T c0 = pe0 * inv, c1 = pe1 * inv;
+            ATACOM_UNROLL
+            for (int j = 0; j < n; ++j) {
+              const T x0 = Xr[0][j], x1 = Xr[1][j];
+              xl[j] += bnew * (c0 * x0 + c1 * x1);
+              Xr[0][j] = take ? (c0 * x1 - c1 * x0) : x0;
+              Xr[1][j] = take ? T(0) : x1;
+            }
             ATACOM_UNROLL
             for (int t = 0; t < TMAX; ++t) {
-              e[0] = (t == slot) ? Zr[0][t] : e[0];
-              e[1] = (t == slot) ? Zr[1][t] : e[1];
-              part = (t == slot) ? zl[t] : part;
+              const T z0 = Zr[0][t], z1 = Zr[1][t];
+              zl[t] += bnew * (c0 * z0 + c1 * z1);
+              Zr[0][t] = take ? (c0 * z1 - c1 * z0) : z0;
+              Zr[1][t] = take ? T(0) : z1;
             }
+            npiv += take ? 1 : 0;
+            rem -= take ? 1 : 0;
+            last = piv;
           }
-          const T sigma = num<T>::sqrt(e[0] * e[0] + e[1] * e[1]);
-          testmask |= 1u << i;
-          const bool take = sigma > tol;
-          T al = T(0);
-          ATACOM_UNROLL
-          for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
-          zloc[i] = take ? al : part;
-          status |= take ? ST_SLACK_PIVOT : ST_COLUMN_DROPPED;
-          const T inv = take ? num<T>::div(T(1), sigma) : T(0);
-          const T bnew = (al - part) * inv;
-          // direction of the new row inside the remaining subspace (c0, c1); what is left of the subspace is
-          // its in-plane normal.  Nothing changes when the column is dropped (c = (0, 1) rotation skipped).
-          const T c0 = e[0] * inv, c1 = e[1] * inv;
-          ATACOM_UNROLL
-          for (int j = 0; j < n; ++j) {
-            const T x0 = Xr[0][j], x1 = Xr[1][j];
-            xl[j] += bnew * (c0 * x0 + c1 * x1);
-            Xr[0][j] = take ? (c0 * x1 - c1 * x0) : x0;
-            Xr[1][j] = take ? T(0) : x1;
-          }
-          ATACOM_UNROLL
-          for (int t = 0; t < TMAX; ++t) {
-            const T z0 = Zr[0][t], z1 = Zr[1][t];
-            zl[t] += bnew * (c0 * z0 + c1 * z1);
-            Zr[0][t] = take ? (c0 * z1 - c1 * z0) : z0;
-            Zr[1][t] = take ? T(0) : z1;
-          }
-          npiv += take ? 1 : 0;
-          rem -= take ? 1 : 0;
-#if !ATACOM_ROLL_SLACK
-          }
-#endif
         }
         ATACOM_UNROLL
         for (int i = 0; i < G; ++i) {
