@@ -214,6 +214,14 @@ def ours(args):
         q, dq, s, alpha = synthetic.device_batch("iiwa", B, 1234 + rank + 1000 * r, dev, N_JOINTS, params)
         sets.append(dict(q=q, dq=dq, s=s, alpha=alpha, ddq=torch.empty_like(q), s_out=torch.empty_like(s)))
     gathered = torch.empty(world * B, n, device=dev) if world > 1 else None
+    fused, fused_note = None, "not attempted"
+    if world > 1 and args.gather == "fused":
+        try:
+            from rl_on_manifold_b200.sharding import SymmetricGather
+            fused = SymmetricGather(B, n)
+            fused_note = "fused peer-store epilogue over NVLink symmetric memory + one device barrier per step"
+        except Exception as exc:
+            fused_note = "fused gather unavailable (%s: %s); NCCL all-gather used" % (type(exc).__name__, exc)
 
     def step(i):
         d = sets[i % ring]
@@ -221,6 +229,10 @@ def ours(args):
                         ddq=d["ddq"], s_out=d["s_out"])
         if world > 1:
             dist.all_gather_into_tensor(gathered, d["ddq"])
+
+    def step_fused(i):
+        d = sets[i % ring]
+        fused.step(d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS, s_out=d["s_out"])
 
     def kernel_only(i):
         d = sets[i % ring]
@@ -258,6 +270,14 @@ def ours(args):
     eager_ms = timed(step, args.steps, args.warmup)
     launches = _lib.launch_count() - launches0 - args.warmup
     total_ms, launch_mode = eager_ms, "eager launches from Python (ctypes)"
+    gather_mode = "single GPU" if world == 1 else "one NCCL all-gather of ddq per step"
+    nccl_ms = eager_ms if world > 1 else None
+    if fused is not None:
+        launches1 = _lib.launch_count()
+        fused_ms = timed(step_fused, args.steps, args.warmup)
+        if fused_ms < total_ms:
+            total_ms, gather_mode = fused_ms, fused_note
+            launches = _lib.launch_count() - launches1 - args.warmup
     kernel_ms = eager_ms if world == 1 else timed(kernel_only, args.steps, args.warmup)
 
     def timed_graph(fn, steps):
@@ -336,8 +356,9 @@ def ours(args):
             steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="f32 (constraint residual in f64)", data="synthetic",
             config=dict(workload=workload_name(world), batch_per_gpu=B, global_batch=world * B,
-                        parallelism="env-shard x%d, one NCCL all-gather of ddq per step" % world if world > 1
-                        else "single GPU",
+                        parallelism="env-shard x%d; %s" % (world, gather_mode) if world > 1 else "single GPU",
+                        gather=fused_note if world > 1 else None,
+                        nccl_all_gather_ms_per_step=(nccl_ms / args.steps) if nccl_ms else None,
                         cold_inputs="ring of %d distinct batches (%.0f MB > 2x L2) rotated every step"
                                     % (ring, ring * B * BYTES_PER_ENV_STEP / 1e6),
                         bytes_per_env_step=BYTES_PER_ENV_STEP, launch=launch_mode,
@@ -368,6 +389,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

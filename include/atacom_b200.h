@@ -34,6 +34,7 @@ extern "C" {
 #define ATACOM_MAX_G 16  /* inequality rows / slacks   */
 #define ATACOM_MAX_C 20  /* F + G                      */
 #define ATACOM_ENV_PARAMS 24
+#define ATACOM_MAX_PEERS 8 /* GPUs of one NVSwitch domain */
 
 enum {
   ATACOM_OK = 0,
@@ -108,6 +109,17 @@ int atacom_planar_step(const float* q, const float* dq, const float* s_in, const
 int atacom_iiwa_step(int n_ctrl_joints, const float* q, const float* dq, const float* s_in, const float* alpha,
                      float* ddq, float* s_out, uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p,
                      void* stream);
+
+/* ---- the same step with the per-step gather fused into its epilogue (multi-GPU) ----
+ * The batch is sharded by environment; every rank needs all projected accelerations after each step.
+ * Instead of a separate all-gather, the kernel stores each environment's ddq row straight into every
+ * rank's gather buffer: peer_ddq[w] is rank w's [world * B, n] buffer mapped into this process (NVLink
+ * peer / symmetric memory; peer_ddq[rank] is the local one), this rank's rows start at row_offset.
+ * ddq (the local [B, n] copy) may be NULL.  The caller synchronises the ranks afterwards (one barrier). */
+int atacom_iiwa_step_gather(int n_ctrl_joints, const float* q, const float* dq, const float* s_in,
+                            const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
+                            const AtacomParams* p, void* stream, float* const* peer_ddq, int world,
+                            int64_t row_offset);
 
 /* ---- AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149): s = sqrt(max(-2 g~, 0)) ----
  * mask (optional, may be NULL): uint8 [B]; only environments with mask != 0 are re-initialised. */

@@ -79,6 +79,11 @@ struct StepArgs {
   uint8_t* status;
   float* w_dbg;
   int64_t B;
+  // fused gather: every rank's [world * B, n] buffer (peer-mapped over NVLink); this rank's rows start at
+  // gather_row0.  n_peers = 0 disables it.
+  float* peer[ATACOM_MAX_PEERS];
+  int64_t gather_row0;
+  int32_t n_peers;
 };
 
 // ------------------------------------------------------------------ row access
@@ -150,8 +155,10 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(StepArgs a, 
   const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, ATACOM_PHASE_BARRIERS != 0>(P, R, dq, s, al, ddq, so, dbg);
   if (valid) {
     if (a.status) a.status[e] = st;
-    row_store<n>(a.ddq, e, ddq);
+    if (a.ddq) row_store<n>(a.ddq, e, ddq);
     if (G > 0) row_store<G1>(a.s_out, e, so);
+    // fused all-gather: store this environment's row straight into every rank's gather buffer
+    for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
   }
 }
 
@@ -351,15 +358,21 @@ int check_common(int64_t B, const AtacomParams* p) {
 
 template <class Env>
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
-                uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream) {
+                uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
+                float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0) {
   int rc = check_common(B, p);
   if (rc) return rc;
   using D = typename Env::D;
   if (B == 0) return ATACOM_OK;
-  if (!q || !dq || !ddq || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
+  if (n_peers < 0 || n_peers > ATACOM_MAX_PEERS || (n_peers > 0 && !peers) || gather_row0 < 0) return ATACOM_ERR_BAD_DIMS;
+  if (!q || !dq || (!ddq && n_peers == 0) || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
-  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B};
+  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers};
+  for (int w = 0; w < n_peers; ++w) {
+    if (!peers[w]) return ATACOM_ERR_NULL_POINTER;
+    a.peer[w] = peers[w];
+  }
   const int tpb = step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   atacom_step_kernel<Env><<<grid, tpb, 0, static_cast<cudaStream_t>(stream)>>>(a, as_params(p));
@@ -511,6 +524,19 @@ int atacom_iiwa_step(int n, const float* q, const float* dq, const float* s_in, 
   return ATACOM_ERR_BAD_DIMS;
 }
 
+int atacom_iiwa_step_gather(int n, const float* q, const float* dq, const float* s_in, const float* alpha,
+                            float* ddq, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p,
+                            void* stream, float* const* peer_ddq, int world, int64_t row_offset) {
+  if (world < 1) return ATACOM_ERR_BAD_DIMS;
+  if (n == 6)
+    return launch_step<IiwaEnv<6>>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq, world,
+                                   row_offset);
+  if (n == 7)
+    return launch_step<IiwaEnv<7>>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq, world,
+                                   row_offset);
+  return ATACOM_ERR_BAD_DIMS;
+}
+
 int atacom_circle_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,
                              const AtacomParams* p, void* stream) {
   return launch_slack_init<CircleEnv>(q, dq, s, mask, B, p, stream);
@@ -600,7 +626,7 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   if (!c || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
-  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B};
+  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define X(n_, F_, G_)                                                                             \
   if (n == n_ && F == F_ && G == G_)                                                              \

@@ -87,6 +87,32 @@ def step(family, q, dq, s, alpha, params, *, n_ctrl_joints=6, ddq=None, s_out=No
     return ddq, s_out
 
 
+def iiwa_step_gather(q, dq, s, alpha, params, peer_ptrs, world, row_offset, *, n_ctrl_joints=6, ddq=None,
+                     s_out=None, status=None):
+    """`step("iiwa", ...)` with the multi-GPU gather fused into the kernel epilogue: every environment's ddq row
+    is stored into each rank's [world * B, n] gather buffer (`peer_ptrs`: ctypes array of `world` device pointers,
+    peer-mapped; see sharding.SymmetricGather).  Returns s_out."""
+    n, F, G = family_dims("iiwa", n_ctrl_joints)
+    B = q.shape[0]
+    _check(q, "q", B, n)
+    _check(dq, "dq", B, n)
+    _check(s, "s", B, G)
+    _check(alpha, "alpha", B, _alpha_dim(params, n, F))
+    if s_out is None:
+        s_out = torch.empty_like(s)
+    _check(s_out, "s_out", B, G)
+    if ddq is not None:
+        _check(ddq, "ddq", B, n)
+    if status is not None:
+        _check(status, "status", B, None, torch.uint8)
+    with torch.cuda.device(q.device):
+        rc = _lib.lib.atacom_iiwa_step_gather(n, _ptr(q), _ptr(dq), _ptr(s), _ptr(alpha), _ptr(ddq), _ptr(s_out),
+                                              _ptr(status), B, ctypes.byref(params), _stream(q), peer_ptrs, world,
+                                              row_offset)
+    _lib.check(rc)
+    return s_out
+
+
 def slack_init(family, q, dq, params, *, n_ctrl_joints=6, s=None, mask=None):
     """AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149)."""
     n, F, G = family_dims(family, n_ctrl_joints)

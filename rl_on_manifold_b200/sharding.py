@@ -4,6 +4,8 @@ The projection has no cross-environment term (atacom.py:123-139), so rank r of W
 block [lo_r, hi_r) of the environment index and its slices of q, dq, s, alpha, ddq; the slack state `s`
 never leaves its rank.  The only exchange is one all-gather of the projected accelerations
 ddq[B/W, n] per step, issued on the stream the kernel ran on."""
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -50,3 +52,45 @@ class EnvShard:
             lo, hi = shard_bounds(self.global_B, r, self.world)
             out[lo:hi] = part[:hi - lo]
         return out
+
+
+class SymmetricGather:
+    """Gather targets for the fused epilogue of `atacom_iiwa_step_gather`.
+
+    Each rank owns `buffers` [world * local_B, n] fp32 tensors in NVLink symmetric memory
+    (torch.distributed._symmetric_memory); after the rendezvous every rank holds peer-mapped pointers to all
+    of them.  The step kernel stores its shard's rows straight into every rank's buffer (P2P stores over
+    NVLink / NVSwitch), so the per-step all-gather costs no extra launch and no extra pass over HBM; one
+    device-side barrier on the kernel's stream then publishes the step.  Buffers alternate between steps so
+    that a rank still reading step i cannot be overwritten by a peer already writing step i + 1.
+    """
+
+    def __init__(self, local_B, n, group=None, buffers=2):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("fused gather supports one NVSwitch domain (<= 8 ranks)")
+        self.local_B, self.n = local_B, n
+        name = group.group_name
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.bufs, self.handles, self.ptrs = [], [], []
+        for _ in range(buffers):
+            t = symm_mem.empty(self.world * local_B, n, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(t, name)
+            self.bufs.append(t)
+            self.handles.append(hdl)
+            self.ptrs.append((ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs]))
+        self._i = 0
+
+    def step(self, q, dq, s, alpha, params, *, n_ctrl_joints=6, s_out=None, status=None):
+        """Project this rank's shard and gather: returns (gathered ddq [world * local_B, n], s_out)."""
+        from . import projection
+        b = self._i % len(self.bufs)
+        self._i += 1
+        s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
+                                            self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
+                                            status=status)
+        self.handles[b].barrier()
+        return self.bufs[b], s_out
