@@ -27,6 +27,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define ATACOM_HD __host__ __device__ __forceinline__
 #define ATACOM_UNROLL _Pragma("unroll")
@@ -84,6 +86,28 @@ template <> struct num<double> {
   static ATACOM_HD double div(double a, double b) { return a / b; }
   static ATACOM_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
 };
+
+// float <-> double conversion of a run-time value.  The library is compiled with --ftz=true, under which a
+// plain cast becomes a flush (FMUL / DSETP) plus the conversion; the exact single-instruction cvt is what the
+// mixed-precision code wants (fp32 denormals do not occur in this data).
+template <typename To, typename From>
+ATACOM_HD To cvt(From x) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (std::is_same<To, double>::value && std::is_same<From, float>::value) {
+    double y;
+    asm("cvt.f64.f32 %0, %1;" : "=d"(y) : "f"(x));
+    return y;
+  } else if constexpr (std::is_same<To, float>::value && std::is_same<From, double>::value) {
+    float y;
+    asm("cvt.rn.f32.f64 %0, %1;" : "=f"(y) : "d"(x));
+    return y;
+  } else {
+    return static_cast<To>(x);
+  }
+#else
+  return static_cast<To>(x);
+#endif
+}
 
 template <int N_, int F_, int G_>
 struct Dims {

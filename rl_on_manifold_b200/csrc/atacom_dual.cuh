@@ -1,0 +1,403 @@
+// Dual (covariance-form) projection: the hot path of the step kernels.
+//
+// Same result as project_dense (atacom_core.cuh) — w_mn = -Jc^+ r and w_null = Nc alpha with
+// the canonical column-ordered null basis and the reference's tolerance-RREF
+// (atacom/atacom.py:127-133, atacom/utils/null_space_coordinate.py:8-26,40-79) — computed
+// through the block structure  Jc = [[A_f, 0], [A_g, diag(s)]]  on the DUAL side, where nothing
+// is ever divided by a slack variable, so soft rows, stiff rows (s_i -> 0) and active
+// constraints (s_i = 0) are one uniform, branch-free code path:
+//
+//  (1) a trailing inequality row with a diagonal Jacobian (joint limit: d_j x_j + s_j z_j = rho_j)
+//      is absorbed exactly by a change of coordinates in its (x_j, z_j) plane:
+//          x_j = mu_j + sigma_j t_j,  z_j = zeta_j - gamma_j t_j,
+//          (sigma_j, gamma_j) = (s_j, d_j) / sqrt(d_j^2 + s_j^2),
+//      an isometry from the free coordinate t_j onto the row's solution line;
+//  (2) the m = F + GD dense rows become  B t + S_d z_d = rho~  with  B = A_d diag(sigma); their
+//      Gram matrix  H = B B^T + S_d^2  (m x m, SPD whenever Jc has full row rank) is factored
+//      H = L L^T and the minimum-norm solution is  t = B^T lambda, z_d = S_d lambda,
+//      lambda = H^-1 rho~;
+//  (3) the x-x block of the projector onto null(Jc) is  Gx = Sigma^1/2 (I - Y^T Y) Sigma^1/2
+//      with  Y = L^-1 B;
+//  (4) the canonical basis (oracle/nullspace.py:canonical_null_basis) is the Cholesky
+//      factorisation of the projector in column order, skipping a column whose pivot is
+//      <= tol: on the x columns that is a skip-Cholesky of Gx.  The RREF multipliers beta
+//      (forward substitution) give the x entries of w_null directly — a dropped column keeps
+//      only the rows pivoted before it, which is what the upper-triangular storage holds;
+//  (5,6) the slack entries are those of the null vector  v* = Pi u,  u = sum_r theta_r e_{c_r},
+//      theta = V_p^-1 beta, again through the dual:  lambda* = H^-1 B g,  z_d = -S_d lambda*,
+//      t* = g - B^T lambda*,  z_diag = -gamma t*;
+//  (7) if one pivot is still missing after the x columns (an active constraint took a
+//      direction away from x), the remaining null direction is  (nu, -A_g nu / s)  with nu
+//      supported on the two (F = 1) / one (F = 0) unpivoted x columns; the first slack column
+//      whose entry exceeds tol becomes the coordinate.  Two or more missing pivots, or F > 1,
+//      return ST_DENSE_PATH and the caller runs the general structured / dense path.
+//
+// All arithmetic is in R (double on the device: B200 runs FP64 at half the FP32 rate and the
+// dual Gram matrix squares cond(Jc)); ~1.0 kFLOP per iiwa environment, no data-dependent
+// branch before (7).
+#pragma once
+
+#include "atacom_core.cuh"
+
+namespace atacom {
+
+// 1 / sqrt(x) for x inside the fp32 range (every use below is guarded): fp32 MUFU.RSQ seed and one
+// third-order correction in R, 8 instructions and no slow path; ::rsqrt(double) costs ~27 with a call.
+template <typename R>
+ATACOM_HD R dual_rsqrt(R x) {
+#if defined(__CUDA_ARCH__)
+  float yf;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(cvt<float>(x)));
+  const R y = cvt<R>(yf);
+  const R e = ::fma(-x * y, y, R(1));               // 1 - x y^2 ~ 1e-7
+  return ::fma(y, ::fma(R(0.375), e, R(0.5)) * e, y);   // y (1 + e/2 + 3 e^2 / 8): error O(e^3)
+#else
+  return R(1) / ::sqrt(x);
+#endif
+}
+constexpr double DUAL_TINY = 1e-24;   // floor of every rsqrt argument: squares of fp32 data below it are zero here
+
+// Per-environment scratch of the dual projection.  LocalStore: a plain array (registers / local
+// memory; the host build and the small environments).  SharedStore: the environment's column of a
+// [SIZE][STRIDE] shared-memory array, one environment per thread — conflict-free, and it takes the
+// two big operands (Y: m x n, L: m(m+1)/2) out of the register budget of the iiwa kernels.
+template <typename R, int SIZE>
+struct LocalStore {
+  R v[SIZE > 0 ? SIZE : 1];
+  ATACOM_HD R get(int i) const { return v[i]; }
+  ATACOM_HD void set(int i, R x) { v[i] = x; }
+};
+template <typename R, int STRIDE>
+struct SharedStore {
+  R* base;   // &array[0][threadIdx.x]
+  // volatile: a plain access lets the compiler forward the stored value to the later load through a
+  // register, i.e. keep the operand in the register file after all (and spill it to local memory)
+  ATACOM_HD R get(int i) const { return *static_cast<const volatile R*>(base + i * STRIDE); }
+  ATACOM_HD void set(int i, R x) { *static_cast<volatile R*>(base + i * STRIDE) = x; }
+};
+
+template <typename R, class D, int NDIAG>
+struct Dual {
+  static constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
+  static constexpr int GD = G - NDIAG;  // dense inequality rows
+  static constexpr int m = F + GD;      // dense rows (equalities first)
+  static constexpr int M1 = at_least_1<m>::value, K1 = at_least_1<k>::value, G1 = at_least_1<G>::value;
+  static constexpr int Y_SIZE = m * n, L_SIZE = m * (m + 1) / 2;
+  static_assert(NDIAG <= n && NDIAG <= G, "diagonal rows: row GD + j has its single entry in column j");
+  static constexpr ATACOM_HD int lidx(int i, int l) { return i * (i - 1) / 2 + l; }   // strictly lower part of L
+  static constexpr int LI0 = m * (m - 1) / 2;                                        // then 1 / diag(L)
+
+  // Y: on entry the m x n dense rows of A (row-major, equalities first), overwritten; Ls: scratch for L.
+  // dg: NDIAG diagonal entries, s: G, r: C (rows ordered equality, dense inequality, diagonal
+  // inequality), alpha: k.  w_mn (type W), w_null (type R): N each.
+  template <class YS, class LS, typename W>
+  static ATACOM_HD uint8_t project(YS& Y, LS& Ls, const R* dg, const R* s, const R* r, const R* alpha, R tol,
+                                   bool want_null, W* w_mn, R* w_null) {
+    uint8_t status = 0;
+
+    // ---- (1) diagonal rows -> coordinates t_j
+    R sig[n], gam[n], mu[n], zeta[n];
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) {
+      sig[j] = R(1);
+      gam[j] = R(0);
+      mu[j] = R(0);
+      zeta[j] = R(0);
+      if (j < NDIAG) {
+        const R d = dg[j < NDIAG ? j : 0], sj = s[GD + (j < NDIAG ? j : 0)];
+        const R den = d * d + sj * sj;
+        if (den > R(DUAL_TINY)) {
+          const R rs = dual_rsqrt(den);
+          const R rho = -r[F + GD + (j < NDIAG ? j : 0)] * rs;
+          sig[j] = sj * rs;
+          gam[j] = d * rs;
+          mu[j] = rho * gam[j];
+          zeta[j] = rho * sig[j];
+        } else {
+          status |= ST_RANK_DEFICIENT;  // all-zero row of Jc
+        }
+      }
+    }
+
+    // ---- (2) dense rows, one column of A at a time: rho~ = -r - A mu, B = A diag(sigma) (stored back),
+    // H = B B^T + S_d^2 accumulated as rank-1 updates
+    R L[M1][M1], li[M1], u[M1];
+    ATACOM_UNROLL
+    for (int i = 0; i < m; ++i) {
+      u[i] = -r[i];
+      ATACOM_UNROLL
+      for (int l = 0; l <= i; ++l) L[i][l] = (l == i && i >= F) ? s[i >= F ? i - F : 0] * s[i >= F ? i - F : 0] : R(0);
+    }
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) {
+      R bj[M1];
+      ATACOM_UNROLL
+      for (int i = 0; i < m; ++i) {
+        const R a = Y.get(i * n + j);
+        u[i] -= a * mu[j];
+        bj[i] = (j < NDIAG) ? a * sig[j] : a;
+        if (j < NDIAG) Y.set(i * n + j, bj[i]);
+      }
+      ATACOM_UNROLL
+      for (int i = 0; i < m; ++i) {
+        ATACOM_UNROLL
+        for (int l = 0; l <= i; ++l) L[i][l] += bj[i] * bj[l];
+      }
+    }
+    // H = L L^T (in place), li = 1 / diag(L)
+    ATACOM_UNROLL
+    for (int i = 0; i < m; ++i) {
+      ATACOM_UNROLL
+      for (int l = 0; l < i; ++l) {
+        R v = L[i][l];
+        ATACOM_UNROLL
+        for (int p = 0; p < l; ++p) v -= L[i][p] * L[l][p];
+        L[i][l] = v * li[l];
+      }
+      R d = L[i][i];
+      const R d0 = d;
+      ATACOM_UNROLL
+      for (int p = 0; p < i; ++p) d -= L[i][p] * L[i][p];
+      if (d > R(512) * num<R>::eps() * d0 && d > R(DUAL_TINY)) {
+        li[i] = dual_rsqrt(d);
+      } else {  // dependent row of Jc: dropped from the solve, flagged
+        status |= ST_RANK_DEFICIENT;
+        li[i] = R(0);
+      }
+    }
+    // u = L^-1 rho~, lambda = L^-T u;  B^T lambda = Y^T u is picked up while Y is formed below
+    ATACOM_UNROLL
+    for (int i = 0; i < m; ++i) {
+      R acc = u[i];
+      ATACOM_UNROLL
+      for (int l = 0; l < i; ++l) acc -= L[i][l] * u[l];
+      u[i] = acc * li[i];
+    }
+    {
+      R lam[M1];
+      ATACOM_UNROLL
+      for (int i = m - 1; i >= 0; --i) {
+        R acc = u[i];
+        ATACOM_UNROLL
+        for (int l = i + 1; l < m; ++l) acc -= L[l][i] * lam[l];
+        lam[i] = acc * li[i];
+      }
+      ATACOM_UNROLL
+      for (int i = 0; i < G; ++i) {
+        if (i < GD) w_mn[n + i] = cvt<W>(s[i] * lam[F + (i < GD ? i : 0)]);
+        w_null[n + i] = R(0);
+      }
+    }
+
+    // ---- (3a) Y = L^-1 B, one column at a time (stored back); t = Y^T u
+    const bool null_part = want_null && k > 0;
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) {
+      R yj[M1];
+      R t = R(0);
+      ATACOM_UNROLL
+      for (int i = 0; i < m; ++i) {
+        R v = Y.get(i * n + j);
+        ATACOM_UNROLL
+        for (int l = 0; l < i; ++l) v -= L[i][l] * yj[l];
+        yj[i] = v * li[i];
+        t += yj[i] * u[i];
+        if (null_part) Y.set(i * n + j, yj[i]);
+      }
+      w_mn[j] = cvt<W>((j < NDIAG) ? mu[j] + sig[j] * t : t);
+      if (j < NDIAG) w_mn[n + GD + j] = cvt<W>(zeta[j] - gam[j] * t);
+      w_null[j] = R(0);
+    }
+    if (!null_part) return status;
+    ATACOM_UNROLL
+    for (int i = 0; i < m; ++i) {
+      Ls.set(LI0 + i, li[i]);
+      ATACOM_UNROLL
+      for (int l = 0; l < i; ++l) Ls.set(lidx(i, l), L[i][l]);
+    }
+
+    // ---- (3b) Gx = Sigma^1/2 (I - Y^T Y) Sigma^1/2 (upper triangle), one row of Y at a time
+    R Gx[n][n];
+    ATACOM_UNROLL
+    for (int a = 0; a < n; ++a) {
+      ATACOM_UNROLL
+      for (int b = a; b < n; ++b) Gx[a][b] = (a == b) ? R(1) : R(0);
+    }
+    ATACOM_UNROLL
+    for (int i = 0; i < m; ++i) {
+      R yi[n];
+      ATACOM_UNROLL
+      for (int j = 0; j < n; ++j) yi[j] = Y.get(i * n + j);
+      ATACOM_UNROLL
+      for (int a = 0; a < n; ++a) {
+        ATACOM_UNROLL
+        for (int b = a; b < n; ++b) Gx[a][b] -= yi[a] * yi[b];
+      }
+    }
+    ATACOM_UNROLL
+    for (int a = 0; a < n; ++a) {
+      ATACOM_UNROLL
+      for (int b = a; b < n; ++b) {
+        if (a < NDIAG) Gx[a][b] *= sig[a];
+        if (b < NDIAG) Gx[a][b] *= sig[b];
+      }
+    }
+
+    // ---- (4) skip-Cholesky of Gx in column order with the rref tolerance, in place; row c of the basis is
+    // stored by pivot COLUMN (zero row for a skipped column), so every loop range is static.
+    R (&Vc)[n][n] = Gx;
+    R vinv[n], bcol[n];
+    bool take[n];
+    int npiv = 0;
+    ATACOM_UNROLL
+    for (int c = 0; c < n; ++c) {
+      const R d = Gx[c][c];
+      const bool tested = npiv < k;
+      const bool tk = tested && (d > tol * tol) && (d > R(DUAL_TINY));
+      const R inv = tk ? dual_rsqrt(d) : R(0);
+      take[c] = tk;
+      vinv[c] = inv;
+      if (tested && !tk) status |= ST_COLUMN_DROPPED;
+      ATACOM_UNROLL
+      for (int b = c; b < n; ++b) Vc[c][b] = Gx[c][b] * inv;
+      ATACOM_UNROLL
+      for (int a = c + 1; a < n; ++a) {
+        ATACOM_UNROLL
+        for (int b = a; b < n; ++b) Gx[a][b] -= Vc[c][a] * Vc[c][b];
+      }
+      R part = R(0);
+      ATACOM_UNROLL
+      for (int cp = 0; cp < c; ++cp) part += bcol[cp] * Vc[cp][c];
+      R al = R(0);
+      ATACOM_UNROLL
+      for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
+      bcol[c] = (al - part) * inv;        // 0 for a skipped column
+      w_null[c] = tk ? al : part;         // pivot: alpha; dropped / untested: rows pivoted before it
+      npiv += tk ? 1 : 0;
+    }
+
+    // ---- (5) theta = V_p^-1 beta (back substitution), g = Sigma^1/2 theta
+    R gt[n];
+    ATACOM_UNROLL
+    for (int c = n - 1; c >= 0; --c) {
+      R acc = bcol[c];
+      ATACOM_UNROLL
+      for (int b = c + 1; b < n; ++b) acc -= Vc[c][b] * gt[b];
+      gt[c] = acc * vinv[c];
+    }
+    ATACOM_UNROLL
+    for (int j = 0; j < NDIAG; ++j) gt[j] *= sig[j];
+
+    // ---- (6) slack entries of v* = Pi u:  y = Y g,  t* = g - Y^T y,  lambda* = L^-T y
+    R yv[M1], ts[n];
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) ts[j] = gt[j];
+    ATACOM_UNROLL
+    for (int i = 0; i < m; ++i) {
+      R yi[n];
+      R acc = R(0);
+      ATACOM_UNROLL
+      for (int j = 0; j < n; ++j) {
+        yi[j] = Y.get(i * n + j);
+        acc += yi[j] * gt[j];
+      }
+      yv[i] = acc;
+      ATACOM_UNROLL
+      for (int j = 0; j < NDIAG; ++j) ts[j] -= yi[j] * acc;
+    }
+    ATACOM_UNROLL
+    for (int j = 0; j < NDIAG; ++j) w_null[n + GD + j] = -gam[j] * ts[j];
+    ATACOM_UNROLL
+    for (int i = m - 1; i >= 0; --i) {
+      R acc = yv[i];
+      ATACOM_UNROLL
+      for (int l = i + 1; l < m; ++l) acc -= Ls.get(lidx(l, i)) * yv[l];
+      yv[i] = acc * Ls.get(LI0 + i);
+    }
+    ATACOM_UNROLL
+    for (int i = 0; i < GD; ++i) w_null[n + i] = -s[i] * yv[F + i];
+    if (npiv == k) return status;
+
+    // ---- (7) one slack column becomes a tangent-space coordinate
+    if (k - npiv > 1 || F > 1) return status | ST_DENSE_PATH;
+    // remaining null direction in the free coordinates: tau supported on the unpivoted columns with
+    // B_f tau = 0; its entries are x_j = sigma_j tau_j, z_diag,j = -gamma_j tau_j, z_dense,i = -(b_i . tau) / s_i.
+    // The equality row of Y is B_f / L_00: same direction.
+    R nu[n];
+    {
+      R a1 = R(0), a2 = R(0);
+      int cnt = 0;
+      if (F == 1) {
+        ATACOM_UNROLL
+        for (int c = 0; c < n; ++c) {
+          const R y0 = Y.get(c);
+          if (!take[c]) {
+            a1 = (cnt == 0) ? y0 : a1;
+            a2 = (cnt == 1) ? y0 : a2;
+            ++cnt;
+          }
+        }
+      }
+      cnt = 0;
+      ATACOM_UNROLL
+      for (int c = 0; c < n; ++c) {
+        nu[c] = take[c] ? R(0) : (F == 1 ? (cnt == 0 ? a2 : -a1) : R(1));
+        cnt += take[c] ? 0 : 1;
+      }
+    }
+    R e[G1], yt[M1];
+    R nrm2 = R(0);
+    ATACOM_UNROLL
+    for (int c = 0; c < n; ++c) nrm2 += nu[c] * nu[c];
+    ATACOM_UNROLL
+    for (int l = 0; l < m; ++l) {   // B = L Y  =>  b_i . tau = sum_{l <= i} L[i][l] (Y[l] . tau)
+      R acc = R(0);
+      ATACOM_UNROLL
+      for (int j = 0; j < n; ++j) acc += Y.get(l * n + j) * nu[j];
+      yt[l] = acc;
+    }
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) {
+      if (i < GD) {
+        const int ri = F + (i < GD ? i : 0);
+        const R lii = Ls.get(LI0 + ri);
+        R an = (lii > R(0)) ? yt[ri] / lii : R(0);
+        ATACOM_UNROLL
+        for (int l = 0; l < ri; ++l) an += Ls.get(lidx(ri, l)) * yt[l];
+        const R s2 = s[i] * s[i];
+        const R rs = dual_rsqrt(s2 > R(DUAL_TINY) ? s2 : R(DUAL_TINY));   // 1 / |s_i|, s_i = 0 -> the limit
+        e[i] = (s[i] < R(0) ? an : -an) * rs;
+        nrm2 += e[i] * e[i];
+      } else {
+        e[i] = -gam[i >= GD ? i - GD : 0] * nu[i >= GD ? i - GD : 0];   // sigma^2 + gamma^2 = 1: already in nrm2
+      }
+    }
+    const R rn = dual_rsqrt(nrm2);
+    int ip = G;
+    ATACOM_UNROLL
+    for (int i = G - 1; i >= 0; --i) {
+      e[i] *= rn;
+      ip = (num<R>::abs(e[i]) > tol) ? i : ip;
+    }
+    if (ip == G) return status | ST_RANK_DEFICIENT;
+    status |= ST_SLACK_PIVOT;
+    if (ip > 0) status |= ST_COLUMN_DROPPED;
+    R ep = R(0), zp = R(0), al = R(0);
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) {
+      ep = (i == ip) ? e[i] : ep;
+      zp = (i == ip) ? w_null[n + i] : zp;
+    }
+    ATACOM_UNROLL
+    for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
+    const R bl = (al - zp) / ep;   // beta of the new row times the sign of its pivot entry
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) {
+      const R v = w_null[n + i];
+      w_null[n + i] = (i == ip) ? al : (i > ip ? v + bl * e[i] : v);
+    }
+    return status;
+  }
+};
+
+}  // namespace atacom

@@ -16,6 +16,7 @@
 
 #include "atacom_core.cuh"
 #include "atacom_structured.cuh"
+#include "atacom_dual.cuh"
 
 namespace atacom {
 
@@ -40,13 +41,23 @@ struct ParamsT {
 enum { VARIANT_ATACOM = 0, VARIANT_EC = 1 };
 enum { BIAS_JDOT_QDOT = 0, BIAS_OMEGA_X_V = 1 };
 
-template <typename T, typename HP, class D>
+// The environment functors hand their results to a SINK, one value at a time and as early as it is
+// known: put_c(i, c_i(q)), put_Jdq(i, (J dq)_i), put_J(i, j, J_ij), put_b(i, b_i(q, dq)), i over
+// the C rows (equalities first).  RawConstraints is the sink that just keeps them (JT_ is the type the
+// Jacobian entries are kept in); DualSink (below) folds them into the operands of the dual projection on
+// the fly, so nothing of size C x n is ever live in registers.
+template <typename T, typename HP, class D, typename JT_ = T>
 struct RawConstraints {
+  using JT = JT_;
   static constexpr int C1 = at_least_1<D::C>::value;
-  HP c[C1];       // c(q)
-  HP Jdq[C1];     // J(q) dq
-  T J[C1][D::n];  // J(q)
-  T b[C1];        // b(q, dq)
+  HP c[C1];        // c(q)
+  HP Jdq[C1];      // J(q) dq
+  JT J[C1][D::n];  // J(q)
+  T b[C1];         // b(q, dq)
+  ATACOM_HD void put_c(int i, HP v) { c[i] = v; }
+  ATACOM_HD void put_Jdq(int i, HP v) { Jdq[i] = v; }
+  ATACOM_HD void put_J(int i, int j, JT v) { J[i][j] = v; }
+  ATACOM_HD void put_b(int i, T v) { b[i] = v; }
 };
 
 // sin and cos of a joint angle in double precision, ~1e-16 absolute: Cody-Waite reduction by
@@ -86,19 +97,20 @@ ATACOM_HD void sincos_hp(double x, double* sn, double* cs) {
 struct CircleEnv {
   using D = Dims<2, 1, 1>;
   static constexpr int NDIAG = 0;   // trailing inequality rows with a diagonal Jacobian
-  template <typename T, typename HP>
-  static ATACOM_HD void eval(const ParamsT<T>&, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
+  template <typename T, typename HP, class Out>
+  static ATACOM_HD void eval(const ParamsT<T>&, const T* q, const T* dq, Out& R) {
+    using JT = typename Out::JT;
     const HP q0 = q[0], q1 = q[1], d0 = dq[0], d1 = dq[1];
-    R.c[0] = q0 * q0 + q1 * q1 - HP(1);
-    R.Jdq[0] = HP(2) * (q0 * d0 + q1 * d1);
-    R.J[0][0] = T(2) * q[0];
-    R.J[0][1] = T(2) * q[1];
-    R.b[0] = T(2) * dq[0] * dq[0] + T(2) * dq[1] * dq[1];
-    R.c[1] = -q1 - HP(0.5);
-    R.Jdq[1] = -d1;
-    R.J[1][0] = T(0);
-    R.J[1][1] = T(-1);
-    R.b[1] = T(0);
+    R.put_c(0, q0 * q0 + q1 * q1 - HP(1));
+    R.put_Jdq(0, HP(2) * (q0 * d0 + q1 * d1));
+    R.put_J(0, 0, JT(2) * JT(q[0]));
+    R.put_J(0, 1, JT(2) * JT(q[1]));
+    R.put_b(0, T(2) * dq[0] * dq[0] + T(2) * dq[1] * dq[1]);
+    R.put_c(1, -q1 - HP(0.5));
+    R.put_Jdq(1, -d1);
+    R.put_J(1, 0, JT(0));
+    R.put_J(1, 1, JT(-1));
+    R.put_b(1, T(0));
   }
 };
 
@@ -107,8 +119,9 @@ struct CircleEnv {
 struct PlanarEnv {
   using D = Dims<3, 0, 6>;
   static constexpr int NDIAG = 3;   // joint-limit rows q_j^2 - qmax_j^2
-  template <typename T, typename HP>
-  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
+  template <typename T, typename HP, class Out>
+  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, Out& R) {
+    using JT = typename Out::JT;
     HP th = HP(0), om = HP(0);
     HP lc[3], ls[3], w[3];
     ATACOM_UNROLL
@@ -141,26 +154,26 @@ struct PlanarEnv {
       by = T(om * vx);
     }
     const HP hl = HP(P.env[8]), hw = HP(P.env[9]);
-    R.c[0] = -x - hl;
-    R.c[1] = -y - hw;
-    R.c[2] = y - hw;
-    R.Jdq[0] = -vx;
-    R.Jdq[1] = -vy;
-    R.Jdq[2] = vy;
-    R.b[0] = -bx;
-    R.b[1] = -by;
-    R.b[2] = by;
+    R.put_c(0, -x - hl);
+    R.put_c(1, -y - hw);
+    R.put_c(2, y - hw);
+    R.put_Jdq(0, -vx);
+    R.put_Jdq(1, -vy);
+    R.put_Jdq(2, vy);
+    R.put_b(0, -bx);
+    R.put_b(1, -by);
+    R.put_b(2, by);
     ATACOM_UNROLL
     for (int j = 0; j < 3; ++j) {
-      R.J[0][j] = -T(Jx[j]);
-      R.J[1][j] = -T(Jy[j]);
-      R.J[2][j] = T(Jy[j]);
+      R.put_J(0, j, -JT(Jx[j]));
+      R.put_J(1, j, -JT(Jy[j]));
+      R.put_J(2, j, JT(Jy[j]));
       const HP qm = HP(P.env[5 + j]), qj = q[j];
-      R.c[3 + j] = qj * qj - qm * qm;
-      R.Jdq[3 + j] = HP(2) * qj * HP(dq[j]);
-      R.b[3 + j] = T(2) * dq[j] * dq[j];
+      R.put_c(3 + j, qj * qj - qm * qm);
+      R.put_Jdq(3 + j, HP(2) * qj * HP(dq[j]));
+      R.put_b(3 + j, T(2) * dq[j] * dq[j]);
       ATACOM_UNROLL
-      for (int i = 0; i < 3; ++i) R.J[3 + j][i] = (i == j) ? T(2) * q[j] : T(0);
+      for (int i = 0; i < 3; ++i) R.put_J(3 + j, i, (i == j) ? JT(2) * JT(q[j]) : JT(0));
     }
   }
 };
@@ -178,7 +191,7 @@ template <typename T> ATACOM_HD Vec3<T> cross(const Vec3<T>& a, const Vec3<T>& b
 template <typename T> ATACOM_HD Vec3<T> operator+(const Vec3<T>& a, const Vec3<T>& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 template <typename T> ATACOM_HD Vec3<T> operator-(const Vec3<T>& a, const Vec3<T>& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 template <typename T> ATACOM_HD Vec3<T> operator*(T s, const Vec3<T>& a) { return {s * a.x, s * a.y, s * a.z}; }
-template <typename T, typename U> ATACOM_HD Vec3<T> vcast(const Vec3<U>& a) { return {T(a.x), T(a.y), T(a.z)}; }
+template <typename T, typename U> ATACOM_HD Vec3<T> vcast(const Vec3<U>& a) { return {cvt<T>(a.x), cvt<T>(a.y), cvt<T>(a.z)}; }
 template <typename T> ATACOM_HD T dot(const Vec3<T>& a, const Vec3<T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 template <int NJ>
@@ -187,17 +200,22 @@ struct IiwaEnv {
   using D = Dims<NJ, 1, 5 + NJ>;
   static constexpr int NDIAG = NJ;  // joint-limit rows q_j^2 - qmax_j^2
 
-  template <typename T, typename HP>
-  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, RawConstraints<T, HP, D>& R) {
+  template <typename T, typename HP, class Out>
+  static ATACOM_HD void eval(const ParamsT<T>& P, const T* q, const T* dq, Out& R) {
+    using JT = typename Out::JT;
     // joint placement in the parent frame: translation along z or along y
     constexpr double len[7] = {0.1575, 0.2025, 0.2045, 0.2155, 0.1845, 0.2155, 0.081};
     constexpr int along_y[7] = {0, 0, 1, 0, 1, 0, 1};
     constexpr int rot_kind[7] = {0, 1, 1, 2, 1, 2, 1};  // 0: I, 1: A, 2: Bm (see header comment)
     constexpr double tip_len = 0.585;                   // env_base.py:148-149
 
-    // ---- geometry in HP: frame axes ex, ey, ez and origin o in the robot base frame
+    // ---- one forward pass over the chain.  Geometry in HP: frame axes ex, ey, ez and origin o in the
+    // robot base frame.  Riding along in T (velocity-product terms are not amplified by K_c): the
+    // zero-joint-acceleration recursion for the acceleration of the link-4 / link-7 origins and the tip.
     Vec3<HP> ex{HP(1), HP(0), HP(0)}, ey{HP(0), HP(1), HP(0)}, ez{HP(0), HP(0), HP(1)}, o{HP(0), HP(0), HP(0)};
     Vec3<HP> zax[7], org[7];
+    Vec3<T> w{T(0), T(0), T(0)}, al = w, ao = w, oprev = w;
+    Vec3<T> acc4 = w, acc7 = w, w4 = w, w7 = w;
     ATACOM_UNROLL
     for (int i = 0; i < 7; ++i) {
       o = o + HP(len[i]) * (along_y[i] ? ey : ez);
@@ -207,7 +225,7 @@ struct IiwaEnv {
       else { nx = ex; ny = ez; nz = HP(-1) * ey; }
       if (i < NJ) {         // R <- R * Rz(q_i)
         double sn, cs;
-        sincos_hp(static_cast<double>(q[i < NJ ? i : 0]), &sn, &cs);
+        sincos_hp(cvt<double>(q[i < NJ ? i : 0]), &sn, &cs);
         ex = HP(cs) * nx + HP(sn) * ny;
         ey = HP(cs) * ny - HP(sn) * nx;
       } else {
@@ -217,50 +235,61 @@ struct IiwaEnv {
       ez = nz;
       zax[i] = ez;
       org[i] = o;
-    }
-    const Vec3<HP> tip = o + HP(tip_len) * ez;
-
-    // world-aligned linear Jacobians, column j = z_j x (p - o_j); J dq accumulated in HP
-    Vec3<HP> vt{HP(0), HP(0), HP(0)}, v4 = vt, v7 = vt;
-    T Jt[3][NJ], J4z[NJ], J7z[NJ];
-    ATACOM_UNROLL
-    for (int j = 0; j < NJ; ++j) {
-      const HP dqj = dq[j];
-      const Vec3<HP> ct = cross(zax[j], tip - org[j]);
-      Jt[0][j] = T(ct.x); Jt[1][j] = T(ct.y); Jt[2][j] = T(ct.z);
-      vt = vt + dqj * ct;
-      Vec3<HP> c4{HP(0), HP(0), HP(0)}, c7 = c4;
-      if (j < 3) c4 = cross(zax[j], org[3] - org[j]);
-      if (j < 6) c7 = cross(zax[j], org[6] - org[j]);
-      J4z[j] = T(c4.z);
-      J7z[j] = T(c7.z);
-      v4 = v4 + dqj * c4;
-      v7 = v7 + dqj * c7;
-    }
-
-    // ---- velocity-product terms in T (not amplified by K_c): zero-joint-acceleration recursion
-    // for the acceleration of the link-4 / link-7 origins and the tip
-    Vec3<T> w{T(0), T(0), T(0)}, al = w, ao = w, oprev = w;
-    Vec3<T> acc4 = w, acc7 = w, w4 = w, w7 = w;
-    ATACOM_UNROLL
-    for (int i = 0; i < 7; ++i) {
-      const Vec3<T> oi = vcast<T>(org[i]);
+      const Vec3<T> oi = vcast<T>(o);
       const Vec3<T> rr = oi - oprev;
       ao = ao + cross(al, rr) + cross(w, cross(w, rr));
       if (i == 3) { acc4 = ao; w4 = w; }
       if (i == 6) { acc7 = ao; w7 = w; }
       if (i < NJ) {
-        const Vec3<T> zq = dq[i < NJ ? i : 0] * vcast<T>(zax[i]);
+        const Vec3<T> zq = dq[i < NJ ? i : 0] * vcast<T>(ez);
         al = al + cross(w, zq);
         w = w + zq;
       }
       oprev = oi;
     }
+    const Vec3<HP> tip = o + HP(tip_len) * ez;
     const Vec3<T> rt = vcast<T>(tip) - oprev;
     Vec3<T> acct = ao + cross(al, rt) + cross(w, cross(w, rt));
+
+    // ---- world-aligned linear Jacobians, column j = z_j x (p - o_j), handed on as they are formed; J dq
+    // accumulated in HP.  Only the z rows of the link-4 / link-7 Jacobians enter the constraints.
+    HP dqh[NJ];
+    ATACOM_UNROLL
+    for (int j = 0; j < NJ; ++j) dqh[j] = cvt<HP>(dq[j]);
+    Vec3<HP> vt{HP(0), HP(0), HP(0)};
+    HP v4z = HP(0), v7z = HP(0);
+    ATACOM_UNROLL
+    for (int j = 0; j < NJ; ++j) {
+      const Vec3<HP> ct = cross(zax[j], tip - org[j]);
+      vt = vt + dqh[j] * ct;
+      HP c4z = HP(0), c7z = HP(0);
+      if (j < 3) c4z = zax[j].x * (org[3].y - org[j].y) - zax[j].y * (org[3].x - org[j].x);
+      if (j < 6) c7z = zax[j].x * (org[6].y - org[j].y) - zax[j].y * (org[6].x - org[j].x);
+      v4z += dqh[j] * c4z;
+      v7z += dqh[j] * c7z;
+      R.put_J(0, j, cvt<JT>(ct.z));
+      R.put_J(1, j, cvt<JT>(-ct.x));
+      R.put_J(2, j, cvt<JT>(-ct.y));
+      R.put_J(3, j, cvt<JT>(ct.y));
+      R.put_J(4, j, cvt<JT>(-c4z));
+      R.put_J(5, j, cvt<JT>(-c7z));
+      const HP qm = HP(P.env[6 + j]), qj = cvt<HP>(q[j]);
+      R.put_c(6 + j, qj * qj - qm * qm);
+      R.put_Jdq(6 + j, HP(2) * qj * dqh[j]);
+      R.put_b(6 + j, T(2) * dq[j] * dq[j]);
+      ATACOM_UNROLL
+      for (int i = 0; i < NJ; ++i) R.put_J(6 + j, i, (i == j) ? cvt<JT>(HP(2) * qj) : JT(0));
+    }
+
     if (P.bias_mode == BIAS_OMEGA_X_V) {
-      // link-4 / link-7 frames are the child frames of joints 4 / 7: their angular velocity
-      // includes that joint's own rate
+      // pinocchio classical acceleration with zero spatial acceleration: omega x v.  The link-4 / link-7
+      // frames are the child frames of joints 4 / 7: their angular velocity includes that joint's own rate
+      Vec3<HP> v4{HP(0), HP(0), HP(0)}, v7 = v4;
+      ATACOM_UNROLL
+      for (int j = 0; j < NJ; ++j) {
+        if (j < 3) v4 = v4 + dqh[j] * cross(zax[j], org[3] - org[j]);
+        if (j < 6) v7 = v7 + dqh[j] * cross(zax[j], org[6] - org[j]);
+      }
       const Vec3<T> w4f = w4 + dq[3] * vcast<T>(zax[3]);
       const Vec3<T> w7f = (NJ == 7) ? w7 + dq[NJ == 7 ? 6 : 0] * vcast<T>(zax[6]) : w7;
       acct = cross(w, vcast<T>(vt));
@@ -270,27 +299,12 @@ struct IiwaEnv {
 
     const HP xw = tip.x + HP(P.env[0]);
     const HP hl = HP(P.env[1]), hw = HP(P.env[2]);
-    R.c[0] = tip.z - HP(P.env[3]);     R.Jdq[0] = vt.z;    R.b[0] = acct.z;
-    R.c[1] = -xw - hl;                 R.Jdq[1] = -vt.x;   R.b[1] = -acct.x;
-    R.c[2] = -tip.y - hw;              R.Jdq[2] = -vt.y;   R.b[2] = -acct.y;
-    R.c[3] = tip.y - hw;               R.Jdq[3] = vt.y;    R.b[3] = acct.y;
-    R.c[4] = HP(P.env[4]) - org[3].z;  R.Jdq[4] = -v4.z;   R.b[4] = -acc4.z;
-    R.c[5] = HP(P.env[5]) - org[6].z;  R.Jdq[5] = -v7.z;   R.b[5] = -acc7.z;
-    ATACOM_UNROLL
-    for (int j = 0; j < NJ; ++j) {
-      R.J[0][j] = Jt[2][j];
-      R.J[1][j] = -Jt[0][j];
-      R.J[2][j] = -Jt[1][j];
-      R.J[3][j] = Jt[1][j];
-      R.J[4][j] = -J4z[j];
-      R.J[5][j] = -J7z[j];
-      const HP qm = HP(P.env[6 + j]), qj = q[j];
-      R.c[6 + j] = qj * qj - qm * qm;
-      R.Jdq[6 + j] = HP(2) * qj * HP(dq[j]);
-      R.b[6 + j] = T(2) * dq[j] * dq[j];
-      ATACOM_UNROLL
-      for (int i = 0; i < NJ; ++i) R.J[6 + j][i] = (i == j) ? T(2) * q[j] : T(0);
-    }
+    R.put_c(0, tip.z - HP(P.env[3]));     R.put_Jdq(0, vt.z);    R.put_b(0, acct.z);
+    R.put_c(1, -xw - hl);                 R.put_Jdq(1, -vt.x);   R.put_b(1, -acct.x);
+    R.put_c(2, -tip.y - hw);              R.put_Jdq(2, -vt.y);   R.put_b(2, -acct.y);
+    R.put_c(3, tip.y - hw);               R.put_Jdq(3, vt.y);    R.put_b(3, acct.y);
+    R.put_c(4, HP(P.env[4]) - org[3].z);  R.put_Jdq(4, -v4z);    R.put_b(4, -acc4.z);
+    R.put_c(5, HP(P.env[5]) - org[6].z);  R.put_Jdq(5, -v7z);    R.put_b(5, -acc7.z);
   }
 };
 
@@ -412,9 +426,132 @@ ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP,
   return st;
 }
 
+// Gains the dual path multiplies in HP, converted and combined once on the host side of the launch:
+//   r_i = psi_i + K_c,i c_i  with  psi_i = (J dq)_i + K_i b_i,  c_i = c_i(q) + K_i (J dq)_i [+ s_i^2 / 2]
+//       = K_c,i c_i(q) + wJ_i (J dq)_i + wb_i b_i [+ K_c,i s_i^2 / 2]      (constraints.py:33-43, atacom.py:181,195)
+// variant E drops psi (error_correction_wrapper.py:117-134).
+template <typename HP>
+struct DualConsts {
+  HP K[20];     // K_f then K_g (constraints.py:26-29)
+  HP K_c[20];   // atacom.py:42-48
+  HP wJ[20];    // 1 + K_c K   (variant E: K_c K)
+  HP wb[20];    // K           (variant E: 0)
+  HP dt, tol;
+};
+
+template <typename T, typename HP>
+inline DualConsts<HP> make_dual_consts(const ParamsT<T>& P, int F, int G) {
+  DualConsts<HP> c;
+  const bool ec = P.variant == VARIANT_EC;
+  for (int i = 0; i < 20; ++i) {
+    c.K[i] = i < F ? HP(P.K_f[i]) : (i - F < G && i - F < 16 ? HP(P.K_g[i - F]) : HP(0));
+    c.K_c[i] = HP(P.K_c[i]);
+    c.wJ[i] = (ec ? HP(0) : HP(1)) + c.K_c[i] * c.K[i];
+    c.wb[i] = ec ? HP(0) : c.K[i];
+  }
+  c.dt = HP(P.dt);
+  c.tol = HP(P.rref_tol);
+  return c;
+}
+
+// Sink of the dual path: K-scaled dense Jacobian rows go straight to the scratch Y, the diagonal rows
+// to dg, and the three scalar streams are folded into r as they arrive.
+template <typename T, typename HP, class D, int NDIAG, class YS>
+struct DualSink {
+  using JT = HP;
+  static constexpr int n = D::n, F = D::F, G = D::G, C = D::C, m = D::F + D::G - NDIAG;
+  const DualConsts<HP>& Kd;
+  YS& Y;
+  HP r[at_least_1<C>::value], dg[at_least_1<NDIAG>::value];
+  ATACOM_HD DualSink(const DualConsts<HP>& Kd_, YS& Y_, const HP* sh) : Kd(Kd_), Y(Y_) {
+    ATACOM_UNROLL
+    for (int i = 0; i < C; ++i) r[i] = (i >= F) ? HP(0.5) * Kd.K_c[i] * sh[i >= F ? i - F : 0] * sh[i >= F ? i - F : 0] : HP(0);
+  }
+  ATACOM_HD void put_c(int i, HP v) { r[i] += Kd.K_c[i] * v; }
+  ATACOM_HD void put_Jdq(int i, HP v) { r[i] += Kd.wJ[i] * v; }
+  ATACOM_HD void put_b(int i, T v) { r[i] += Kd.wb[i] * cvt<HP>(v); }
+  ATACOM_HD void put_J(int i, int j, HP v) {
+    if (i < m) Y.set(i * n + j, Kd.K[i] * v);                 // constraints.py:39-40
+    else if (j == i - m) dg[j] = Kd.K[i] * v;
+  }
+};
+
+// The whole step around the dual projection (atacom_dual.cuh): everything between the fp32 inputs and
+// the fp32 outputs is carried in HP.  An environment the dual path defers (two or more slack pivots)
+// comes back flagged ST_DENSE_PATH with no outputs written: the caller reruns it on the general fp32
+// path.
+template <class Env, typename T, typename HP, class YS, class LS>
+ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q, const T* dq,
+                            const T* s, const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+  using D = typename Env::D;
+  constexpr int NDIAG = Env::NDIAG;
+  constexpr int n = D::n, G = D::G, N = D::N, k = D::k;
+  HP sh[at_least_1<G>::value], ah[at_least_1<k>::value];
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
+  const bool ec = P.variant == VARIANT_EC;
+  DualSink<T, HP, D, NDIAG, YS> sink(Kd, Y, sh);
+  Env::template eval<T, HP>(P, q, dq, sink);
+  ATACOM_UNROLL
+  for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
+  T w_mn[N];
+  HP w_null[N];
+  uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, sink.dg, sh, sink.r, ah, Kd.tol, !ec, w_mn, w_null);
+  if (st & ST_DENSE_PATH) return st;
+  if (ec) {
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) w_null[j] = cvt<HP>(alpha[j]);    // error_correction_wrapper.py:127
+  }
+  bool finite = true;
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) {
+    const HP wz = cvt<HP>(w_mn[n + i]) + w_null[n + i];
+    const T so = cvt<T>(sh[i] + wz * Kd.dt);                      // atacom.py:135
+    s_out[i] = so;
+    finite = finite && (so - so == T(0));
+  }
+  ATACOM_UNROLL
+  for (int j = 0; j < n; ++j) {
+    T a = cvt<T>(cvt<HP>(w_mn[j]) + w_null[j]);
+    finite = finite && (a - a == T(0));
+    if (P.clip_acc) {                                             // atacom.py:117-121
+      const T am = P.acc_max[j];
+      T up = -P.K_q[j] * (dq[j] - P.vel_max[j]);
+      up = up < am ? up : am;
+      up = up > -am ? up : -am;
+      T lo = -P.K_q[j] * (dq[j] + P.vel_max[j]);
+      lo = lo > -am ? lo : -am;
+      lo = lo < am ? lo : am;
+      a = a > lo ? a : lo;
+      a = a < up ? a : up;
+    }
+    ddq[j] = a;
+  }
+  if (w_dbg) {
+    ATACOM_UNROLL
+    for (int i = 0; i < N; ++i) {
+      w_dbg[i] = w_mn[i];
+      w_dbg[N + i] = cvt<T>(w_null[i]);
+    }
+  }
+  if (!finite) st |= ST_NONFINITE;
+  return st;
+}
+
+// The general fp32 path (structured -> dense) from scratch, kept out of line: the rarely taken
+// fallback of the dual path must not set the register budget of the kernels that inline the latter.
+template <class Env, typename T, typename HP>
+ATACOM_NOINLINE uint8_t step_general_outlined(const ParamsT<T>& P, const T* q, const T* dq, const T* s,
+                                              const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+  using D = typename Env::D;
+  RawConstraints<T, HP, D> R;
+  Env::template eval<T, HP>(P, q, dq, R);
+  return step_from_raw<T, HP, D, Env::NDIAG>(P, R, dq, s, alpha, ddq, s_out, w_dbg);
+}
+
 // atacom.py:145-149
-template <typename T, typename HP, class D>
-ATACOM_HD void slack_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP, D>& R, T* s) {
+template <typename T, typename HP, class D, typename JT>
+ATACOM_HD void slack_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP, D, JT>& R, T* s) {
   constexpr int F = D::F, G = D::G;
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) {

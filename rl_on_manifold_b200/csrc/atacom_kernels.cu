@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <new>
+#include <type_traits>
 
 #include "../../include/atacom_b200.h"
 #include "atacom_envs.cuh"
@@ -29,8 +30,11 @@ namespace {
 #ifndef ATACOM_PHASE_BARRIERS
 #define ATACOM_PHASE_BARRIERS 0   // 1: block barriers between the phases of the projection (measured: no gain)
 #endif
+#ifndef ATACOM_STEP_DUAL
+#define ATACOM_STEP_DUAL 1        // 1: dual projection in FP64 (atacom_dual.cuh); 0: fp32 structured path
+#endif
 #ifndef ATACOM_STEP_MAXNREG
-#define ATACOM_STEP_MAXNREG 128   // a 448-thread block is allocated as 16 warps: 16 x 32 x 128 = the SM register file
+#define ATACOM_STEP_MAXNREG 128   // 448 threads = 14 warps, 4 on two of the SM sub-partitions: 16384 / (4 x 32) registers each
 #endif
 constexpr int TPB = ATACOM_TPB;
 constexpr int STEP_MAX_TPB = ATACOM_STEP_MAX_TPB;
@@ -119,13 +123,46 @@ __device__ __forceinline__ void row_store(float* __restrict__ g, int64_t e, cons
   }
 }
 
+// ------------------------------------------------------------------ scratch of the dual projection
+// Small environments keep Y and L in registers.  The iiwa kernels put them in dynamic shared memory,
+// one column of a [Y_SIZE + L_SIZE][STEP_MAX_TPB] array of doubles per thread (conflict-free): 57 x 448 x 8
+// = 204 KB for IiwaEnv<6>, which is the whole point — together with the register file it holds the
+// per-environment working set of all 448 environments of the SM at once.
+template <class Env>
+struct StepScratch {
+  using DU = Dual<double, typename Env::D, Env::NDIAG>;
+  static constexpr bool SHARED = DU::Y_SIZE + DU::L_SIZE > 24;
+  static constexpr int STRIDE = ATACOM_STEP_MAX_TPB;
+  static constexpr size_t BYTES = SHARED ? sizeof(double) * (DU::Y_SIZE + DU::L_SIZE) * STRIDE : 0;
+  using YS = typename std::conditional<SHARED, SharedStore<double, STRIDE>, LocalStore<double, DU::Y_SIZE>>::type;
+  using LS = typename std::conditional<SHARED, SharedStore<double, STRIDE>, LocalStore<double, DU::L_SIZE>>::type;
+  static __device__ __forceinline__ YS y() {
+    if constexpr (SHARED) {
+      extern __shared__ double atacom_scratch[];
+      return YS{atacom_scratch + threadIdx.x};
+    } else {
+      return YS{};
+    }
+  }
+  static __device__ __forceinline__ LS l() {
+    if constexpr (SHARED) {
+      extern __shared__ double atacom_scratch[];
+      return LS{atacom_scratch + DU::Y_SIZE * STRIDE + threadIdx.x};
+    } else {
+      return LS{};
+    }
+  }
+};
+
 // ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
 // One thread = one environment.  The block size is chosen at launch (<= STEP_MAX_TPB) so that the batch
 // spreads evenly over the SMs, ideally one block per SM: the body is a long fully unrolled instruction
 // stream and the block barriers between its phases keep all warps of the SM in the same code region,
 // so each instruction line is fetched once per SM rather than once per warp.
 template <class Env>
-__global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(StepArgs a, ParamsT<float> P) {
+__global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
+                                                                    const __grid_constant__ ParamsT<float> P,
+                                                                    const __grid_constant__ DualConsts<double> Kd) {
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
@@ -149,10 +186,18 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(StepArgs a, 
     for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
   }
 
+  float* dbg = (a.w_dbg && valid) ? a.w_dbg + e * (2 * N) : nullptr;
+#if ATACOM_STEP_DUAL
+  using DU = Dual<double, D, Env::NDIAG>;
+  typename StepScratch<Env>::YS Ys = StepScratch<Env>::y();
+  typename StepScratch<Env>::LS Ls = StepScratch<Env>::l();
+  uint8_t st = step_dual<Env, float, double>(P, Kd, Ys, Ls, q, dq, s, al, ddq, so, dbg);
+  if (st & ST_DENSE_PATH) st = ST_DENSE_PATH | step_general_outlined<Env, float, double>(P, q, dq, s, al, ddq, so, dbg);
+#else
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
-  float* dbg = (a.w_dbg && valid) ? a.w_dbg + e * (2 * N) : nullptr;
   const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, ATACOM_PHASE_BARRIERS != 0>(P, R, dq, s, al, ddq, so, dbg);
+#endif
   if (valid) {
     if (a.status) a.status[e] = st;
     if (a.ddq) row_store<n>(a.ddq, e, ddq);
@@ -375,7 +420,18 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   }
   const int tpb = step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
-  atacom_step_kernel<Env><<<grid, tpb, 0, static_cast<cudaStream_t>(stream)>>>(a, as_params(p));
+  constexpr size_t smem = ATACOM_STEP_DUAL ? StepScratch<Env>::BYTES : 0;
+  if (smem > 48 * 1024) {
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+      if (cudaFuncSetAttribute(atacom_step_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)) != cudaSuccess)
+        return ATACOM_ERR_CUDA;
+      configured = true;
+    }
+  }
+  atacom_step_kernel<Env><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
+      a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
 }

@@ -65,6 +65,9 @@ static ParamsT<T> unpack(const double* f) {
   return P;
 }
 
+static int g_general_path = 0;
+extern "C" void harness_set_general_path(int on) { g_general_path = on; }
+
 template <typename T, class Env>
 static void run_step(int64_t B, const double* params, const T* q, const T* dq, const T* s, const T* alpha, T* ddq,
                      T* s_out, T* w_dbg, uint8_t* status, int init_only) {
@@ -72,16 +75,36 @@ static void run_step(int64_t B, const double* params, const T* q, const T* dq, c
   const ParamsT<T> P = unpack<T>(params);
   const int na = P.variant == VARIANT_EC ? D::n : D::k;
   for (int64_t b = 0; b < B; ++b) {
-    RawConstraints<T, double, D> R;
-    Env::template eval<T, double>(P, q + b * D::n, dq + b * D::n, R);
-    if (init_only) {
-      slack_from_raw<T, double, D>(P, R, s_out + b * D::G);
-      continue;
-    }
     T al[D::n];
     for (int j = 0; j < D::n; ++j) al[j] = j < na ? alpha[b * na + j] : T(0);
-    status[b] = step_from_raw<T, double, D, Env::NDIAG>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n, s_out + b * D::G,
-                                    w_dbg + b * 2 * D::N);
+    if (g_general_path) {   // the fp32 structured / dense path (generic kernels, fallback of the dual path)
+      RawConstraints<T, double, D> R;
+      Env::template eval<T, double>(P, q + b * D::n, dq + b * D::n, R);
+      if (init_only) {
+        slack_from_raw<T, double, D>(P, R, s_out + b * D::G);
+        continue;
+      }
+      status[b] = step_from_raw<T, double, D, Env::NDIAG>(P, R, dq + b * D::n, s + b * D::G, al, ddq + b * D::n,
+                                                          s_out + b * D::G, w_dbg + b * 2 * D::N);
+    } else {                // what the step kernels run: dual projection in double
+      if (init_only) {
+        RawConstraints<T, double, D> R;
+        Env::template eval<T, double>(P, q + b * D::n, dq + b * D::n, R);
+        slack_from_raw<T, double, D>(P, R, s_out + b * D::G);
+        continue;
+      }
+      const DualConsts<double> Kd = make_dual_consts<T, double>(P, D::F, D::G);
+      using DU = Dual<double, D, Env::NDIAG>;
+      LocalStore<double, DU::Y_SIZE> Ys;
+      LocalStore<double, DU::L_SIZE> Ls;
+      uint8_t st = step_dual<Env, T, double>(P, Kd, Ys, Ls, q + b * D::n, dq + b * D::n, s + b * D::G, al,
+                                             ddq + b * D::n, s_out + b * D::G, w_dbg + b * 2 * D::N);
+      if (st & ST_DENSE_PATH)
+        st = ST_DENSE_PATH | step_general_outlined<Env, T, double>(P, q + b * D::n, dq + b * D::n, s + b * D::G, al,
+                                                                   ddq + b * D::n, s_out + b * D::G,
+                                                                   w_dbg + b * 2 * D::N);
+      status[b] = st;
+    }
   }
 }
 
