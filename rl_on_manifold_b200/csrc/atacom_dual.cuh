@@ -66,6 +66,14 @@ struct LocalStore {
   R v[SIZE > 0 ? SIZE : 1];
   ATACOM_HD R get(int i) const { return v[i]; }
   ATACOM_HD void set(int i, R x) { v[i] = x; }
+  // entry at a run-time index (a shared-memory address on the device; here a select chain so that the
+  // array can stay in registers)
+  ATACOM_HD R get_dyn(int i) const {
+    R x = R(0);
+    ATACOM_UNROLL
+    for (int c = 0; c < SIZE; ++c) x = (c == i) ? v[c] : x;
+    return x;
+  }
 };
 template <typename R, int STRIDE>
 struct SharedStore {
@@ -74,6 +82,7 @@ struct SharedStore {
   // register, i.e. keep the operand in the register file after all (and spill it to local memory)
   ATACOM_HD R get(int i) const { return *static_cast<const volatile R*>(base + i * STRIDE); }
   ATACOM_HD void set(int i, R x) { *static_cast<volatile R*>(base + i * STRIDE) = x; }
+  ATACOM_HD R get_dyn(int i) const { return *static_cast<const volatile R*>(base + i * STRIDE); }
 };
 
 template <typename R, class D, int NDIAG>
@@ -191,22 +200,36 @@ struct Dual {
 
     // ---- (3a) Y = L^-1 B, one column at a time (stored back); t = Y^T u
     const bool null_part = want_null && k > 0;
-    ATACOM_UNROLL
-    for (int j = 0; j < n; ++j) {
-      R yj[M1];
-      R t = R(0);
+    {
+      R cur[M1], nxt[M1];
       ATACOM_UNROLL
-      for (int i = 0; i < m; ++i) {
-        R v = Y.get(i * n + j);
+      for (int i = 0; i < m; ++i) cur[i] = Y.get(i * n);
+      ATACOM_UNROLL
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) {   // the next column is on its way while this one is solved
+          ATACOM_UNROLL
+          for (int i = 0; i < m; ++i) nxt[i] = Y.get(i * n + (j + 1 < n ? j + 1 : 0));
+        }
+        R yj[M1];
+        R t = R(0);
         ATACOM_UNROLL
-        for (int l = 0; l < i; ++l) v -= L[i][l] * yj[l];
-        yj[i] = v * li[i];
-        t += yj[i] * u[i];
-        if (null_part) Y.set(i * n + j, yj[i]);
+        for (int i = 0; i < m; ++i) {
+          R v = cur[i];
+          ATACOM_UNROLL
+          for (int l = 0; l < i; ++l) v -= L[i][l] * yj[l];
+          yj[i] = v * li[i];
+          t += yj[i] * u[i];
+        }
+        if (null_part) {
+          ATACOM_UNROLL
+          for (int i = 0; i < m; ++i) Y.set(i * n + j, yj[i]);
+        }
+        w_mn[j] = cvt<W>((j < NDIAG) ? mu[j] + sig[j] * t : t);
+        if (j < NDIAG) w_mn[n + GD + j] = cvt<W>(zeta[j] - gam[j] * t);
+        w_null[j] = R(0);
+        ATACOM_UNROLL
+        for (int i = 0; i < m; ++i) cur[i] = nxt[i];
       }
-      w_mn[j] = cvt<W>((j < NDIAG) ? mu[j] + sig[j] * t : t);
-      if (j < NDIAG) w_mn[n + GD + j] = cvt<W>(zeta[j] - gam[j] * t);
-      w_null[j] = R(0);
     }
     if (!null_part) return status;
     ATACOM_UNROLL
@@ -323,37 +346,25 @@ struct Dual {
     // remaining null direction in the free coordinates: tau supported on the unpivoted columns with
     // B_f tau = 0; its entries are x_j = sigma_j tau_j, z_diag,j = -gamma_j tau_j, z_dense,i = -(b_i . tau) / s_i.
     // The equality row of Y is B_f / L_00: same direction.
-    R nu[n];
+    int u1 = 0, u2 = 0;
     {
-      R a1 = R(0), a2 = R(0);
       int cnt = 0;
-      if (F == 1) {
-        ATACOM_UNROLL
-        for (int c = 0; c < n; ++c) {
-          const R y0 = Y.get(c);
-          if (!take[c]) {
-            a1 = (cnt == 0) ? y0 : a1;
-            a2 = (cnt == 1) ? y0 : a2;
-            ++cnt;
-          }
-        }
-      }
-      cnt = 0;
       ATACOM_UNROLL
       for (int c = 0; c < n; ++c) {
-        nu[c] = take[c] ? R(0) : (F == 1 ? (cnt == 0 ? a2 : -a1) : R(1));
+        u1 = (!take[c] && cnt == 0) ? c : u1;
+        u2 = (!take[c] && cnt == 1) ? c : u2;
         cnt += take[c] ? 0 : 1;
       }
     }
+    // tau = (t1 at column u1, t2 at column u2) with B_f tau = 0 (F = 1), or the unit vector of u1 (F = 0)
+    const R t1 = (F == 1) ? Y.get_dyn(u2) : R(1);
+    const R t2 = (F == 1) ? -Y.get_dyn(u1) : R(0);
     R e[G1], yt[M1];
-    R nrm2 = R(0);
-    ATACOM_UNROLL
-    for (int c = 0; c < n; ++c) nrm2 += nu[c] * nu[c];
+    R nrm2 = t1 * t1 + t2 * t2;
     ATACOM_UNROLL
     for (int l = 0; l < m; ++l) {   // B = L Y  =>  b_i . tau = sum_{l <= i} L[i][l] (Y[l] . tau)
-      R acc = R(0);
-      ATACOM_UNROLL
-      for (int j = 0; j < n; ++j) acc += Y.get(l * n + j) * nu[j];
+      R acc = Y.get_dyn(l * n + u1) * t1;
+      if (F == 1) acc += Y.get_dyn(l * n + u2) * t2;
       yt[l] = acc;
     }
     ATACOM_UNROLL
@@ -361,7 +372,7 @@ struct Dual {
       if (i < GD) {
         const int ri = F + (i < GD ? i : 0);
         const R lii = Ls.get(LI0 + ri);
-        R an = (lii > R(0)) ? yt[ri] / lii : R(0);
+        R an = (lii > R(0)) ? yt[ri] * dual_rsqrt(lii * lii) : R(0);   // L[ri][ri] = 1 / li
         ATACOM_UNROLL
         for (int l = 0; l < ri; ++l) an += Ls.get(lidx(ri, l)) * yt[l];
         const R s2 = s[i] * s[i];
@@ -369,7 +380,8 @@ struct Dual {
         e[i] = (s[i] < R(0) ? an : -an) * rs;
         nrm2 += e[i] * e[i];
       } else {
-        e[i] = -gam[i >= GD ? i - GD : 0] * nu[i >= GD ? i - GD : 0];   // sigma^2 + gamma^2 = 1: already in nrm2
+        const int j = i >= GD ? i - GD : 0;
+        e[i] = -gam[j] * ((j == u1) ? t1 : ((F == 1 && j == u2) ? t2 : R(0)));   // sigma^2 + gamma^2 = 1: already in nrm2
       }
     }
     const R rn = dual_rsqrt(nrm2);
@@ -390,7 +402,8 @@ struct Dual {
     }
     ATACOM_UNROLL
     for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
-    const R bl = (al - zp) / ep;   // beta of the new row times the sign of its pivot entry
+    const R ri = dual_rsqrt(ep * ep);
+    const R bl = (al - zp) * (ep * ri * ri);   // (al - zp) / ep: beta of the new row times the sign of its pivot entry
     ATACOM_UNROLL
     for (int i = 0; i < G; ++i) {
       const R v = w_null[n + i];

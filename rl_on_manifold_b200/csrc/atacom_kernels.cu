@@ -33,6 +33,9 @@ namespace {
 #ifndef ATACOM_STEP_DUAL
 #define ATACOM_STEP_DUAL 1        // 1: dual projection in FP64 (atacom_dual.cuh); 0: fp32 structured path
 #endif
+#ifndef ATACOM_STEP_STAGED_IO
+#define ATACOM_STEP_STAGED_IO 0   // 1: per-warp bulk copies (cp.async.bulk + mbarrier) through shared memory; 0: every thread moves its own rows (measured 2 % faster)
+#endif
 #ifndef ATACOM_STEP_MAXNREG
 #define ATACOM_STEP_MAXNREG 128   // 448 threads = 14 warps, 4 on two of the SM sub-partitions: 16384 / (4 x 32) registers each
 #endif
@@ -71,7 +74,10 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* s
   }
 }
 
-template <int X> struct round4_t { static constexpr int value = (X + 3) & ~3; };
+template <int X> struct round4_t {
+  static constexpr int value = (X + 3) & ~3;
+  static __host__ __device__ constexpr int up(int v) { return (v + 3) & ~3; }
+};
 
 struct StepArgs {
   const float* q;
@@ -88,6 +94,7 @@ struct StepArgs {
   float* peer[ATACOM_MAX_PEERS];
   int64_t gather_row0;
   int32_t n_peers;
+  int32_t aligned16;   // every array pointer (and peer buffer) is 16-byte aligned: bulk copies allowed
 };
 
 // ------------------------------------------------------------------ row access
@@ -124,35 +131,66 @@ __device__ __forceinline__ void row_store(float* __restrict__ g, int64_t e, cons
 }
 
 // ------------------------------------------------------------------ scratch of the dual projection
-// Small environments keep Y and L in registers.  The iiwa kernels put them in dynamic shared memory,
-// one column of a [Y_SIZE + L_SIZE][STEP_MAX_TPB] array of doubles per thread (conflict-free): 57 x 448 x 8
-// = 204 KB for IiwaEnv<6>, which is the whole point — together with the register file it holds the
-// per-environment working set of all 448 environments of the SM at once.
+// Dynamic shared memory is cut into one region per warp.  A region is
+//   * the staging area of the warp's I/O: its 32 rows of each [B, dim] array are one contiguous,
+//     16-byte aligned piece per array, moved by the bulk-copy engine (cp.async.bulk, one elected lane,
+//     completion on the warp's own mbarrier — no block barrier anywhere in the kernel), and
+//   * for the iiwa kernels, the scratch of the projection: Y (m x n) and L (m (m+1) / 2) as
+//     [entry][lane] arrays of doubles (conflict-free), 57 x 32 x 8 = 14.6 KB per warp, 204 KB per 448-thread
+//     block — together with the register file that holds the working set of all 448 environments of
+//     the SM at once.  Small environments keep Y and L in registers.
+// The staging area aliases the scratch, which is idle at both ends of the kernel.
 template <class Env>
 struct StepScratch {
-  using DU = Dual<double, typename Env::D, Env::NDIAG>;
+  using ED = typename Env::D;
+  using DU = Dual<double, ED, Env::NDIAG>;
   static constexpr bool SHARED = DU::Y_SIZE + DU::L_SIZE > 24;
-  static constexpr int STRIDE = ATACOM_STEP_MAX_TPB;
-  static constexpr size_t BYTES = SHARED ? sizeof(double) * (DU::Y_SIZE + DU::L_SIZE) * STRIDE : 0;
-  using YS = typename std::conditional<SHARED, SharedStore<double, STRIDE>, LocalStore<double, DU::Y_SIZE>>::type;
-  using LS = typename std::conditional<SHARED, SharedStore<double, STRIDE>, LocalStore<double, DU::L_SIZE>>::type;
-  static __device__ __forceinline__ YS y() {
-    if constexpr (SHARED) {
-      extern __shared__ double atacom_scratch[];
-      return YS{atacom_scratch + threadIdx.x};
-    } else {
-      return YS{};
-    }
+  static constexpr int MAX_WARPS = ATACOM_STEP_MAX_TPB / 32;
+  static constexpr size_t SCRATCH = SHARED ? sizeof(double) * (DU::Y_SIZE + DU::L_SIZE) * 32 : 0;
+  static constexpr size_t STAGE = sizeof(float) * 32 * (3 * ED::n + ED::G);   // q, dq, alpha, s
+  static constexpr size_t WARP_BYTES = ((SCRATCH > STAGE ? SCRATCH : STAGE) + 127) / 128 * 128;
+  static constexpr size_t BYTES = WARP_BYTES * MAX_WARPS + sizeof(uint64_t) * MAX_WARPS;   // + one mbarrier per warp
+  using YS = typename std::conditional<SHARED, SharedStore<double, 32>, LocalStore<double, DU::Y_SIZE>>::type;
+  using LS = typename std::conditional<SHARED, SharedStore<double, 32>, LocalStore<double, DU::L_SIZE>>::type;
+  static __device__ __forceinline__ YS y(unsigned char* region, int lane) {
+    if constexpr (SHARED) return YS{reinterpret_cast<double*>(region) + lane};
+    else return YS{};
   }
-  static __device__ __forceinline__ LS l() {
-    if constexpr (SHARED) {
-      extern __shared__ double atacom_scratch[];
-      return LS{atacom_scratch + DU::Y_SIZE * STRIDE + threadIdx.x};
-    } else {
-      return LS{};
-    }
+  static __device__ __forceinline__ LS l(unsigned char* region, int lane) {
+    if constexpr (SHARED) return LS{reinterpret_cast<double*>(region) + DU::Y_SIZE * 32 + lane};
+    else return LS{};
   }
 };
+
+// ---- bulk-copy engine and mbarrier (PTX ISA 8.x, sm_90+)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
 // One thread = one environment.  The block size is chosen at launch (<= STEP_MAX_TPB) so that the batch
@@ -173,24 +211,64 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   const int64_t e = valid ? e_raw : a.B - 1;
   const bool ec = P.variant == VARIANT_EC;
 
+  // Inputs.  A full warp whose slabs are 16-byte aligned has the bulk-copy engine fetch them into its region
+  // and every lane picks its own rows up from there; any other warp (tail of the batch, unaligned views) has
+  // each thread load its rows directly.
   float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
-  row_load<n>(a.q, e, q);
-  row_load<n>(a.dq, e, dq);
-  if (G > 0) row_load<G1>(a.s_in, e, s);
-  if (ec) {
-    row_load<n>(a.alpha, e, al);
-  } else {
-    float ak[K1];
-    if (k > 0) row_load<K1>(a.alpha, e, ak);
+  extern __shared__ __align__(128) unsigned char atacom_smem[];
+  using SC = StepScratch<Env>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* region = atacom_smem + warp * SC::WARP_BYTES;
+  const int64_t wenv0 = e_raw - lane;
+  const int na = ec ? n : k;
+#if ATACOM_STEP_STAGED_IO
+  uint64_t* bar = reinterpret_cast<uint64_t*>(atacom_smem + SC::MAX_WARPS * SC::WARP_BYTES) + warp;
+  const bool bulk = a.aligned16 && (wenv0 + 32 <= a.B);
+  float* sq = reinterpret_cast<float*>(region);
+  float* sdq = sq + 32 * n;
+  float* ss = sdq + 32 * n;
+  float* sa = ss + 32 * G;
+  if (bulk) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, 4u * 32u * static_cast<uint32_t>(2 * n + G + na));
+      bulk_g2s(sq, a.q + wenv0 * n, 128u * n, bar);
+      bulk_g2s(sdq, a.dq + wenv0 * n, 128u * n, bar);
+      if (G > 0) bulk_g2s(ss, a.s_in + wenv0 * G, 128u * G, bar);
+      if (na > 0) bulk_g2s(sa, a.alpha + wenv0 * na, 128u * static_cast<uint32_t>(na), bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
 #pragma unroll
-    for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
+    for (int j = 0; j < n; ++j) {
+      q[j] = sq[lane * n + j];
+      dq[j] = sdq[lane * n + j];
+      al[j] = j < na ? sa[lane * na + j] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) s[i] = ss[lane * G1 + i];
+    __syncwarp();     // the region is scratch from here on
+  } else
+#endif
+  {
+    row_load<n>(a.q, e, q);
+    row_load<n>(a.dq, e, dq);
+    if (G > 0) row_load<G1>(a.s_in, e, s);
+    if (ec) {
+      row_load<n>(a.alpha, e, al);
+    } else {
+      float ak[K1];
+      if (k > 0) row_load<K1>(a.alpha, e, ak);
+#pragma unroll
+      for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
+    }
   }
 
   float* dbg = (a.w_dbg && valid) ? a.w_dbg + e * (2 * N) : nullptr;
 #if ATACOM_STEP_DUAL
   using DU = Dual<double, D, Env::NDIAG>;
-  typename StepScratch<Env>::YS Ys = StepScratch<Env>::y();
-  typename StepScratch<Env>::LS Ls = StepScratch<Env>::l();
+  typename SC::YS Ys = SC::y(region, lane);
+  typename SC::LS Ls = SC::l(region, lane);
   uint8_t st = step_dual<Env, float, double>(P, Kd, Ys, Ls, q, dq, s, al, ddq, so, dbg);
   if (st & ST_DENSE_PATH) st = ST_DENSE_PATH | step_general_outlined<Env, float, double>(P, q, dq, s, al, ddq, so, dbg);
 #else
@@ -198,11 +276,29 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   Env::template eval<float, double>(P, q, dq, R);
   const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, ATACOM_PHASE_BARRIERS != 0>(P, R, dq, s, al, ddq, so, dbg);
 #endif
+  // Outputs go back the same way: rows to the warp's region, slabs to HBM by the bulk-copy engine.
+  if (valid && a.status) a.status[e] = st;
+#if ATACOM_STEP_STAGED_IO
+  if (bulk) {
+    __syncwarp();     // every lane is done with its scratch
+#pragma unroll
+    for (int j = 0; j < n; ++j) sq[lane * n + j] = ddq[j];
+#pragma unroll
+    for (int i = 0; i < G; ++i) ss[lane * G1 + i] = so[i];
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (a.ddq) bulk_s2g(a.ddq + wenv0 * n, sq, 128u * n);
+      if (G > 0) bulk_s2g(a.s_out + wenv0 * G, ss, 128u * G);
+      // fused all-gather: this warp's slab of rows straight into every rank's gather buffer
+      for (int w = 0; w < a.n_peers; ++w) bulk_s2g(a.peer[w] + (a.gather_row0 + wenv0) * n, sq, 128u * n);
+      bulk_commit_wait_read();
+    }
+  } else
+#endif
   if (valid) {
-    if (a.status) a.status[e] = st;
     if (a.ddq) row_store<n>(a.ddq, e, ddq);
     if (G > 0) row_store<G1>(a.s_out, e, so);
-    // fused all-gather: store this environment's row straight into every rank's gather buffer
     for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
   }
 }
@@ -413,14 +509,18 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   if (!q || !dq || (!ddq && n_peers == 0) || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
-  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers};
+  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0};
+  uintptr_t bits = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(s_in) |
+                   reinterpret_cast<uintptr_t>(alpha) | reinterpret_cast<uintptr_t>(ddq) | reinterpret_cast<uintptr_t>(s_out);
   for (int w = 0; w < n_peers; ++w) {
     if (!peers[w]) return ATACOM_ERR_NULL_POINTER;
     a.peer[w] = peers[w];
+    bits |= reinterpret_cast<uintptr_t>(peers[w]) | static_cast<uintptr_t>((gather_row0 * D::n * 4) & 15);
   }
+  a.aligned16 = (bits & 15) == 0;
   const int tpb = step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
-  constexpr size_t smem = ATACOM_STEP_DUAL ? StepScratch<Env>::BYTES : 0;
+  constexpr size_t smem = StepScratch<Env>::BYTES;
   if (smem > 48 * 1024) {
     static bool configured = false;   // per instantiation
     if (!configured) {
@@ -682,7 +782,7 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   if (!c || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
-  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0};
+  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define X(n_, F_, G_)                                                                             \
   if (n == n_ && F == F_ && G == G_)                                                              \
