@@ -153,9 +153,18 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
 /* ---- host-buffer entry points (what a NumPy caller of the reference binds) ----
  * Same semantics as atacom_iiwa_step but every array pointer is HOST memory (pinned memory makes
  * the copies asynchronous).  The context owns the device staging buffers and streams; the batch is
- * cut into `chunks` pieces whose H2D copy, kernel and D2H copy overlap. */
+ * cut into `chunks` pieces whose H2D copy, kernel and D2H copy overlap.
+ *
+ * Two data paths (atacom_host_ctx_set_mode):
+ *   ATACOM_HOST_STAGED     device staging buffers, copy engines; the whole pipeline of a call is captured in a
+ *                          CUDA graph and replayed while the caller passes the same buffers;
+ *   ATACOM_HOST_ZERO_COPY  the kernel reads and writes the caller's buffers directly over PCIe (they must be
+ *                          page-locked and mapped: cudaHostAlloc / cudaHostRegister / torch pin_memory());
+ *   ATACOM_HOST_AUTO       (default) zero-copy when every buffer of the call is mapped, else staged. */
 typedef struct AtacomHostCtx AtacomHostCtx;
+enum { ATACOM_HOST_AUTO = 0, ATACOM_HOST_STAGED = 1, ATACOM_HOST_ZERO_COPY = 2 };
 int atacom_host_ctx_create(AtacomHostCtx** ctx, int64_t max_B, int chunks);
+int atacom_host_ctx_set_mode(AtacomHostCtx* ctx, int mode);
 int atacom_host_ctx_destroy(AtacomHostCtx* ctx);
 int atacom_iiwa_step_host(AtacomHostCtx* ctx, int n_ctrl_joints, const float* q, const float* dq,
                           const float* s_in, const float* alpha, float* ddq, float* s_out, uint8_t* status,

@@ -16,6 +16,7 @@ OK = 0
 ST_RANK_DEFICIENT, ST_COLUMN_DROPPED, ST_SLACK_PIVOT, ST_NONFINITE, ST_DENSE_PATH = 1, 2, 4, 8, 16
 VARIANT_ATACOM, VARIANT_ERROR_CORRECTION = 0, 1
 BIAS_JDOT_QDOT, BIAS_OMEGA_X_V = 0, 1
+HOST_AUTO, HOST_STAGED, HOST_ZERO_COPY = 0, 1, 2
 
 
 class AtacomParams(ctypes.Structure):
@@ -88,6 +89,7 @@ SIGNATURES = {
     "atacom_generic_step": ([ctypes.c_int, ctypes.c_int, ctypes.c_int, _f, _f, _f, _f, _f, _f, _f, _f, _u8, _f,
                              _i64, _P, _stream], ctypes.c_int),
     "atacom_host_ctx_create": ([ctypes.POINTER(ctypes.c_void_p), _i64, ctypes.c_int], ctypes.c_int),
+    "atacom_host_ctx_set_mode": ([ctypes.c_void_p, ctypes.c_int], ctypes.c_int),
     "atacom_host_ctx_destroy": ([ctypes.c_void_p], ctypes.c_int),
     "atacom_iiwa_step_host": ([ctypes.c_void_p, ctypes.c_int, _f, _f, _f, _f, _f, _f, _u8, _i64, _P],
                               ctypes.c_int),

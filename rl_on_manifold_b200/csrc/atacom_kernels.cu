@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <type_traits>
 
@@ -34,7 +35,10 @@ namespace {
 #define ATACOM_STEP_DUAL 1        // 1: dual projection in FP64 (atacom_dual.cuh); 0: fp32 structured path
 #endif
 #ifndef ATACOM_STEP_STAGED_IO
-#define ATACOM_STEP_STAGED_IO 0   // 1: per-warp bulk copies (cp.async.bulk + mbarrier) through shared memory; 0: every thread moves its own rows (measured 2 % faster)
+// I/O of the step kernels.  0: every thread moves its own rows (best on HBM-resident arrays, by 2 %);
+// 1: per-warp bulk copies (cp.async.bulk + mbarrier) through shared memory (best when the arrays are mapped
+// host memory: large PCIe requests, +30 % end to end); 2 (default): two instantiations, chosen per launch.
+#define ATACOM_STEP_STAGED_IO 2
 #endif
 #ifndef ATACOM_STEP_MAXNREG
 #define ATACOM_STEP_MAXNREG 128   // 448 threads = 14 warps, 4 on two of the SM sub-partitions: 16384 / (4 x 32) registers each
@@ -197,7 +201,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // spreads evenly over the SMs, ideally one block per SM: the body is a long fully unrolled instruction
 // stream and the block barriers between its phases keep all warps of the SM in the same code region,
 // so each instruction line is fetched once per SM rather than once per warp.
-template <class Env>
+template <class Env, bool BULK_IO>
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
                                                                     const __grid_constant__ DualConsts<double> Kd) {
@@ -221,9 +225,8 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   unsigned char* region = atacom_smem + warp * SC::WARP_BYTES;
   const int64_t wenv0 = e_raw - lane;
   const int na = ec ? n : k;
-#if ATACOM_STEP_STAGED_IO
   uint64_t* bar = reinterpret_cast<uint64_t*>(atacom_smem + SC::MAX_WARPS * SC::WARP_BYTES) + warp;
-  const bool bulk = a.aligned16 && (wenv0 + 32 <= a.B);
+  const bool bulk = BULK_IO && a.aligned16 && (wenv0 + 32 <= a.B);
   float* sq = reinterpret_cast<float*>(region);
   float* sdq = sq + 32 * n;
   float* ss = sdq + 32 * n;
@@ -248,9 +251,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
 #pragma unroll
     for (int i = 0; i < G; ++i) s[i] = ss[lane * G1 + i];
     __syncwarp();     // the region is scratch from here on
-  } else
-#endif
-  {
+  } else {
     row_load<n>(a.q, e, q);
     row_load<n>(a.dq, e, dq);
     if (G > 0) row_load<G1>(a.s_in, e, s);
@@ -278,7 +279,6 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
 #endif
   // Outputs go back the same way: rows to the warp's region, slabs to HBM by the bulk-copy engine.
   if (valid && a.status) a.status[e] = st;
-#if ATACOM_STEP_STAGED_IO
   if (bulk) {
     __syncwarp();     // every lane is done with its scratch
 #pragma unroll
@@ -294,9 +294,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
       for (int w = 0; w < a.n_peers; ++w) bulk_s2g(a.peer[w] + (a.gather_row0 + wenv0) * n, sq, 128u * n);
       bulk_commit_wait_read();
     }
-  } else
-#endif
-  if (valid) {
+  } else if (valid) {
     if (a.ddq) row_store<n>(a.ddq, e, ddq);
     if (G > 0) row_store<G1>(a.s_out, e, so);
     for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
@@ -497,7 +495,20 @@ int check_common(int64_t B, const AtacomParams* p) {
   return ATACOM_OK;
 }
 
-template <class Env>
+// Opt the kernel in to its dynamic shared memory (once per process and instantiation).
+template <class Env, bool BULK_IO>
+bool configure_step_kernel() {
+  static int state = 0;   // 0: not yet, 1: done, -1: failed
+  if (state == 0) {
+    constexpr size_t smem = StepScratch<Env>::BYTES;
+    state = (smem <= 48 * 1024 ||
+             cudaFuncSetAttribute(atacom_step_kernel<Env, BULK_IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)) == cudaSuccess) ? 1 : -1;
+  }
+  return state == 1;
+}
+
+template <class Env, bool BULK_IO = (ATACOM_STEP_STAGED_IO == 1)>
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
                 float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0) {
@@ -521,16 +532,8 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const int tpb = step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   constexpr size_t smem = StepScratch<Env>::BYTES;
-  if (smem > 48 * 1024) {
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-      if (cudaFuncSetAttribute(atacom_step_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)) != cudaSuccess)
-        return ATACOM_ERR_CUDA;
-      configured = true;
-    }
-  }
-  atacom_step_kernel<Env><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
+  if (!configure_step_kernel<Env, BULK_IO>()) return ATACOM_ERR_CUDA;
+  atacom_step_kernel<Env, BULK_IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
       a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
@@ -794,13 +797,62 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
 }
 
 // ------------------------------------------------------------------ host-buffer entry points
+// The call a user of the NumPy reference binds: host arrays in, host arrays out.  The batch is cut into
+// chunks that pipeline H2D copy -> kernel -> D2H copy over a few streams.  The whole pipeline of one call
+// (every copy and every launch) is captured once into a CUDA graph and replayed while the caller keeps
+// passing the same buffers, batch size and parameters: one driver call per step instead of ~30.
 struct AtacomHostCtx {
   int64_t max_B;
   int chunks;
   float *q, *dq, *s_in, *alpha, *ddq, *s_out;
   uint8_t* status;
   cudaStream_t streams[4];
+  cudaEvent_t fork, join[4];
+  // cached graph and the call it was captured for
+  cudaGraphExec_t exec;
+  const void* key_ptr[7];
+  int64_t key_B;
+  int key_n, key_launches;
+  AtacomParams key_params;
+  int mode;
 };
+
+// Device-visible alias of a page-locked, mapped host pointer (nullptr if it is not one).
+static void* mapped_alias(const void* h) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+static int host_pipeline(AtacomHostCtx* c, int n, const float* q, const float* dq, const float* s_in,
+                         const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
+                         const AtacomParams* p, int n_streams) {
+  const int G = 5 + n;
+  const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? n : n - 1;
+  // chunk boundaries are multiples of TPB so every chunk's rows stay 16-byte aligned
+  int64_t per = (B + c->chunks - 1) / c->chunks;
+  per = (per + TPB - 1) / TPB * TPB;
+  int rc = ATACOM_OK;
+  int ci = 0;
+  for (int64_t e0 = 0; e0 < B && rc == ATACOM_OK; e0 += per, ++ci) {
+    const int64_t nb = (B - e0) < per ? (B - e0) : per;
+    cudaStream_t st = c->streams[ci % n_streams];
+    cudaMemcpyAsync(c->q + e0 * n, q + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->dq + e0 * n, dq + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->s_in + e0 * G, s_in + e0 * G, sizeof(float) * G * nb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->alpha + e0 * na, alpha + e0 * na, sizeof(float) * na * nb, cudaMemcpyHostToDevice, st);
+    rc = atacom_iiwa_step(n, c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
+                          c->ddq + e0 * n, c->s_out + e0 * G, status ? c->status + e0 : nullptr, nullptr, nb, p,
+                          st);
+    cudaMemcpyAsync(ddq + e0 * n, c->ddq + e0 * n, sizeof(float) * n * nb, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(s_out + e0 * G, c->s_out + e0 * G, sizeof(float) * G * nb, cudaMemcpyDeviceToHost, st);
+    if (status) cudaMemcpyAsync(status + e0, c->status + e0, nb, cudaMemcpyDeviceToHost, st);
+  }
+  return rc;
+}
 
 int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   if (!out) return ATACOM_ERR_NULL_POINTER;
@@ -817,6 +869,12 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
             cudaMalloc(&c->s_in, g_bytes) == cudaSuccess && cudaMalloc(&c->s_out, g_bytes) == cudaSuccess &&
             cudaMalloc(&c->status, max_B) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+  constexpr bool HOST_BULK = ATACOM_STEP_STAGED_IO != 0;
+  ok = ok && configure_step_kernel<IiwaEnv<6>, false>() && configure_step_kernel<IiwaEnv<7>, false>() &&
+       configure_step_kernel<IiwaEnv<6>, HOST_BULK>() && configure_step_kernel<IiwaEnv<7>, HOST_BULK>();   // not while capturing
+  step_block_size(1);
+  ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     delete c;
@@ -826,11 +884,21 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   return ATACOM_OK;
 }
 
+int atacom_host_ctx_set_mode(AtacomHostCtx* c, int mode) {
+  if (!c) return ATACOM_ERR_NULL_POINTER;
+  if (mode != ATACOM_HOST_AUTO && mode != ATACOM_HOST_STAGED && mode != ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
+  c->mode = mode;
+  return ATACOM_OK;
+}
+
 int atacom_host_ctx_destroy(AtacomHostCtx* c) {
   if (!c) return ATACOM_OK;
+  if (c->exec) cudaGraphExecDestroy(c->exec);
   cudaFree(c->q); cudaFree(c->dq); cudaFree(c->alpha); cudaFree(c->ddq);
   cudaFree(c->s_in); cudaFree(c->s_out); cudaFree(c->status);
   for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->streams[i]);
+  cudaEventDestroy(c->fork);
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(c->join[i]);
   delete c;
   return ATACOM_OK;
 }
@@ -841,32 +909,69 @@ int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* 
   if (!c || !p || !q || !dq || !s_in || !alpha || !ddq || !s_out) return ATACOM_ERR_NULL_POINTER;
   if (n != 6 && n != 7) return ATACOM_ERR_BAD_DIMS;
   if (B < 0 || B > c->max_B) return ATACOM_ERR_BAD_DIMS;
+  int rc = check_common(B, p);
+  if (rc) return rc;
   if (B == 0) return ATACOM_OK;
-  const int G = 5 + n;
-  const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? n : n - 1;
-  // chunk boundaries are multiples of TPB so every chunk's slabs stay 16-byte aligned
-  int64_t per = (B + c->chunks - 1) / c->chunks;
-  per = (per + TPB - 1) / TPB * TPB;
-  int rc = ATACOM_OK;
-  int ci = 0;
-  for (int64_t e0 = 0; e0 < B && rc == ATACOM_OK; e0 += per, ++ci) {
-    const int64_t nb = (B - e0) < per ? (B - e0) : per;
-    cudaStream_t st = c->streams[ci & 3];
-    cudaMemcpyAsync(c->q + e0 * n, q + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->dq + e0 * n, dq + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->s_in + e0 * G, s_in + e0 * G, sizeof(float) * G * nb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->alpha + e0 * na, alpha + e0 * na, sizeof(float) * na * nb, cudaMemcpyHostToDevice, st);
-    rc = atacom_iiwa_step(n, c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
-                          c->ddq + e0 * n, c->s_out + e0 * G, status ? c->status + e0 : nullptr, nullptr, nb, p,
-                          st);
-    cudaMemcpyAsync(ddq + e0 * n, c->ddq + e0 * n, sizeof(float) * n * nb, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(s_out + e0 * G, c->s_out + e0 * G, sizeof(float) * G * nb, cudaMemcpyDeviceToHost, st);
-    if (status) cudaMemcpyAsync(status + e0, c->status + e0, nb, cudaMemcpyDeviceToHost, st);
+  if (c->mode != ATACOM_HOST_STAGED) {
+    // zero-copy: one launch on the device aliases of the caller's buffers; loads and stores cross PCIe
+    void* d[7] = {mapped_alias(q), mapped_alias(dq), mapped_alias(s_in), mapped_alias(alpha), mapped_alias(ddq),
+                  mapped_alias(s_out), status ? mapped_alias(status) : nullptr};
+    const bool all = d[0] && d[1] && d[2] && d[3] && d[4] && d[5] && (!status || d[6]);
+    if (all) {
+      const float *zq = static_cast<const float*>(d[0]), *zdq = static_cast<const float*>(d[1]);
+      const float *zs = static_cast<const float*>(d[2]), *za = static_cast<const float*>(d[3]);
+      float *zddq = static_cast<float*>(d[4]), *zso = static_cast<float*>(d[5]);
+      uint8_t* zst = static_cast<uint8_t*>(d[6]);
+      constexpr bool HOST_BULK = ATACOM_STEP_STAGED_IO != 0;
+      rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_BULK>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0])
+                  : launch_step<IiwaEnv<7>, HOST_BULK>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0]);
+      if (rc != ATACOM_OK) return rc;
+      if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+      return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+    }
+    if (c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
   }
-  for (int i = 0; i < 4; ++i)
-    if (cudaStreamSynchronize(c->streams[i]) != cudaSuccess) rc = ATACOM_ERR_CUDA;
-  if (rc == ATACOM_OK && cudaGetLastError() != cudaSuccess) rc = ATACOM_ERR_CUDA;
-  return rc;
+  const void* key[7] = {q, dq, s_in, alpha, ddq, s_out, status};
+  bool hit = c->exec != nullptr && c->key_B == B && c->key_n == n &&
+             memcmp(&c->key_params, p, sizeof(AtacomParams)) == 0;
+  for (int i = 0; i < 7 && hit; ++i) hit = c->key_ptr[i] == key[i];
+  if (!hit) {
+    if (c->exec) {
+      cudaGraphExecDestroy(c->exec);
+      c->exec = nullptr;
+    }
+    // capture: stream 0 is the origin, the others fork from it and join back
+    cudaGraph_t graph = nullptr;
+    const int ns = c->chunks < 4 ? c->chunks : 4;
+    bool ok = cudaStreamBeginCapture(c->streams[0], cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      cudaEventRecord(c->fork, c->streams[0]);
+      for (int i = 1; i < ns; ++i) cudaStreamWaitEvent(c->streams[i], c->fork, 0);
+      const int64_t before = g_launches.load(std::memory_order_relaxed);
+      rc = host_pipeline(c, n, q, dq, s_in, alpha, ddq, s_out, status, B, p, ns);
+      c->key_launches = static_cast<int>(g_launches.exchange(before, std::memory_order_relaxed) - before);   // captured, not run
+      for (int i = 1; i < ns; ++i) {
+        cudaEventRecord(c->join[i], c->streams[i]);
+        cudaStreamWaitEvent(c->streams[0], c->join[i], 0);
+      }
+      ok = cudaStreamEndCapture(c->streams[0], &graph) == cudaSuccess && graph != nullptr && rc == ATACOM_OK;
+    }
+    if (ok) ok = cudaGraphInstantiate(&c->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      c->exec = nullptr;
+      return rc != ATACOM_OK ? rc : ATACOM_ERR_CUDA;
+    }
+    for (int i = 0; i < 7; ++i) c->key_ptr[i] = key[i];
+    c->key_B = B;
+    c->key_n = n;
+    c->key_params = *p;
+  }
+  if (cudaGraphLaunch(c->exec, c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+  g_launches.fetch_add(c->key_launches, std::memory_order_relaxed);   // kernel launches inside the replayed graph
+  if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
 }
 
 }  // extern "C"

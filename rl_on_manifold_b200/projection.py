@@ -221,9 +221,14 @@ class HostContext:
     """Host-buffer entry point (`atacom_iiwa_step_host`): NumPy / pinned-tensor in, NumPy out,
     copies inside the call — what a caller of the NumPy reference binds."""
 
-    def __init__(self, max_B, chunks=4):
+    MODES = {"auto": _lib.HOST_AUTO, "staged": _lib.HOST_STAGED, "zero_copy": _lib.HOST_ZERO_COPY}
+
+    def __init__(self, max_B, chunks=2, mode="auto"):
+        """mode: 'staged' (device staging buffers + copy engines, replayed as a CUDA graph), 'zero_copy' (the
+        kernel works on the caller's page-locked buffers over PCIe) or 'auto' (zero-copy when possible)."""
         self._ctx = ctypes.c_void_p()
         _lib.check(_lib.lib.atacom_host_ctx_create(ctypes.byref(self._ctx), max_B, chunks))
+        _lib.check(_lib.lib.atacom_host_ctx_set_mode(self._ctx, self.MODES[mode]))
         self.max_B = max_B
 
     def iiwa_step(self, n, q, dq, s, alpha, ddq, s_out, params, status=None):

@@ -245,15 +245,33 @@ def test_empty_and_tiny_batches(cuda_device):
         assert torch.isfinite(ddq).all()
 
 
-def test_host_buffer_entry_point(cuda_device):
+@pytest.mark.parametrize("mode", ["staged", "zero_copy", "auto"])
+def test_host_buffer_entry_point(cuda_device, mode):
+    """atacom_iiwa_step_host: host arrays in, host arrays out, bit-identical to the device-resident call on
+    both data paths (copy engines + CUDA graph replay; kernel working on the mapped host buffers)."""
     p = _lib.default_params("iiwa", 6)
     B = 5000
     q, dq, s, alpha = synthetic.device_batch("iiwa", B, 77, cuda_device, 6, p)
     ddq, s_out = projection.step("iiwa", q, dq, s, alpha, p)
-    ctx = projection.HostContext(B, chunks=4)
+    ctx = projection.HostContext(B, chunks=4, mode=mode)
     h = [t.cpu().pin_memory() for t in (q, dq, s, alpha)]
     ddq_h = torch.empty(B, 6).pin_memory()
     s_h = torch.empty(B, 11).pin_memory()
-    ctx.iiwa_step(6, *h, ddq_h, s_h, p)
-    assert torch.equal(ddq_h, ddq.cpu()) and torch.equal(s_h, s_out.cpu())
+    st_h = torch.zeros(B, dtype=torch.uint8).pin_memory()
+    for rep in range(3):                     # the second and third call replay the cached graph
+        ddq_h.zero_()
+        ctx.iiwa_step(6, *h, ddq_h, s_h, p, status=st_h)
+        assert torch.equal(ddq_h, ddq.cpu()) and torch.equal(s_h, s_out.cpu())
+    # a different batch size / buffer invalidates the cached pipeline
+    ctx.iiwa_step(6, *[t[:1234] for t in h], ddq_h[:1234], s_h[:1234], p)
+    assert torch.equal(ddq_h[:1234], ddq.cpu()[:1234])
+    if mode != "zero_copy":                  # pageable host memory goes through the staged path
+        hp = [t.cpu().numpy().copy() for t in (q, dq, s, alpha)]
+        out_ddq, out_s = np.zeros((B, 6), np.float32), np.zeros((B, 11), np.float32)
+        ctx.iiwa_step(6, *hp, out_ddq, out_s, p)
+        assert np.array_equal(out_ddq, ddq.cpu().numpy()) and np.array_equal(out_s, s_out.cpu().numpy())
+    else:
+        hp = [t.cpu().numpy().copy() for t in (q, dq, s, alpha)]
+        with pytest.raises(_lib.AtacomError):
+            ctx.iiwa_step(6, *hp, np.zeros((B, 6), np.float32), np.zeros((B, 11), np.float32), p)
     ctx.close()
