@@ -40,6 +40,12 @@ namespace {
 // host memory: large PCIe requests, +30 % end to end); 2 (default): two instantiations, chosen per launch.
 #define ATACOM_STEP_STAGED_IO 2
 #endif
+#ifndef ATACOM_X_BULK_LOAD      // experiments: which half of the I/O the bulk instantiation moves with cp.async.bulk
+#define ATACOM_X_BULK_LOAD 1
+#endif
+#ifndef ATACOM_X_BULK_STORE
+#define ATACOM_X_BULK_STORE 1
+#endif
 #ifndef ATACOM_STEP_MAXNREG
 #define ATACOM_STEP_MAXNREG 128   // 448 threads = 14 warps, 4 on two of the SM sub-partitions: 16384 / (4 x 32) registers each
 #endif
@@ -231,7 +237,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   float* sdq = sq + 32 * n;
   float* ss = sdq + 32 * n;
   float* sa = ss + 32 * G;
-  if (bulk) {
+  if (bulk && ATACOM_X_BULK_LOAD) {
     if (lane == 0) {
       mbar_init(bar, 1);
       mbar_expect_tx(bar, 4u * 32u * static_cast<uint32_t>(2 * n + G + na));
@@ -277,27 +283,36 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   Env::template eval<float, double>(P, q, dq, R);
   const uint8_t st = step_from_raw<float, double, D, Env::NDIAG, ATACOM_PHASE_BARRIERS != 0>(P, R, dq, s, al, ddq, so, dbg);
 #endif
-  // Outputs go back the same way: rows to the warp's region, slabs to HBM by the bulk-copy engine.
-  if (valid && a.status) a.status[e] = st;
-  if (bulk) {
+  // Outputs go back the same way: rows to the warp's region, slabs to HBM by the bulk-copy engine.  Thread and
+  // row indices are recomputed here (a volatile read of %tid.x cannot be merged with the one at the top), so
+  // that nothing of the prologue stays live in registers across the projection.
+  unsigned tid2;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid2));
+  const int lane2 = tid2 & 31;
+  const int64_t e2 = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid2;
+  const int64_t wenv2 = e2 - lane2;
+  if (e2 < a.B && a.status) a.status[e2] = st;
+  if (BULK_IO && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
+    float* oq = reinterpret_cast<float*>(atacom_smem + (tid2 >> 5) * SC::WARP_BYTES);
+    float* os = oq + 32 * n;
     __syncwarp();     // every lane is done with its scratch
 #pragma unroll
-    for (int j = 0; j < n; ++j) sq[lane * n + j] = ddq[j];
+    for (int j = 0; j < n; ++j) oq[lane2 * n + j] = ddq[j];
 #pragma unroll
-    for (int i = 0; i < G; ++i) ss[lane * G1 + i] = so[i];
+    for (int i = 0; i < G; ++i) os[lane2 * G1 + i] = so[i];
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      if (a.ddq) bulk_s2g(a.ddq + wenv0 * n, sq, 128u * n);
-      if (G > 0) bulk_s2g(a.s_out + wenv0 * G, ss, 128u * G);
+    if (lane2 == 0) {
+      if (a.ddq) bulk_s2g(a.ddq + wenv2 * n, oq, 128u * n);
+      if (G > 0) bulk_s2g(a.s_out + wenv2 * G, os, 128u * G);
       // fused all-gather: this warp's slab of rows straight into every rank's gather buffer
-      for (int w = 0; w < a.n_peers; ++w) bulk_s2g(a.peer[w] + (a.gather_row0 + wenv0) * n, sq, 128u * n);
+      for (int w = 0; w < a.n_peers; ++w) bulk_s2g(a.peer[w] + (a.gather_row0 + wenv2) * n, oq, 128u * n);
       bulk_commit_wait_read();
     }
-  } else if (valid) {
-    if (a.ddq) row_store<n>(a.ddq, e, ddq);
-    if (G > 0) row_store<G1>(a.s_out, e, so);
-    for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
+  } else if (e2 < a.B) {
+    if (a.ddq) row_store<n>(a.ddq, e2, ddq);
+    if (G > 0) row_store<G1>(a.s_out, e2, so);
+    for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e2, ddq);
   }
 }
 
