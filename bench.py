@@ -136,7 +136,7 @@ def reference_arm(args):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=desc),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -310,14 +310,32 @@ def ours(args):
         barrier()
         return e0.elapsed_time(e1)
 
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             graph_ms = timed_graph(kernel_only, args.steps)
-            if graph_ms < total_ms:
-                total_ms = kernel_ms = graph_ms
+            if world > 1:
+                t = torch.tensor([graph_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                graph_ms = float(t.item())
+            if graph_ms < kernel_ms:
+                kernel_ms = graph_ms
+            if world == 1 and graph_ms < total_ms:
+                total_ms = graph_ms
                 launch_mode = "CUDA graph of %d launches, one replay" % args.steps
         except Exception as exc:                         # pragma: no cover
             launch_mode += " (graph capture failed: %s)" % type(exc).__name__
+        if world > 1 and fused is not None:
+            # the fused step (kernel with peer-store epilogue + symmetric-memory barrier) replayed as a graph
+            try:
+                fg_ms = timed_graph(step_fused, args.steps)
+                t = torch.tensor([fg_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                fg_ms = float(t.item())
+                if fg_ms < total_ms:
+                    total_ms, gather_mode = fg_ms, fused_note
+                    launch_mode = "CUDA graph of %d fused steps, one replay" % args.steps
+            except Exception as exc:                     # pragma: no cover
+                launch_mode += " (fused-step graph capture failed: %s)" % type(exc).__name__
 
     # End to end through the host-buffer entry point: pinned host arrays in, pinned host arrays out, every
     # byte of the step's inputs and outputs crosses PCIe inside the timed region.  Two data paths of the same
@@ -401,12 +419,32 @@ def ours(args):
         )
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _reserve_stdout():
+    """Libraries (NCCL's version banner, torchrun warnings) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the rest of the process and keep the real stdout for the result line."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
+RESULT_OUT = None
+
+
+def emit(line):
+    out = RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global RESULT_OUT
+    RESULT_OUT = _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -48,8 +48,9 @@ def circle_traj(cls, act_dim, steps, seed, fixed=None):
         st, r, _, _ = env.step(a)
         acts.append(a); states.append(st.copy()); ss.append(env.s.copy()); rews.append(r)
         aa.append(env._act_a.copy()); ab.append(env._act_b.copy()); ae.append(env._act_err.copy())
+    logs = np.array(env.get_constraints_logs())          # (c_avg, c_max, c_dq_max) over the trajectory
     return dict(actions=np.array(acts), states=np.array(states), s=np.array(ss), rewards=np.array(rews),
-                act_a=np.array(aa), act_b=np.array(ab), act_err=np.array(ae))
+                act_a=np.array(aa), act_b=np.array(ab), act_err=np.array(ae), logs=logs)
 
 for key, val in circle_traj(R.CircleEnvAtacom, 1, 500, 1, fixed=[[0.7], [-0.2], [1.5], [0.3]]).items():
     out["circleA_" + key] = val
@@ -81,14 +82,29 @@ np.random.seed(1)
 env = R.PointReachAtacom(n_objects=4, random_walk=True)
 st = env.reset().copy()
 rng = np.random.default_rng(3)
-pre, acts, s_hist, u_hist, post = [], [], [env.s.copy()], [], []
+pre, acts, s_hist, u_hist, post, obj_draws, rews = [], [], [env.s.copy()], [], [], [], []
+_uniform = np.random.uniform
 for i in range(300):
     a = np.array([0.5, -0.5]) if i == 0 else (np.array([1.0, 1.0]) if i == 1 else rng.uniform(-1, 1, 2))
     pre.append(env._state.copy())
-    env.step(a)
+    draws = []
+
+    def _recording_uniform(*args, **kwargs):             # the obstacles' random-walk draws of this step
+        v = _uniform(*args, **kwargs)
+        draws.append(np.array(v, dtype=np.float64))
+        return v
+
+    np.random.uniform = _recording_uniform
+    try:
+        _, r, _, _ = env.step(a)
+    finally:
+        np.random.uniform = _uniform
     acts.append(a); s_hist.append(env.s.copy()); u_hist.append(env._action.copy()); post.append(env._state.copy())
+    obj_draws.append(np.concatenate(draws)); rews.append(r)
 out["collC_pre"], out["collC_actions"], out["collC_s"], out["collC_u"], out["collC_post"] = \
     map(np.array, (pre, acts, s_hist, u_hist, post))
+out["collC_obj_draws"], out["collC_rewards"] = np.array(obj_draws), np.array(rews)   # draws: U(-1,1), [T, 2 * n_objects]
+out["collC_logs"] = np.array(env.get_constraints_logs())
 
 # ---------------------------------------------------------------- generic wrapper, synthetic ConstraintsSets
 class _Base(R.Environment):
