@@ -76,7 +76,9 @@ typedef struct AtacomParams {
   double env[ATACOM_ENV_PARAMS]; /* geometry constants, double because K_c amplifies their rounding:
                                     planar: l1 l2 l3 base_x base_y qmax[3] half_len half_wid;
                                     iiwa: base_x half_len half_wid height z4_min z7_min qmax[7];
-                                    point_reach: radius^2 K K_c                                        */
+                                    circle: action_scale base_dt goal_x goal_y;
+                                    point_reach: radius^2 K K_c action_scale base_dt goal_x goal_y wall_lo
+                                    wall_hi obst_lo obst_hi obst_action_scale obst_vel_max obst_circle_radius */
 } AtacomParams;
 
 const char* atacom_version(void);
@@ -140,6 +142,41 @@ int atacom_point_reach_step(int n_objects, const float* q, const float* dq, cons
                             void* stream);
 int atacom_point_reach_slack_init(int n_objects, const float* q, const float* obs_p, float* s,
                                   const uint8_t* mask, int64_t B, const AtacomParams* p, void* stream);
+
+/* ---- constraint statistics (AtacomEnvWrapper._update_constraint_stats / get_constraints_logs, atacom.py:201-216) ----
+ * Per environment c_i = max(|c_f(q)|, c_g(q)) (origin constraints) and c_dq_i = max_j(|dq_j| - vel_max_j).
+ * per_env: [B, 2] = (c_i, c_dq_i) or NULL; stats: 4 doubles in device memory or NULL, updated atomically:
+ * { sum of c_i, max of c_i, max of c_dq_i, number of samples } — initialise to { 0, -inf, -inf, 0 }; after an epoch
+ * (c_avg, c_max, c_dq_max) = (stats[0] / stats[3], stats[1], stats[2]). */
+int atacom_circle_constraint_stats(const float* q, const float* dq, float* per_env, double* stats, int64_t B,
+                                   const AtacomParams* p, void* stream);
+int atacom_planar_constraint_stats(const float* q, const float* dq, float* per_env, double* stats, int64_t B,
+                                   const AtacomParams* p, void* stream);
+int atacom_iiwa_constraint_stats(int n_ctrl_joints, const float* q, const float* dq, float* per_env, double* stats,
+                                 int64_t B, const AtacomParams* p, void* stream);
+
+/* ---- fused roll-outs of the two environments whose base dynamics are plain arithmetic ----
+ * T agent steps per launch with the state in registers: action scaling, projection, base-env integration,
+ * reward and the constraint log, in double precision throughout (state, slack and rewards are stored fp32).
+ *
+ * atacom_circle_rollout: CircleEnvAtacom / CircleEnvErrorCorrection.step for T steps
+ *   (atacom.py:106-115, circle_base.py:53-67,86-115, circle_atacom.py:26-27).  state: [B, 4] (x, y, dx, dy),
+ *   s: [B, 1], actions: [T, B, 1] (variant ATACOM) or [T, B, 2] (ERROR_CORRECTION), raw agent actions (clipped to
+ *   [-1, 1] and scaled here); rewards: [T, B] or NULL; stats as above, with the circle's own log
+ *   (c = max(|x^2+y^2-1|, -y-0.5), c_dq = max(|dx|, |dy|) - 1, taken BEFORE each step).
+ *
+ * atacom_point_reach_rollout: PointReachAtacom.step for T steps (collision_avoidance_atacom.py:29-48,
+ *   collision_avoidance_base.py:41-76).  state: [B, 4 + 4 G] (agent x y dx dy, then per obstacle x y dx dy),
+ *   s: [B, G], actions: [T, B, 2]; obstacle_draws: [T, B, 2 G] U(-1, 1) draws of the obstacles' random walk
+ *   (the reference draws them with np.random.uniform inside step), or NULL with obstacle_centers [B, 2 G] for the
+ *   circling obstacles starting at time0, or both NULL for static obstacles; stats[2] stays untouched
+ *   (the reference logs c_dq = 0). */
+int atacom_circle_rollout(float* state, float* s, const float* actions, float* rewards, double* stats,
+                          uint8_t* status, int64_t B, int T, const AtacomParams* p, void* stream);
+int atacom_point_reach_rollout(int n_objects, float* state, float* s, const float* actions,
+                               const float* obstacle_draws, const float* obstacle_centers, double time0,
+                               float* rewards, double* stats, uint8_t* status, int64_t B, int T,
+                               const AtacomParams* p, void* stream);
 
 /* ---- generic ConstraintsSet (atacom/constraints.py:46-82) ----
  * For a user-defined ConstraintsSet whose callbacks were evaluated batched by the caller:

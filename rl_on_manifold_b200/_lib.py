@@ -85,6 +85,12 @@ SIGNATURES = {
     "atacom_point_reach_step": ([ctypes.c_int, _f, _f, _f, _f, _f, _f, _f, _f, _u8, _f, _i64, _P, _stream],
                                 ctypes.c_int),
     "atacom_point_reach_slack_init": ([ctypes.c_int, _f, _f, _f, _u8, _i64, _P, _stream], ctypes.c_int),
+    "atacom_circle_constraint_stats": ([_f, _f, _f, _f, _i64, _P, _stream], ctypes.c_int),
+    "atacom_planar_constraint_stats": ([_f, _f, _f, _f, _i64, _P, _stream], ctypes.c_int),
+    "atacom_iiwa_constraint_stats": ([ctypes.c_int, _f, _f, _f, _f, _i64, _P, _stream], ctypes.c_int),
+    "atacom_circle_rollout": ([_f, _f, _f, _f, _f, _u8, _i64, ctypes.c_int, _P, _stream], ctypes.c_int),
+    "atacom_point_reach_rollout": ([ctypes.c_int, _f, _f, _f, _f, _f, ctypes.c_double, _f, _f, _u8, _i64, ctypes.c_int,
+                                    _P, _stream], ctypes.c_int),
     "atacom_generic_supported": ([ctypes.c_int, ctypes.c_int, ctypes.c_int], ctypes.c_int),
     "atacom_generic_step": ([ctypes.c_int, ctypes.c_int, ctypes.c_int, _f, _f, _f, _f, _f, _f, _f, _f, _u8, _f,
                              _i64, _P, _stream], ctypes.c_int),

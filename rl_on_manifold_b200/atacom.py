@@ -248,6 +248,10 @@ class AtacomEnvWrapper:
         return torch.cat(parts, 1)
 
     def _update_constraint_stats(self, q, dq):
+        if self._family is not None:      # built-in functor: one kernel, per-env (c_i, c_dq_i)
+            self.constr_logs.append(projection.constraint_stats(self._family, q.contiguous(), dq.contiguous(),
+                                                                self.params, n_ctrl_joints=self._n_ctrl_joints))
+            return
         c_i = self._origin_constraints(q, dq)
         F = self.dims['f']
         c_i = torch.cat([c_i[:, :F].abs(), c_i[:, F:]], 1)

@@ -60,6 +60,23 @@ struct RawConstraints {
   ATACOM_HD void put_b(int i, T v) { b[i] = v; }
 };
 
+// Sink that keeps only what the constraint statistics need (AtacomEnvWrapper._update_constraint_stats,
+// atacom.py:201-205): max over the rows of |c_f(q)| and c_g(q).  Everything else the functor computes
+// for it is dead code and disappears at compile time.
+template <typename T, typename HP, class D>
+struct StatsSink {
+  using JT = HP;
+  HP cmax;
+  ATACOM_HD StatsSink() : cmax(HP(-1e300)) {}
+  ATACOM_HD void put_c(int i, HP v) {
+    const HP a = (i < D::F) ? (v < HP(0) ? -v : v) : v;
+    cmax = a > cmax ? a : cmax;
+  }
+  ATACOM_HD void put_Jdq(int, HP) {}
+  ATACOM_HD void put_J(int, int, HP) {}
+  ATACOM_HD void put_b(int, T) {}
+};
+
 // sin and cos of a joint angle in double precision, ~1e-16 absolute: Cody-Waite reduction by
 // multiples of pi/2 and Taylor polynomials on [-pi/4, pi/4] (|x| < ~1e5; joint angles are < 3.1).
 // About 30 FP64 operations, a fraction of the library sincos(double).
@@ -452,6 +469,29 @@ inline DualConsts<HP> make_dual_consts(const ParamsT<T>& P, int F, int G) {
   c.dt = HP(P.dt);
   c.tol = HP(P.rref_tol);
   return c;
+}
+
+// ParamsT<float> (the C ABI struct) widened to another scalar type: the roll-out kernels run in double
+// throughout, so that a T-step roll-out tracks the float64 reference instead of accumulating fp32 rounding.
+template <typename To, typename From>
+inline ParamsT<To> widen_params(const ParamsT<From>& P) {
+  ParamsT<To> Q;
+  for (int i = 0; i < 4; ++i) Q.K_f[i] = To(P.K_f[i]);
+  for (int i = 0; i < 16; ++i) Q.K_g[i] = To(P.K_g[i]);
+  for (int i = 0; i < 20; ++i) Q.K_c[i] = To(P.K_c[i]);
+  for (int i = 0; i < 8; ++i) {
+    Q.K_q[i] = To(P.K_q[i]);
+    Q.vel_max[i] = To(P.vel_max[i]);
+    Q.acc_max[i] = To(P.acc_max[i]);
+  }
+  Q.dt = To(P.dt);
+  Q.rref_tol = To(P.rref_tol);
+  Q.variant = P.variant;
+  Q.bias_mode = P.bias_mode;
+  Q.clip_acc = P.clip_acc;
+  Q.reserved = P.reserved;
+  for (int i = 0; i < 24; ++i) Q.env[i] = P.env[i];
+  return Q;
 }
 
 // Sink of the dual path: K-scaled dense Jacobian rows go straight to the scratch Y, the diagonal rows

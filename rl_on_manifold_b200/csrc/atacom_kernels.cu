@@ -465,6 +465,242 @@ __global__ void __launch_bounds__(TPB) point_reach_slack_init_kernel(const float
   for (int i = 0; i < G_; ++i) s[e * G_ + i] = so[i];
 }
 
+// ------------------------------------------------------------------ constraint statistics and fused roll-outs
+// stats[4] (device, double): { sum of c_i, max of c_i, max of c_dq_i, number of samples } with
+// c_i = max(|c_f(q)|, c_g(q)) and c_dq_i = max_j(|dq_j| - vel_max_j) per environment and step
+// (atacom.py:201-216; circle_base.py:86-115 for the circle's own log).  One warp-reduced atomic update per warp.
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double(static_cast<long long>(old)) < v) {
+    const unsigned long long seen = atomicCAS(a, old, static_cast<unsigned long long>(__double_as_longlong(v)));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
+__device__ __forceinline__ void stats_commit(double* stats, double sum_c, double max_c, double max_dq, double count) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum_c += __shfl_xor_sync(0xffffffffu, sum_c, o);
+    count += __shfl_xor_sync(0xffffffffu, count, o);
+    max_c = fmax(max_c, __shfl_xor_sync(0xffffffffu, max_c, o));
+    max_dq = fmax(max_dq, __shfl_xor_sync(0xffffffffu, max_dq, o));
+  }
+  if ((threadIdx.x & 31) == 0 && count > 0.0) {
+    atomicAdd(stats + 0, sum_c);
+    atomic_max_double(stats + 1, max_c);
+    atomic_max_double(stats + 2, max_dq);
+    atomicAdd(stats + 3, count);
+  }
+}
+
+template <class Env>
+__global__ void __launch_bounds__(TPB) atacom_constraint_stats_kernel(const float* __restrict__ q,
+                                                                      const float* __restrict__ dq,
+                                                                      float* per_env, double* stats, int64_t B,
+                                                                      const __grid_constant__ ParamsT<float> P) {
+  using D = typename Env::D;
+  constexpr int n = D::n;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  double cm = -1e300, cdq = -1e300;
+  if (e < B) {
+    float qq[n], dd[n];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      qq[j] = q[e * n + j];
+      dd[j] = dq[e * n + j];
+      const double v = fabs(static_cast<double>(dd[j])) - static_cast<double>(P.vel_max[j]);
+      cdq = v > cdq ? v : cdq;
+    }
+    StatsSink<float, double, D> sink;
+    Env::template eval<float, double>(P, qq, dd, sink);
+    cm = sink.cmax;
+    if (per_env) {
+      per_env[e * 2] = static_cast<float>(cm);
+      per_env[e * 2 + 1] = static_cast<float>(cdq);
+    }
+  }
+  if (stats) stats_commit(stats, e < B ? cm : 0.0, cm, cdq, e < B ? 1.0 : 0.0);
+}
+
+struct RolloutArgs {
+  float* state;          // [B, state_dim], in / out
+  float* s;              // [B, G], in / out
+  const float* actions;  // [T, B, action_dim]
+  const float* draws;    // point reach: [T, B, 2 G] U(-1, 1) draws of the obstacles' random walk, or null
+  const float* centers;  // point reach: [B, 2 G] circle centres of the obstacles (when draws is null), or null
+  float* rewards;        // [T, B] or null
+  double* stats;         // [4] or null
+  uint8_t* status;       // [B] or null: OR of the status bits of every step
+  int64_t B;
+  int32_t T;
+  double time0;
+};
+
+// CircleEnvAtacom / CircleEnvErrorCorrection, T agent steps per launch with the state in registers:
+// AtacomEnvWrapper.step (atacom.py:106-115) -> CircularMotion.step (circle_base.py:53-67) -> hook
+// step_action_function (atacom.py:123-139).  env[] = action_scale, base time step, goal x, goal y.
+__global__ void __launch_bounds__(TPB) circle_rollout_kernel(const __grid_constant__ RolloutArgs a,
+                                                             const __grid_constant__ ParamsT<double> P,
+                                                             const __grid_constant__ DualConsts<double> Kd) {
+  using Env = CircleEnv;
+  using D = Env::D;
+  using DU = Dual<double, D, Env::NDIAG>;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  const bool valid = e < a.B;
+  const int64_t ee = valid ? e : a.B - 1;
+  const bool ec = P.variant == VARIANT_EC;
+  const int na = ec ? 2 : 1;
+  double st[4], s[1];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st[j] = a.state[ee * 4 + j];
+  s[0] = a.s[ee];
+  const double scale = P.env[0], dt = P.env[1];
+  const double alpha_max = P.acc_max[0] > P.acc_max[1] ? P.acc_max[0] : P.acc_max[1];   // atacom.py:71
+  double sum_c = 0.0, max_c = -1e300, max_dq = -1e300;
+  uint8_t status = 0;
+  for (int t = 0; t < a.T; ++t) {
+    double al[2] = {0.0, 0.0};
+    for (int j = 0; j < na; ++j) {
+      double v = a.actions[(static_cast<int64_t>(t) * a.B + ee) * na + j];
+      v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);                                         // atacom.py:107
+      al[j] = v * (ec ? P.acc_max[j] : alpha_max);                                       // :108 / ec_wrapper:105-106
+    }
+    // CircularMotion.check_constraint (circle_base.py:86-92), logged before the step
+    {
+      const double c1 = fabs(st[0] * st[0] + st[1] * st[1] - 1.0), c2 = -st[1] - 0.5;
+      const double cm = c1 > c2 ? c1 : c2;
+      const double c3 = fabs(st[2]) - 1.0, c4 = fabs(st[3]) - 1.0;
+      sum_c += cm;
+      max_c = cm > max_c ? cm : max_c;
+      max_dq = fmax(max_dq, c3 > c4 ? c3 : c4);
+    }
+    double ddq[2], so[1];
+    LocalStore<double, DU::Y_SIZE> Ys;
+    LocalStore<double, DU::L_SIZE> Ls;
+    uint8_t stp = step_dual<Env, double, double>(P, Kd, Ys, Ls, st, st + 2, s, al, ddq, so, nullptr);
+    if (stp & ST_DENSE_PATH)
+      stp = ST_DENSE_PATH | step_general_outlined<Env, double, double>(P, st, st + 2, s, al, ddq, so, nullptr);
+    status |= stp;
+    s[0] = so[0];
+    double r2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double u = ddq[j] / P.acc_max[j];                                                  // circle_atacom.py:26-27
+      u = (u < -1.0 ? -1.0 : (u > 1.0 ? 1.0 : u)) * scale;                               // circle_base.py:59-60
+      st[j] += st[2 + j] * dt + u * dt * dt / 2;                                         // :62
+      st[2 + j] += u * dt;                                                               // :63
+      const double d = P.env[2 + j] - st[j];
+      r2 += d * d;
+    }
+    if (a.rewards && valid) a.rewards[static_cast<int64_t>(t) * a.B + e] = static_cast<float>(exp(-sqrt(r2)));   // :65
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.state[e * 4 + j] = static_cast<float>(st[j]);
+    a.s[e] = static_cast<float>(s[0]);
+    if (a.status) a.status[e] = status;
+  }
+  if (a.stats) stats_commit(a.stats, valid ? sum_c : 0.0, valid ? max_c : -1e300, valid ? max_dq : -1e300,
+                            valid ? static_cast<double>(a.T) : 0.0);
+}
+
+// PointReachAtacom.step (collision_avoidance_atacom.py:29-48) -> PointGoalReach.step
+// (collision_avoidance_base.py:41-76), T steps per launch.  env[] = radius^2, K, K_c, action_scale, base time
+// step, goal x, goal y, wall lo, wall hi, obstacle lo, obstacle hi, obstacle action scale, obstacle speed limit,
+// obstacle circle radius.
+template <int G_>
+__global__ void __launch_bounds__(TPB) point_reach_rollout_kernel(const __grid_constant__ RolloutArgs a,
+                                                                  const __grid_constant__ ParamsT<double> P) {
+  constexpr int G = G_, SD = 4 + 4 * G_;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  const bool valid = e < a.B;
+  const int64_t ee = valid ? e : a.B - 1;
+  double q[2], dq[2], p[2 * G], dp[2 * G], s[G];
+  q[0] = a.state[ee * SD]; q[1] = a.state[ee * SD + 1];
+  dq[0] = a.state[ee * SD + 2]; dq[1] = a.state[ee * SD + 3];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    p[2 * i] = a.state[ee * SD + 4 + 4 * i];
+    p[2 * i + 1] = a.state[ee * SD + 5 + 4 * i];
+    dp[2 * i] = a.state[ee * SD + 6 + 4 * i];
+    dp[2 * i + 1] = a.state[ee * SD + 7 + 4 * i];
+    s[i] = a.s[ee * G + i];
+  }
+  const double scale = P.env[3], dt = P.env[4];
+  double sum_c = 0.0, max_c = -1e300, time = a.time0;
+  uint8_t status = 0;
+  for (int t = 0; t < a.T; ++t) {
+    double act[2], w[2], so[G];
+    act[0] = a.actions[(static_cast<int64_t>(t) * a.B + ee) * 2];
+    act[1] = a.actions[(static_cast<int64_t>(t) * a.B + ee) * 2 + 1];
+    {  // constr_logs.append([max(c_origin), 0]) (collision_avoidance_atacom.py:38-40)
+      double cm = -1e300;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const double dx = q[0] - p[2 * i], dy = q[1] - p[2 * i + 1];
+        const double c = P.env[0] - (dx * dx + dy * dy);
+        cm = c > cm ? c : cm;
+      }
+      sum_c += cm;
+      max_c = cm > max_c ? cm : max_c;
+    }
+    status |= PointReachEnv<G>::template step<double, double>(P, q, dq, p, dp, s, act, w, so, nullptr);
+#pragma unroll
+    for (int i = 0; i < G; ++i) s[i] = so[i];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double u = (w[j] < -1.0 ? -1.0 : (w[j] > 1.0 ? 1.0 : w[j])) * scale;          // base.py:44-45
+      q[j] += dq[j] * dt;                                                                // :47
+      dq[j] += u * dt;                                                                   // :48
+      if (q[j] <= P.env[7] || q[j] >= P.env[8]) dq[j] = -dq[j];                          // :50-52
+    }
+    if (a.draws) {                                                                       // random walk, :57-66
+#pragma unroll
+      for (int c = 0; c < 2 * G; ++c) {
+        p[c] += dp[c] * dt;
+        p[c] = p[c] < P.env[9] ? P.env[9] : (p[c] > P.env[10] ? P.env[10] : p[c]);
+        const double oa = a.draws[(static_cast<int64_t>(t) * a.B + ee) * (2 * G) + c] * P.env[11];
+        if (p[c] <= P.env[9] || p[c] >= P.env[10]) dp[c] = -dp[c];
+        dp[c] += oa * dt;
+        dp[c] = dp[c] < -P.env[12] ? -P.env[12] : (dp[c] > P.env[12] ? P.env[12] : dp[c]);
+      }
+    } else if (a.centers) {                                                              // circles, :67-72
+      const double ang = time * 6.283185307179586, rad = P.env[13];
+      double sn, cs;
+      sincos(ang, &sn, &cs);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        p[2 * i] = a.centers[ee * 2 * G + 2 * i] + rad * cs;
+        p[2 * i + 1] = a.centers[ee * 2 * G + 2 * i + 1] + rad * sn;
+        dp[2 * i] = -2 * rad * 3.141592653589793 * sn;
+        dp[2 * i + 1] = 2 * rad * 3.141592653589793 * cs;
+      }
+    }
+    time += dt;                                                                          // :74
+    if (a.rewards && valid) {
+      const double dx = P.env[5] - q[0], dy = P.env[6] - q[1];
+      a.rewards[static_cast<int64_t>(t) * a.B + e] = static_cast<float>(-sqrt(dx * dx + dy * dy) / (8.0 * 1.4142135623730951));   // :75
+    }
+  }
+  if (valid) {
+    a.state[e * SD] = static_cast<float>(q[0]); a.state[e * SD + 1] = static_cast<float>(q[1]);
+    a.state[e * SD + 2] = static_cast<float>(dq[0]); a.state[e * SD + 3] = static_cast<float>(dq[1]);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      a.state[e * SD + 4 + 4 * i] = static_cast<float>(p[2 * i]);
+      a.state[e * SD + 5 + 4 * i] = static_cast<float>(p[2 * i + 1]);
+      a.state[e * SD + 6 + 4 * i] = static_cast<float>(dp[2 * i]);
+      a.state[e * SD + 7 + 4 * i] = static_cast<float>(dp[2 * i + 1]);
+      a.s[e * G + i] = static_cast<float>(s[i]);
+    }
+    if (a.status) a.status[e] = status;
+  }
+  if (a.stats) stats_commit(a.stats, valid ? sum_c : 0.0, valid ? max_c : -1e300, valid ? 0.0 : -1e300,
+                            valid ? static_cast<double>(a.T) : 0.0);
+}
+
 // ------------------------------------------------------------------ host-side helpers
 inline const ParamsT<float>& as_params(const AtacomParams* p) {
   return *reinterpret_cast<const ParamsT<float>*>(p);
@@ -567,6 +803,19 @@ int launch_slack_init(const float* q, const float* dq, float* s, const uint8_t* 
   return check_launch();
 }
 
+template <class Env>
+int launch_stats(const float* q, const float* dq, float* per_env, double* stats, int64_t B,
+                        const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (B == 0) return ATACOM_OK;
+  if (!q || !dq || (!per_env && !stats)) return ATACOM_ERR_NULL_POINTER;
+  atacom_constraint_stats_kernel<Env><<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, dq, per_env, stats, B, as_params(p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
 void fill_common(AtacomParams* p) {
   for (size_t i = 0; i < sizeof(*p) / 4; ++i) reinterpret_cast<uint32_t*>(p)[i] = 0;
   p->rref_tol = 0.05f;  // atacom.py:128
@@ -609,6 +858,10 @@ int atacom_circle_default_params(AtacomParams* p) {
     p->acc_max[i] = 10.f;
   }
   p->dt = 0.01f;
+  p->env[0] = 10.0;   // CircularMotion.action_scale   circle_base.py:26
+  p->env[1] = 0.01;   // CircularMotion.time_step      circle_base.py:12
+  p->env[2] = 1.0;    // goal                          circle_base.py:65
+  p->env[3] = 0.0;
   return ATACOM_OK;
 }
 
@@ -675,6 +928,17 @@ int atacom_point_reach_default_params(AtacomParams* p) {
   p->env[0] = 0.36;   // collision_avoidance_atacom.py:75
   p->env[1] = 0.5;    // :14
   p->env[2] = 100.0;  // :13
+  p->env[3] = 10.0;   // PointGoalReach.action_scale             collision_avoidance_base.py:19
+  p->env[4] = 0.01;   // time_step                               :7
+  p->env[5] = 9.0;    // goal                                    :75
+  p->env[6] = 9.0;
+  p->env[7] = 0.0;    // walls                                   :50
+  p->env[8] = 10.0;
+  p->env[9] = 2.0;    // obstacle box                            :59,61
+  p->env[10] = 10.0;
+  p->env[11] = 10.0;  // obstacle random-walk action scale       :60
+  p->env[12] = 1.0;   // obstacle speed limit                    :66
+  p->env[13] = 2.0;   // obstacle circle radius                  :21
   return ATACOM_OK;
 }
 
@@ -775,6 +1039,64 @@ int atacom_point_reach_slack_init(int n_objects, const float* q, const float* ob
     default: return ATACOM_ERR_BAD_DIMS;
   }
 #undef ATACOM_PR_INIT
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------ constraint statistics, fused roll-outs
+int atacom_circle_constraint_stats(const float* q, const float* dq, float* per_env, double* stats, int64_t B,
+                                   const AtacomParams* p, void* stream) {
+  return launch_stats<CircleEnv>(q, dq, per_env, stats, B, p, stream);
+}
+int atacom_planar_constraint_stats(const float* q, const float* dq, float* per_env, double* stats, int64_t B,
+                                   const AtacomParams* p, void* stream) {
+  return launch_stats<PlanarEnv>(q, dq, per_env, stats, B, p, stream);
+}
+int atacom_iiwa_constraint_stats(int n, const float* q, const float* dq, float* per_env, double* stats, int64_t B,
+                                 const AtacomParams* p, void* stream) {
+  if (n == 6) return launch_stats<IiwaEnv<6>>(q, dq, per_env, stats, B, p, stream);
+  if (n == 7) return launch_stats<IiwaEnv<7>>(q, dq, per_env, stats, B, p, stream);
+  return ATACOM_ERR_BAD_DIMS;
+}
+
+int atacom_circle_rollout(float* state, float* s, const float* actions, float* rewards, double* stats,
+                          uint8_t* status, int64_t B, int T, const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (T < 0) return ATACOM_ERR_BAD_DIMS;
+  if (B == 0 || T == 0) return ATACOM_OK;
+  if (!state || !s || !actions) return ATACOM_ERR_NULL_POINTER;
+  RolloutArgs a{state, s, actions, nullptr, nullptr, rewards, stats, status, B, T, 0.0};
+  const ParamsT<double> Pd = widen_params<double>(as_params(p));
+  circle_rollout_kernel<<<blocks_for(B), TPB, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, Pd, make_dual_consts<double, double>(Pd, 1, 1));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
+int atacom_point_reach_rollout(int n_objects, float* state, float* s, const float* actions,
+                               const float* obstacle_draws, const float* obstacle_centers, double time0,
+                               float* rewards, double* stats, uint8_t* status, int64_t B, int T,
+                               const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (T < 0) return ATACOM_ERR_BAD_DIMS;
+  if (B == 0 || T == 0) return ATACOM_OK;
+  if (!state || !s || !actions) return ATACOM_ERR_NULL_POINTER;
+  RolloutArgs a{state, s, actions, obstacle_draws, obstacle_centers, rewards, stats, status, B, T, time0};
+  const ParamsT<double> Pd = widen_params<double>(as_params(p));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ATACOM_PR_ROLL(G_) point_reach_rollout_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(a, Pd)
+  switch (n_objects) {
+    ATACOM_POINT_DISPATCH(1, ATACOM_PR_ROLL)
+    ATACOM_POINT_DISPATCH(2, ATACOM_PR_ROLL)
+    ATACOM_POINT_DISPATCH(3, ATACOM_PR_ROLL)
+    ATACOM_POINT_DISPATCH(4, ATACOM_PR_ROLL)
+    ATACOM_POINT_DISPATCH(6, ATACOM_PR_ROLL)
+    ATACOM_POINT_DISPATCH(8, ATACOM_PR_ROLL)
+    default: return ATACOM_ERR_BAD_DIMS;
+  }
+#undef ATACOM_PR_ROLL
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
 }

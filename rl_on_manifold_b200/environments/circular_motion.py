@@ -29,6 +29,7 @@ class CircularMotion:
         self.action_scale = torch.tensor([10., 10.], device=self.device)
         self._gen = torch.Generator(device="cpu")
         self.constr_logs = list()
+        self._stats = None           # device accumulators of the fused roll-out path (projection.new_stats)
         self._state = None
 
     @property
@@ -98,12 +99,20 @@ class CircularMotion:
         return torch.cat([(q[:, :1] ** 2 + q[:, 1:2] ** 2 - 1), (-q[:, 1:2] - 0.5), dq.abs() - 1], 1)
 
     def get_constraints_logs(self):
-        logs = torch.stack(self.constr_logs, 0)                        # [T, B, 4]
-        c_avg = float(logs[..., :2].max(-1).values.mean())
-        c_max = float(logs[..., :2].max())
-        c_dq_max = float(logs[..., 2:].max())
-        self.constr_logs.clear()
-        return c_avg, c_max, c_dq_max
+        """(c_avg, c_max, c_dq_max) since the last call (circle_base.py:109-115): per-step logs of step() merged
+        with the device accumulators of the fused roll-out path."""
+        total, n, c_max, c_dq_max = 0.0, 0, -math.inf, -math.inf
+        if self.constr_logs:
+            logs = torch.stack(self.constr_logs, 0)                    # [T, B, 4]
+            per_step = logs[..., :2].max(-1).values
+            total, n = float(per_step.sum()), per_step.numel()
+            c_max, c_dq_max = float(logs[..., :2].max()), float(logs[..., 2:].max())
+            self.constr_logs.clear()
+        if self._stats is not None:
+            v = self._stats.cpu().tolist()
+            total, n, c_max, c_dq_max = total + v[0], n + int(v[3]), max(c_max, v[1]), max(c_dq_max, v[2])
+            self._stats = None
+        return total / max(n, 1), c_max, c_dq_max
 
 
 def _circle_sets():
@@ -122,6 +131,25 @@ def _circle_sets():
 
 
 class _CircleMixin:
+    def rollout(self, actions):
+        """T agent steps in ONE kernel launch (atacom_circle_rollout): `actions` [T, B, action_dim] raw agent
+        actions (CUDA float32).  Equivalent to T calls of step(); returns rewards [T, B].  State, slack and the
+        constraint log advance exactly as step() would advance them."""
+        from .. import projection
+        actions = torch.as_tensor(actions, dtype=torch.float32, device=self.device).contiguous()
+        base = self.env
+        if base._stats is None:
+            base._stats = projection.new_stats(self.device)
+        state = base._state.contiguous()
+        rewards = projection.circle_rollout(state, self.s, actions, self.params, stats=base._stats,
+                                            status=self._status)
+        if state.data_ptr() != base._state.data_ptr():
+            base._state.copy_(state)
+        self.state = base._state
+        self.q = self._get_q(self.state).contiguous()
+        self.dq = self._get_dq(self.state).contiguous()
+        return rewards
+
     def _get_q(self, state):
         return state[:, :2]
 

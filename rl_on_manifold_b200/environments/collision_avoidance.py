@@ -112,6 +112,7 @@ class PointReachAtacom(PointGoalReach):
         self._w = torch.zeros(n_envs, 2, device=self.device)
         self.status = torch.zeros(n_envs, dtype=torch.uint8, device=self.device)
         self.constr_logs = list()
+        self._stats = None
 
     def _split(self, state):
         B = state.shape[0]
@@ -140,8 +141,37 @@ class PointReachAtacom(PointGoalReach):
             return tuple(o[0].cpu().numpy() if isinstance(o, torch.Tensor) else o for o in out)
         return out
 
+    def rollout(self, actions, obstacle_draws=None):
+        """T steps in ONE kernel launch (atacom_point_reach_rollout): `actions` [T, B, 2]; with random_walk the
+        obstacles' U(-1, 1) draws [T, B, 2 n_objects] are taken from `obstacle_draws` or drawn here from the env's
+        generator.  Equivalent to T calls of step(); returns rewards [T, B]."""
+        actions = torch.as_tensor(actions, dtype=torch.float32, device=self.device).contiguous()
+        T, B, G = actions.shape[0], self.n_envs, self.n_objects
+        centers = None
+        if self.random_walk:
+            if obstacle_draws is None:
+                obstacle_draws = torch.rand(T, B, 2 * G, generator=self._gen) * 2 - 1
+            obstacle_draws = torch.as_tensor(obstacle_draws, dtype=torch.float32, device=self.device).contiguous()
+        else:
+            obstacle_draws = None
+            centers = self._obj_circle_center.reshape(B, 2 * G).contiguous()
+        if self._stats is None:
+            self._stats = projection.new_stats(self.device)
+        rewards = projection.point_reach_rollout(self._state, self.s, actions, self.params,
+                                                 obstacle_draws=obstacle_draws, obstacle_centers=centers,
+                                                 time0=self._time, stats=self._stats, status=self.status)
+        self._time += T * self.time_step
+        self.q, self.dq, self.p, self.dp = self._split(self._state)
+        return rewards
+
     def get_constraints_logs(self):
-        logs = torch.stack(self.constr_logs, 0)
-        c_avg, c_max, c_dq_max = float(logs[..., 0].mean()), float(logs[..., 0].max()), float(logs[..., 1].max())
-        self.constr_logs.clear()
-        return c_avg, c_max, c_dq_max
+        total, n, c_max, c_dq_max = 0.0, 0, -math.inf, 0.0
+        if self.constr_logs:
+            logs = torch.stack(self.constr_logs, 0)
+            total, n, c_max = float(logs[..., 0].sum()), logs[..., 0].numel(), float(logs[..., 0].max())
+            self.constr_logs.clear()
+        if self._stats is not None:
+            v = self._stats.cpu().tolist()
+            total, n, c_max = total + v[0], n + int(v[3]), max(c_max, v[1])
+            self._stats = None
+        return total / max(n, 1), c_max, c_dq_max

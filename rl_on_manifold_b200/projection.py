@@ -6,6 +6,7 @@ rejected: there is no CPU fallback (the NumPy oracle lives in `oracle/` and is t
 infrastructure).
 """
 import ctypes
+import math
 
 import torch
 
@@ -215,6 +216,91 @@ def generic_step(n, F, G, c, J, b, dq, s, alpha, params, *, ddq=None, s_out=None
                                           _ptr(w_dbg), B, ctypes.byref(params), _stream(dq))
     _lib.check(rc)
     return ddq, s_out
+
+
+# ------------------------------------------------------------------ constraint statistics, fused roll-outs
+def new_stats(device):
+    """Device accumulators of the constraint log: { sum c_i, max c_i, max c_dq_i, count } (float64 [4])."""
+    return torch.tensor([0.0, -math.inf, -math.inf, 0.0], dtype=torch.float64, device=device)
+
+
+def read_stats(stats):
+    """(c_avg, c_max, c_dq_max) as get_constraints_logs returns them (atacom.py:207-216)."""
+    v = stats.cpu().tolist()
+    return v[0] / max(v[3], 1.0), v[1], v[2]
+
+
+def constraint_stats(family, q, dq, params, *, n_ctrl_joints=6, per_env=None, stats=None):
+    """AtacomEnvWrapper._update_constraint_stats (atacom.py:201-205) for B environments: returns per_env [B, 2]
+    = (max(|c_f|, c_g), max_j(|dq_j| - vel_max_j)); `stats` (see new_stats) is updated in place if given."""
+    n, F, G = family_dims(family, n_ctrl_joints)
+    B = q.shape[0]
+    _check(q, "q", B, n)
+    _check(dq, "dq", B, n)
+    if per_env is None:
+        per_env = torch.empty(B, 2, device=q.device, dtype=torch.float32)
+    _check(per_env, "per_env", B, 2)
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 4 or not stats.is_cuda):
+        raise ValueError("stats must be a CUDA float64 tensor of 4 elements (projection.new_stats)")
+    with torch.cuda.device(q.device):
+        args = (_ptr(q), _ptr(dq), _ptr(per_env), _ptr(stats), B, ctypes.byref(params), _stream(q))
+        if family == "circle":
+            rc = _lib.lib.atacom_circle_constraint_stats(*args)
+        elif family == "planar":
+            rc = _lib.lib.atacom_planar_constraint_stats(*args)
+        elif family.startswith("iiwa"):
+            rc = _lib.lib.atacom_iiwa_constraint_stats(n, *args)
+        else:
+            raise ValueError(family)
+    _lib.check(rc)
+    return per_env
+
+
+def circle_rollout(state, s, actions, params, *, rewards=None, stats=None, status=None):
+    """T fused agent steps of CircleEnvAtacom / CircleEnvErrorCorrection (atacom.py:106-115,
+    circle_base.py:53-67): `state` [B, 4] and `s` [B, 1] are advanced in place, `actions` is [T, B, 1]
+    (or [T, B, 2] for the error-correction variant); returns rewards [T, B]."""
+    B = state.shape[0]
+    na = 2 if params.variant == _lib.VARIANT_ERROR_CORRECTION else 1
+    _check(state, "state", B, 4)
+    _check(s, "s", B, 1)
+    if actions.dim() != 3 or actions.shape[1:] != (B, na) or not actions.is_contiguous() or not actions.is_cuda \
+            or actions.dtype != torch.float32:
+        raise ValueError("actions: expected a contiguous CUDA float32 tensor of shape [T, %d, %d]" % (B, na))
+    T = actions.shape[0]
+    if rewards is None:
+        rewards = torch.empty(T, B, device=state.device, dtype=torch.float32)
+    if status is not None:
+        _check(status, "status", B, None, torch.uint8)
+    with torch.cuda.device(state.device):
+        rc = _lib.lib.atacom_circle_rollout(_ptr(state), _ptr(s), _ptr(actions), _ptr(rewards), _ptr(stats),
+                                            _ptr(status), B, T, ctypes.byref(params), _stream(state))
+    _lib.check(rc)
+    return rewards
+
+
+def point_reach_rollout(state, s, actions, params, *, obstacle_draws=None, obstacle_centers=None, time0=0.0,
+                        rewards=None, stats=None, status=None):
+    """T fused steps of PointReachAtacom (collision_avoidance_atacom.py:29-48 + collision_avoidance_base.py:41-76):
+    `state` [B, 4 + 4 G] and `s` [B, G] are advanced in place; `actions` [T, B, 2]; `obstacle_draws` [T, B, 2 G]
+    are the U(-1, 1) draws of the obstacles' random walk.  Returns rewards [T, B]."""
+    B, G = s.shape
+    _check(state, "state", B, 4 + 4 * G)
+    _check(s, "s", B, G)
+    T = actions.shape[0]
+    for name, t, shape in (("actions", actions, (T, B, 2)), ("obstacle_draws", obstacle_draws, (T, B, 2 * G)),
+                           ("obstacle_centers", obstacle_centers, (B, 2 * G))):
+        if t is not None and (tuple(t.shape) != shape or not t.is_contiguous() or not t.is_cuda
+                              or t.dtype != torch.float32):
+            raise ValueError("%s: expected a contiguous CUDA float32 tensor of shape %s" % (name, shape))
+    if rewards is None:
+        rewards = torch.empty(T, B, device=state.device, dtype=torch.float32)
+    with torch.cuda.device(state.device):
+        rc = _lib.lib.atacom_point_reach_rollout(G, _ptr(state), _ptr(s), _ptr(actions), _ptr(obstacle_draws),
+                                                 _ptr(obstacle_centers), float(time0), _ptr(rewards), _ptr(stats),
+                                                 _ptr(status), B, T, ctypes.byref(params), _stream(state))
+    _lib.check(rc)
+    return rewards
 
 
 class HostContext:

@@ -204,3 +204,32 @@ def test_generic_constraints_set_through_wrapper(cuda_device):
             continue
         worst = max(worst, np.abs(ddq[i] - o["ddq"]).max() / max(1.0, np.abs(o["w"]).max()))
     assert worst < 5e-5
+
+
+def test_env_rollout_equals_repeated_step(cuda_device, golden):
+    """env.rollout(actions) (one fused launch) against T calls of env.step(): states, rewards, constraint log."""
+    # circle, replaying the first steps of the reference episode in 64 identical environments
+    acts = torch.tensor(golden["circleA_actions"][:30], dtype=torch.float32, device=cuda_device)
+    B = 64
+    a = CircleEnvAtacom(n_envs=B, device=cuda_device); a.reset()
+    b = CircleEnvAtacom(n_envs=B, device=cuda_device); b.reset()
+    rew_a = a.rollout(acts[:, None, :].repeat(1, B, 1))
+    rew_b = torch.stack([b.step(acts[t][None, :].repeat(B, 1))[1] for t in range(acts.shape[0])])
+    np.testing.assert_allclose(a.state.cpu().numpy()[0], golden["circleA_states"][30], atol=2e-6)
+    np.testing.assert_allclose(a.state.cpu().numpy(), b.state.cpu().numpy(), atol=2e-4)
+    np.testing.assert_allclose(a.s.cpu().numpy(), b.s.cpu().numpy(), atol=2e-3)
+    np.testing.assert_allclose(rew_a.cpu().numpy(), rew_b.cpu().numpy(), atol=1e-4)
+    la, lb = a.get_constraints_logs(), b.get_constraints_logs()
+    np.testing.assert_allclose(la, lb, atol=1e-4)
+    # a later step() keeps working on the advanced state, and the merged log covers both paths
+    a.rollout(acts[:5, None, :].repeat(1, B, 1)); a.step(acts[5][None, :].repeat(B, 1))
+    assert np.isfinite(a.get_constraints_logs()).all()
+    # point reach with the recorded obstacle draws
+    draws = torch.tensor(golden["collC_obj_draws"][:30], dtype=torch.float32, device=cuda_device)
+    pacts = torch.tensor(golden["collC_actions"][:30], dtype=torch.float32, device=cuda_device)
+    env = PointReachAtacom(n_objects=4, random_walk=True, n_envs=1, device=cuda_device)
+    env.reset(golden["collC_pre"][0])
+    rew = env.rollout(pacts[:, None, :], draws[:, None, :])
+    np.testing.assert_allclose(env._state.cpu().numpy()[0], golden["collC_post"][29], atol=2e-5)
+    np.testing.assert_allclose(env.s.cpu().numpy()[0], golden["collC_s"][30], atol=2e-5)
+    np.testing.assert_allclose(rew.cpu().numpy()[:, 0], golden["collC_rewards"][:30], atol=1e-6)
