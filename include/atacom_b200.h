@@ -123,6 +123,18 @@ int atacom_iiwa_step_gather(int n_ctrl_joints, const float* q, const float* dq, 
                             const AtacomParams* p, void* stream, float* const* peer_ddq, int world,
                             int64_t row_offset);
 
+/* The same with the cross-rank synchronisation inside the kernel as well: when this launch has completed on a
+ * rank, the rows of EVERY rank are in that rank's gather buffer.  peer_flags[w] is rank w's flag array
+ * (uint32 [world], zero-initialised once, in peer-mapped memory like the gather buffers); local_sync points to
+ * 2 zero-initialised uint32 in this rank's own device memory (block counter, step sequence number).  The last
+ * block of the launch publishes the step to every rank (release, system scope) and waits for every rank's
+ * flag of the same step (acquire).  Every rank must issue the same sequence of launches; safe to capture in
+ * a CUDA graph (the sequence number lives in device memory). */
+int atacom_iiwa_step_gather_sync(int n_ctrl_joints, const float* q, const float* dq, const float* s_in,
+                                 const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
+                                 const AtacomParams* p, void* stream, float* const* peer_ddq, int world,
+                                 int64_t row_offset, uint32_t* const* peer_flags, uint32_t* local_sync, int rank);
+
 /* ---- AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149): s = sqrt(max(-2 g~, 0)) ----
  * mask (optional, may be NULL): uint8 [B]; only environments with mask != 0 are re-initialised. */
 int atacom_circle_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,

@@ -105,6 +105,10 @@ struct StepArgs {
   int64_t gather_row0;
   int32_t n_peers;
   int32_t aligned16;   // every array pointer (and peer buffer) is 16-byte aligned: bulk copies allowed
+  // in-kernel cross-rank barrier of the fused gather (null / unused otherwise)
+  uint32_t* peer_flags[ATACOM_MAX_PEERS];   // rank w's flag array [world]
+  uint32_t* local_sync;                     // this rank: { blocks done, step sequence number }
+  int32_t rank;
 };
 
 // ------------------------------------------------------------------ row access
@@ -200,6 +204,11 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_commit_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
@@ -207,7 +216,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // spreads evenly over the SMs, ideally one block per SM: the body is a long fully unrolled instruction
 // stream and the block barriers between its phases keep all warps of the SM in the same code region,
 // so each instruction line is fetched once per SM rather than once per warp.
-template <class Env, bool BULK_IO>
+template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: direct loads, bulk stores
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
                                                                     const __grid_constant__ DualConsts<double> Kd) {
@@ -232,7 +241,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   const int64_t wenv0 = e_raw - lane;
   const int na = ec ? n : k;
   uint64_t* bar = reinterpret_cast<uint64_t*>(atacom_smem + SC::MAX_WARPS * SC::WARP_BYTES) + warp;
-  const bool bulk = BULK_IO && a.aligned16 && (wenv0 + 32 <= a.B);
+  const bool bulk = IO == 1 && a.aligned16 && (wenv0 + 32 <= a.B);
   float* sq = reinterpret_cast<float*>(region);
   float* sdq = sq + 32 * n;
   float* ss = sdq + 32 * n;
@@ -292,7 +301,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   const int64_t e2 = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid2;
   const int64_t wenv2 = e2 - lane2;
   if (e2 < a.B && a.status) a.status[e2] = st;
-  if (BULK_IO && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
+  if (IO != 0 && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
     float* oq = reinterpret_cast<float*>(atacom_smem + (tid2 >> 5) * SC::WARP_BYTES);
     float* os = oq + 32 * n;
     __syncwarp();     // every lane is done with its scratch
@@ -307,12 +316,35 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
       if (G > 0) bulk_s2g(a.s_out + wenv2 * G, os, 128u * G);
       // fused all-gather: this warp's slab of rows straight into every rank's gather buffer
       for (int w = 0; w < a.n_peers; ++w) bulk_s2g(a.peer[w] + (a.gather_row0 + wenv2) * n, oq, 128u * n);
-      bulk_commit_wait_read();
+      if (a.local_sync != nullptr) bulk_commit_wait_all();   // the step is published below: writes must have landed
+      else bulk_commit_wait_read();
     }
   } else if (e2 < a.B) {
     if (a.ddq) row_store<n>(a.ddq, e2, ddq);
     if (G > 0) row_store<G1>(a.s_out, e2, so);
     for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e2, ddq);
+  }
+  // Fused gather, cross-rank barrier: the last block of this launch publishes the step to every rank and waits
+  // for every rank's flag of the same step, so kernel completion on a rank means its gather buffer is complete.
+  if (a.local_sync != nullptr) {
+    __syncthreads();                                   // every thread of the block has issued its peer stores
+    if (tid2 == 0) {
+      __threadfence_system();
+      const unsigned done = atomicAdd(a.local_sync, 1u);
+      if (done == gridDim.x - 1) {
+        atomicExch(a.local_sync, 0u);
+        const unsigned seq = atomicAdd(a.local_sync + 1, 1u) + 1u;
+        __threadfence_system();
+        for (int w = 0; w < a.n_peers; ++w)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[w] + a.rank), "r"(seq) : "memory");
+        for (int w = 0; w < a.n_peers; ++w) {
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.peer_flags[a.rank] + w) : "memory");
+          } while (static_cast<int>(seen - seq) < 0);
+        }
+      }
+    }
   }
 }
 
@@ -737,6 +769,17 @@ int step_block_size(int64_t B) {
   return static_cast<int>(tpb);
 }
 
+// Fused gather: rows to the peers as per-warp bulk stores (large NVLink writes) or as per-thread row stores.
+// ATACOM_GATHER_IO = rows | bulk overrides the default (experiments).
+bool gather_bulk_stores() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* f = getenv("ATACOM_GATHER_IO");
+    mode = (f && f[0] == 'r') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 int check_common(int64_t B, const AtacomParams* p) {
   if (!p) return ATACOM_ERR_NULL_POINTER;
   if (B < 0 || B > (int64_t(1) << 31) * TPB) return ATACOM_ERR_BAD_DIMS;
@@ -747,22 +790,23 @@ int check_common(int64_t B, const AtacomParams* p) {
 }
 
 // Opt the kernel in to its dynamic shared memory (once per process and instantiation).
-template <class Env, bool BULK_IO>
+template <class Env, int IO>
 bool configure_step_kernel() {
   static int state = 0;   // 0: not yet, 1: done, -1: failed
   if (state == 0) {
     constexpr size_t smem = StepScratch<Env>::BYTES;
     state = (smem <= 48 * 1024 ||
-             cudaFuncSetAttribute(atacom_step_kernel<Env, BULK_IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+             cudaFuncSetAttribute(atacom_step_kernel<Env, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)) == cudaSuccess) ? 1 : -1;
   }
   return state == 1;
 }
 
-template <class Env, bool BULK_IO = (ATACOM_STEP_STAGED_IO == 1)>
+template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : 0)>
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
-                float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0) {
+                float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0,
+                uint32_t* const* peer_flags = nullptr, uint32_t* local_sync = nullptr, int rank = 0) {
   int rc = check_common(B, p);
   if (rc) return rc;
   using D = typename Env::D;
@@ -771,7 +815,15 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   if (!q || !dq || (!ddq && n_peers == 0) || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
-  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0};
+  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0, {}, nullptr, rank};
+  if (local_sync) {
+    if (!peer_flags || n_peers < 1 || rank < 0 || rank >= n_peers) return ATACOM_ERR_BAD_PARAM;
+    for (int w = 0; w < n_peers; ++w) {
+      if (!peer_flags[w]) return ATACOM_ERR_NULL_POINTER;
+      a.peer_flags[w] = peer_flags[w];
+    }
+    a.local_sync = local_sync;
+  }
   uintptr_t bits = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(s_in) |
                    reinterpret_cast<uintptr_t>(alpha) | reinterpret_cast<uintptr_t>(ddq) | reinterpret_cast<uintptr_t>(s_out);
   for (int w = 0; w < n_peers; ++w) {
@@ -783,8 +835,8 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const int tpb = step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   constexpr size_t smem = StepScratch<Env>::BYTES;
-  if (!configure_step_kernel<Env, BULK_IO>()) return ATACOM_ERR_CUDA;
-  atacom_step_kernel<Env, BULK_IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
+  if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
+  atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
       a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
@@ -966,12 +1018,45 @@ int atacom_iiwa_step_gather(int n, const float* q, const float* dq, const float*
                             float* ddq, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p,
                             void* stream, float* const* peer_ddq, int world, int64_t row_offset) {
   if (world < 1) return ATACOM_ERR_BAD_DIMS;
-  if (n == 6)
-    return launch_step<IiwaEnv<6>>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq, world,
-                                   row_offset);
-  if (n == 7)
-    return launch_step<IiwaEnv<7>>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq, world,
-                                   row_offset);
+  if (gather_bulk_stores()) {
+    if (n == 6)
+      return launch_step<IiwaEnv<6>, 2>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset);
+    if (n == 7)
+      return launch_step<IiwaEnv<7>, 2>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset);
+  } else {
+    if (n == 6)
+      return launch_step<IiwaEnv<6>, 0>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset);
+    if (n == 7)
+      return launch_step<IiwaEnv<7>, 0>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset);
+  }
+  return ATACOM_ERR_BAD_DIMS;
+}
+
+int atacom_iiwa_step_gather_sync(int n, const float* q, const float* dq, const float* s_in, const float* alpha,
+                                 float* ddq, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p,
+                                 void* stream, float* const* peer_ddq, int world, int64_t row_offset,
+                                 uint32_t* const* peer_flags, uint32_t* local_sync, int rank) {
+  if (world < 1 || !peer_flags || !local_sync) return ATACOM_ERR_BAD_DIMS;
+  if (B == 0) return ATACOM_ERR_BAD_DIMS;   // an empty launch could not take part in the barrier
+  if (gather_bulk_stores()) {
+    if (n == 6)
+      return launch_step<IiwaEnv<6>, 2>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset, peer_flags, local_sync, rank);
+    if (n == 7)
+      return launch_step<IiwaEnv<7>, 2>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset, peer_flags, local_sync, rank);
+  } else {
+    if (n == 6)
+      return launch_step<IiwaEnv<6>, 0>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset, peer_flags, local_sync, rank);
+    if (n == 7)
+      return launch_step<IiwaEnv<7>, 0>(q, dq, s_in, alpha, ddq, s_out, status, nullptr, B, p, stream, peer_ddq,
+                                        world, row_offset, peer_flags, local_sync, rank);
+  }
   return ATACOM_ERR_BAD_DIMS;
 }
 
@@ -1122,7 +1207,7 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   if (!c || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
-  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0, 0};
+  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0, 0, {}, nullptr, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define X(n_, F_, G_)                                                                             \
   if (n == n_ && F == F_ && G == G_)                                                              \
@@ -1206,9 +1291,9 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
             cudaMalloc(&c->s_in, g_bytes) == cudaSuccess && cudaMalloc(&c->s_out, g_bytes) == cudaSuccess &&
             cudaMalloc(&c->status, max_B) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
-  constexpr bool HOST_BULK = ATACOM_STEP_STAGED_IO != 0;
-  ok = ok && configure_step_kernel<IiwaEnv<6>, false>() && configure_step_kernel<IiwaEnv<7>, false>() &&
-       configure_step_kernel<IiwaEnv<6>, HOST_BULK>() && configure_step_kernel<IiwaEnv<7>, HOST_BULK>();   // not while capturing
+  constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+  ok = ok && configure_step_kernel<IiwaEnv<6>, 0>() && configure_step_kernel<IiwaEnv<7>, 0>() &&
+       configure_step_kernel<IiwaEnv<6>, HOST_IO>() && configure_step_kernel<IiwaEnv<7>, HOST_IO>();   // not while capturing
   step_block_size(1);
   ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1259,9 +1344,9 @@ int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* 
       const float *zs = static_cast<const float*>(d[2]), *za = static_cast<const float*>(d[3]);
       float *zddq = static_cast<float*>(d[4]), *zso = static_cast<float*>(d[5]);
       uint8_t* zst = static_cast<uint8_t*>(d[6]);
-      constexpr bool HOST_BULK = ATACOM_STEP_STAGED_IO != 0;
-      rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_BULK>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0])
-                  : launch_step<IiwaEnv<7>, HOST_BULK>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0]);
+      constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+      rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0])
+                  : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0]);
       if (rc != ATACOM_OK) return rc;
       if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
       return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;

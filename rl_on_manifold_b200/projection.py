@@ -89,7 +89,7 @@ def step(family, q, dq, s, alpha, params, *, n_ctrl_joints=6, ddq=None, s_out=No
 
 
 def iiwa_step_gather(q, dq, s, alpha, params, peer_ptrs, world, row_offset, *, n_ctrl_joints=6, ddq=None,
-                     s_out=None, status=None):
+                     s_out=None, status=None, flag_ptrs=None, local_sync=None, rank=0):
     """`step("iiwa", ...)` with the multi-GPU gather fused into the kernel epilogue: every environment's ddq row
     is stored into each rank's [world * B, n] gather buffer (`peer_ptrs`: ctypes array of `world` device pointers,
     peer-mapped; see sharding.SymmetricGather).  Returns s_out."""
@@ -107,9 +107,15 @@ def iiwa_step_gather(q, dq, s, alpha, params, peer_ptrs, world, row_offset, *, n
     if status is not None:
         _check(status, "status", B, None, torch.uint8)
     with torch.cuda.device(q.device):
-        rc = _lib.lib.atacom_iiwa_step_gather(n, _ptr(q), _ptr(dq), _ptr(s), _ptr(alpha), _ptr(ddq), _ptr(s_out),
-                                              _ptr(status), B, ctypes.byref(params), _stream(q), peer_ptrs, world,
-                                              row_offset)
+        if flag_ptrs is not None:       # cross-rank barrier inside the kernel as well
+            rc = _lib.lib.atacom_iiwa_step_gather_sync(n, _ptr(q), _ptr(dq), _ptr(s), _ptr(alpha), _ptr(ddq),
+                                                       _ptr(s_out), _ptr(status), B, ctypes.byref(params),
+                                                       _stream(q), peer_ptrs, world, row_offset, flag_ptrs,
+                                                       _ptr(local_sync), rank)
+        else:
+            rc = _lib.lib.atacom_iiwa_step_gather(n, _ptr(q), _ptr(dq), _ptr(s), _ptr(alpha), _ptr(ddq),
+                                                  _ptr(s_out), _ptr(status), B, ctypes.byref(params), _stream(q),
+                                                  peer_ptrs, world, row_offset)
     _lib.check(rc)
     return s_out
 

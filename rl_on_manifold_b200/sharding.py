@@ -65,7 +65,7 @@ class SymmetricGather:
     that a rank still reading step i cannot be overwritten by a peer already writing step i + 1.
     """
 
-    def __init__(self, local_B, n, group=None, buffers=2):
+    def __init__(self, local_B, n, group=None, buffers=2, in_kernel_barrier=False):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(group)
@@ -82,6 +82,19 @@ class SymmetricGather:
             self.bufs.append(t)
             self.handles.append(hdl)
             self.ptrs.append((ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs]))
+        # Optional in-kernel barrier: a flag array [world] per rank in symmetric memory and two local counters; the
+        # last block of every launch publishes / awaits the step, so no separate barrier launch is needed.
+        # Measured at N = 2 it is slower than the separate barrier kernel (29.5 vs 25.1 us per step: the system-
+        # scope fences sit on the critical path of every block), hence off by default.
+        self.in_kernel_barrier = in_kernel_barrier
+        if in_kernel_barrier:
+            self._flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+            self._flags.zero_()
+            self._flag_hdl = symm_mem.rendezvous(self._flags, name)
+            self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self._flag_hdl.buffer_ptrs])
+            self._local_sync = torch.zeros(2, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            self._flag_hdl.barrier()          # every rank's flags are zero before the first step
         self._i = 0
 
     def step(self, q, dq, s, alpha, params, *, n_ctrl_joints=6, s_out=None, status=None):
@@ -89,8 +102,14 @@ class SymmetricGather:
         from . import projection
         b = self._i % len(self.bufs)
         self._i += 1
-        s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
-                                            self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
-                                            status=status)
-        self.handles[b].barrier()
+        if self.in_kernel_barrier:
+            s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
+                                                self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
+                                                status=status, flag_ptrs=self._flag_ptrs,
+                                                local_sync=self._local_sync, rank=self.rank)
+        else:
+            s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
+                                                self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
+                                                status=status)
+            self.handles[b].barrier()
         return self.bufs[b], s_out

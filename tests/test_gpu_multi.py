@@ -34,13 +34,18 @@ def _worker(rank, world, port, B, out):
     sq, sdq, ss, sal = (shard.take(t) for t in (q, dq, s, alpha))
     ddq_l, s_l = projection.step("iiwa", sq, sdq, ss, sal, params)
     nccl = shard.gather(ddq_l)
-    fg = SymmetricGather(B, 6)
     ok = True
-    for it in range(3):                                                       # exercises both buffers
-        gathered, s_f = fg.step(sq, sdq, ss, sal, params)
+    for in_kernel in (True, False):            # cross-rank barrier inside the kernel / as a separate launch
+        fg = SymmetricGather(B, 6, in_kernel_barrier=in_kernel)
+        for it in range(5):                                                   # exercises both buffers
+            gathered, s_f = fg.step(sq, sdq, ss, sal, params)
+            # no host synchronisation between launch and check: kernel completion alone must imply that every
+            # rank's rows have arrived (the comparison kernels run on the same stream)
+            ok = ok and torch.equal(gathered, full_ddq) and torch.equal(gathered, nccl)
+            ok = ok and torch.equal(s_f, full_s[shard.lo:shard.hi])
+            if rank == it % world:
+                torch.cuda._sleep(2_000_000)                                  # skew the ranks
         torch.cuda.synchronize()
-        ok = ok and torch.equal(gathered, full_ddq) and torch.equal(gathered, nccl)
-        ok = ok and torch.equal(s_f, full_s[shard.lo:shard.hi])
     torch.save(dict(ok=bool(ok)), os.path.join(out, "r%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
