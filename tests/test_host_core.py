@@ -188,3 +188,49 @@ def test_point_reach_vs_oracle_and_golden(harness, golden):
         errs.append(max(helpers.rel_err(w[i:i + 1], o["w"][None, :2])[0],
                         helpers.rel_err(s_out[i:i + 1], o["s_new"][None])[0]))
     assert n_ok > 200 and max(errs) < 5e-5
+
+
+@pytest.mark.parametrize("family", ["circle", "planar", "iiwa6", "iiwa7"])
+@pytest.mark.parametrize("case", ["one_zero", "one_tiny", "two_zero", "two_small", "all_large"])
+def test_dual_projection_edge_cases(harness, family, case):
+    """The dual path (atacom_dual.cuh) of the step kernels at the corners of its domain: an exactly active
+    constraint (s_i = 0, what reset produces for a violated constraint, atacom.py:145-149), a nearly active one
+    (s_i = 1e-7), two of them at once (two slack pivots: the dual path defers, the general path answers),
+    and the interior.  Against the oracle with the canonical basis, float64 build of the same source."""
+    q, dq, s, alpha = helpers.synthetic_cpu(family, 160, seed=11)
+    n, F, G = helpers.DIMS[family]
+    rng = np.random.default_rng(3)
+    s = s.astype(np.float64)
+    for i in range(s.shape[0]):
+        if case == "all_large":
+            s[i] = np.maximum(s[i], 0.5)
+        else:
+            k_ = 2 if case.startswith("two") and G >= 2 else 1
+            idx = rng.choice(G, k_, replace=False)
+            s[i, idx] = {"one_zero": 0.0, "one_tiny": 1e-7, "two_zero": 0.0, "two_small": 0.01}[case]
+    q, dq, alpha = (a.astype(np.float64) for a in (q, dq, alpha))
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
+    pf = helpers.exact_params_flat(family, _params(family))
+    ddq, s_out, dbg, st = helpers.harness_step(harness, family, pf, q, dq, s, alpha, np.float64)
+    N = n + G
+    ok = ~ref["rank_def"] & (ref["margin"] > 1e-6)
+    assert ok.sum() > 0.5 * len(ok)
+    assert ((st & _lib.ST_NONFINITE) == 0)[ok].all()
+    for name, got, want in (("w_mn", dbg[:, :N], ref["w_mn"]), ("w_null", dbg[:, N:], ref["w_null"]),
+                            ("s", s_out, ref["s_new"])):
+        e = helpers.rel_err(got, want)
+        # float64 on both sides: what is left is eps64 * cond(Jc)^2 of the dual Gram matrix and of the oracle's
+        # own SVD route (cond(Jc) reaches 1e4 with an active constraint); the deferred environments run the
+        # general path, whose conditioning is that of the structured metric (cond(M) up to 1 + 400 G)
+        deferred = (st & _lib.ST_DENSE_PATH) != 0
+        assert (e[ok & ~deferred] < 1e-7).all(), (name, case, e[ok & ~deferred].max())
+        if (ok & ~deferred).any():
+            assert np.median(e[ok & ~deferred]) < 1e-11
+        if (ok & deferred).any():
+            assert (e[ok & deferred] < 1e-6).all(), (name, case, e[ok & deferred].max())
+    if case in ("one_zero", "one_tiny"):
+        # one slack pivot stays on the dual path (15 % of the synthetic batch already has another active slack)
+        assert ((st & _lib.ST_DENSE_PATH) == 0).mean() > 0.8
+        assert ((st & _lib.ST_SLACK_PIVOT) != 0).mean() > 0.5
+    if case == "all_large" and family != "iiwa7":
+        assert ((st & (_lib.ST_SLACK_PIVOT | _lib.ST_DENSE_PATH)) == 0).all()
