@@ -74,6 +74,10 @@ def main(B=65536, launches=10, family="iiwa", nj=6):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "time":
         print("lib:", _lib.LIB_PATH)
+        if len(sys.argv) > 2 and sys.argv[2] == "sweep":       # latency- or throughput-bound?  time vs batch size
+            for B in (4736, 9472, 18944, 37888, 65536, 131072, 262144):
+                time_kernel(B=B)
+            sys.exit(0)
         time_kernel()
         if len(sys.argv) > 2 and sys.argv[2] == "all":
             time_kernel(family="planar", B=16384)
