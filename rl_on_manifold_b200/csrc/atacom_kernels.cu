@@ -1,10 +1,11 @@
 // libatacom_b200.so — kernels and C ABI (include/atacom_b200.h).  sm_100a only.
 //
-// Mapping: one thread owns one environment; a block owns TPB consecutive environments, whose
-// rows of the AoS [B, dim] arrays form one contiguous slab per array.  Slabs move between HBM
-// and shared memory with coalesced 16-byte accesses; each thread then reads its row from shared
-// memory into registers, runs constraint evaluation (one FK pass) + projection, and writes its
-// results back through the same staging buffers.
+// Mapping: one thread owns one environment; a warp owns 32 consecutive environments, whose rows of
+// the AoS [B, dim] arrays form one contiguous piece per array.  The step kernels run constraint
+// evaluation (one FK pass) + the dual projection (atacom_dual.cuh) per thread, with the two big
+// operands of the projection in a per-warp region of shared memory; rows move either directly
+// (device-resident arrays) or through that region with the bulk-copy engine (mapped host arrays,
+// peer buffers of the fused gather).
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -212,10 +213,10 @@ __device__ __forceinline__ void bulk_commit_wait_all() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ AtacomEnvWrapper.step_action_function
-// One thread = one environment.  The block size is chosen at launch (<= STEP_MAX_TPB) so that the batch
-// spreads evenly over the SMs, ideally one block per SM: the body is a long fully unrolled instruction
-// stream and the block barriers between its phases keep all warps of the SM in the same code region,
-// so each instruction line is fetched once per SM rather than once per warp.
+// One thread = one environment; the block size is chosen at launch (<= STEP_MAX_TPB) so that the batch
+// spreads evenly over the SMs in as few waves as possible — 65 536 environments are one block of 448 per SM.
+// No block barrier anywhere on the main path: warps drift apart on purpose (while one waits for its loads
+// another is in the FP64-heavy part of the projection).  Timing model and measurements: DESIGN.md §6.
 template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: direct loads, bulk stores
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
