@@ -204,14 +204,17 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
  * the copies asynchronous).  The context owns the device staging buffers and streams; the batch is
  * cut into `chunks` pieces whose H2D copy, kernel and D2H copy overlap.
  *
- * Two data paths (atacom_host_ctx_set_mode):
- *   ATACOM_HOST_STAGED     device staging buffers, copy engines; the whole pipeline of a call is captured in a
- *                          CUDA graph and replayed while the caller passes the same buffers;
- *   ATACOM_HOST_ZERO_COPY  the kernel reads and writes the caller's buffers directly over PCIe (they must be
- *                          page-locked and mapped: cudaHostAlloc / cudaHostRegister / torch pin_memory());
- *   ATACOM_HOST_AUTO       (default) zero-copy when every buffer of the call is mapped, else staged. */
+ * Data paths (atacom_host_ctx_set_mode); the pipeline of a call is captured in a CUDA graph and replayed while
+ * the caller keeps passing the same buffers:
+ *   ATACOM_HOST_STAGED     device staging buffers, copy engines in both directions;
+ *   ATACOM_HOST_HYBRID     inputs through the copy engines, outputs stored by the kernels straight into the
+ *                          caller's buffers over PCIe (the OUTPUT buffers must be page-locked and mapped:
+ *                          cudaHostAlloc / cudaHostRegister / torch pin_memory());
+ *   ATACOM_HOST_ZERO_COPY  one kernel reads and writes the caller's buffers directly (all of them mapped);
+ *   ATACOM_HOST_AUTO       (default) zero-copy when every buffer of the call is mapped, else staged.
+ * Measured on PCIe gen5 x16, 65 536 iiwa environments per call: zero-copy 230 us, staged 262 us, hybrid 265 us. */
 typedef struct AtacomHostCtx AtacomHostCtx;
-enum { ATACOM_HOST_AUTO = 0, ATACOM_HOST_STAGED = 1, ATACOM_HOST_ZERO_COPY = 2 };
+enum { ATACOM_HOST_AUTO = 0, ATACOM_HOST_STAGED = 1, ATACOM_HOST_ZERO_COPY = 2, ATACOM_HOST_HYBRID = 3 };
 int atacom_host_ctx_create(AtacomHostCtx** ctx, int64_t max_B, int chunks);
 int atacom_host_ctx_set_mode(AtacomHostCtx* ctx, int mode);
 int atacom_host_ctx_destroy(AtacomHostCtx* ctx);

@@ -19,7 +19,8 @@ print("D2H 64MB: %.1f GB/s (%.0f us)" % bw(lambda: big_h.copy_(big_d, non_blocki
 sm_h = big_h[:1 << 20]; sm_d = big_d[:1 << 20]
 print("H2D 1MB: %.1f GB/s (%.0f us)" % bw(lambda: sm_d.copy_(sm_h, non_blocking=True), 1 << 20, 100))
 print("D2H 1MB: %.1f GB/s (%.0f us)" % bw(lambda: sm_h.copy_(sm_d, non_blocking=True), 1 << 20, 100))
-for mode, chunks in (("staged", 1), ("staged", 2), ("staged", 4), ("zero_copy", 1)):
+for mode, chunks in (("staged", 2), ("zero_copy", 1), ("hybrid", 1), ("hybrid", 2), ("hybrid", 3), ("hybrid", 4),
+                     ("hybrid", 8)):
     ctx = projection.HostContext(B, chunks=chunks, mode=mode)
     f = lambda: ctx.iiwa_step(6, *host, ddq_h, s_h, p)
     for _ in range(5): f()

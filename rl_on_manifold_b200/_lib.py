@@ -16,7 +16,7 @@ OK = 0
 ST_RANK_DEFICIENT, ST_COLUMN_DROPPED, ST_SLACK_PIVOT, ST_NONFINITE, ST_DENSE_PATH = 1, 2, 4, 8, 16
 VARIANT_ATACOM, VARIANT_ERROR_CORRECTION = 0, 1
 BIAS_JDOT_QDOT, BIAS_OMEGA_X_V = 0, 1
-HOST_AUTO, HOST_STAGED, HOST_ZERO_COPY = 0, 1, 2
+HOST_AUTO, HOST_STAGED, HOST_ZERO_COPY, HOST_HYBRID = 0, 1, 2, 3
 
 
 class AtacomParams(ctypes.Structure):

@@ -1250,9 +1250,12 @@ static void* mapped_alias(const void* h) {
   return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
+// out_ddq / out_s / out_status non-null: device aliases of the caller's (mapped) output buffers — the kernels
+// store their results there directly (bulk stores over PCIe) and the D2H copies disappear.
 static int host_pipeline(AtacomHostCtx* c, int n, const float* q, const float* dq, const float* s_in,
                          const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
-                         const AtacomParams* p, int n_streams) {
+                         const AtacomParams* p, int n_streams, float* out_ddq = nullptr, float* out_s = nullptr,
+                         uint8_t* out_status = nullptr) {
   const int G = 5 + n;
   const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? n : n - 1;
   // chunk boundaries are multiples of TPB so every chunk's rows stay 16-byte aligned
@@ -1267,6 +1270,14 @@ static int host_pipeline(AtacomHostCtx* c, int n, const float* q, const float* d
     cudaMemcpyAsync(c->dq + e0 * n, dq + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(c->s_in + e0 * G, s_in + e0 * G, sizeof(float) * G * nb, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(c->alpha + e0 * na, alpha + e0 * na, sizeof(float) * na * nb, cudaMemcpyHostToDevice, st);
+    if (out_ddq) {
+      uint8_t* zst = status ? out_status + e0 : nullptr;
+      rc = n == 6 ? launch_step<IiwaEnv<6>, 2>(c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
+                                               out_ddq + e0 * n, out_s + e0 * G, zst, nullptr, nb, p, st)
+                  : launch_step<IiwaEnv<7>, 2>(c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
+                                               out_ddq + e0 * n, out_s + e0 * G, zst, nullptr, nb, p, st);
+      continue;
+    }
     rc = atacom_iiwa_step(n, c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
                           c->ddq + e0 * n, c->s_out + e0 * G, status ? c->status + e0 : nullptr, nullptr, nb, p,
                           st);
@@ -1294,7 +1305,8 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
   ok = ok && configure_step_kernel<IiwaEnv<6>, 0>() && configure_step_kernel<IiwaEnv<7>, 0>() &&
-       configure_step_kernel<IiwaEnv<6>, HOST_IO>() && configure_step_kernel<IiwaEnv<7>, HOST_IO>();   // not while capturing
+       configure_step_kernel<IiwaEnv<6>, HOST_IO>() && configure_step_kernel<IiwaEnv<7>, HOST_IO>() &&
+       configure_step_kernel<IiwaEnv<6>, 2>() && configure_step_kernel<IiwaEnv<7>, 2>();   // not while capturing
   step_block_size(1);
   ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1309,7 +1321,13 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
 
 int atacom_host_ctx_set_mode(AtacomHostCtx* c, int mode) {
   if (!c) return ATACOM_ERR_NULL_POINTER;
-  if (mode != ATACOM_HOST_AUTO && mode != ATACOM_HOST_STAGED && mode != ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
+  if (mode != ATACOM_HOST_AUTO && mode != ATACOM_HOST_STAGED && mode != ATACOM_HOST_ZERO_COPY &&
+      mode != ATACOM_HOST_HYBRID)
+    return ATACOM_ERR_BAD_PARAM;
+  if (mode != c->mode && c->exec) {   // the cached pipeline was captured for the old data path
+    cudaGraphExecDestroy(c->exec);
+    c->exec = nullptr;
+  }
   c->mode = mode;
   return ATACOM_OK;
 }
@@ -1335,24 +1353,35 @@ int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* 
   int rc = check_common(B, p);
   if (rc) return rc;
   if (B == 0) return ATACOM_OK;
-  if (c->mode != ATACOM_HOST_STAGED) {
+  float* out_ddq = nullptr;
+  float* out_s = nullptr;
+  uint8_t* out_status = nullptr;
+  if (c->mode == ATACOM_HOST_HYBRID) {
+    // hybrid: inputs through the copy engines (large PCIe reads), outputs stored by the kernels straight into
+    // the caller's mapped buffers — no D2H stage at the end of the pipeline
+    out_ddq = static_cast<float*>(mapped_alias(ddq));
+    out_s = static_cast<float*>(mapped_alias(s_out));
+    out_status = status ? static_cast<uint8_t*>(mapped_alias(status)) : nullptr;
+    if (!out_ddq || !out_s || (status && !out_status)) return ATACOM_ERR_BAD_PARAM;
+  }
+  if (c->mode == ATACOM_HOST_ZERO_COPY || c->mode == ATACOM_HOST_AUTO) {
     // zero-copy: one launch on the device aliases of the caller's buffers; loads and stores cross PCIe
     void* d[7] = {mapped_alias(q), mapped_alias(dq), mapped_alias(s_in), mapped_alias(alpha), mapped_alias(ddq),
                   mapped_alias(s_out), status ? mapped_alias(status) : nullptr};
     const bool all = d[0] && d[1] && d[2] && d[3] && d[4] && d[5] && (!status || d[6]);
+    if (!all && c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
     if (all) {
-      const float *zq = static_cast<const float*>(d[0]), *zdq = static_cast<const float*>(d[1]);
-      const float *zs = static_cast<const float*>(d[2]), *za = static_cast<const float*>(d[3]);
-      float *zddq = static_cast<float*>(d[4]), *zso = static_cast<float*>(d[5]);
-      uint8_t* zst = static_cast<uint8_t*>(d[6]);
-      constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
-      rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0])
-                  : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0]);
-      if (rc != ATACOM_OK) return rc;
-      if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
-      return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+    const float *zq = static_cast<const float*>(d[0]), *zdq = static_cast<const float*>(d[1]);
+    const float *zs = static_cast<const float*>(d[2]), *za = static_cast<const float*>(d[3]);
+    float *zddq = static_cast<float*>(d[4]), *zso = static_cast<float*>(d[5]);
+    uint8_t* zst = static_cast<uint8_t*>(d[6]);
+    constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+    rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0])
+                : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0]);
+    if (rc != ATACOM_OK) return rc;
+    if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
     }
-    if (c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
   }
   const void* key[7] = {q, dq, s_in, alpha, ddq, s_out, status};
   bool hit = c->exec != nullptr && c->key_B == B && c->key_n == n &&
@@ -1371,7 +1400,7 @@ int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* 
       cudaEventRecord(c->fork, c->streams[0]);
       for (int i = 1; i < ns; ++i) cudaStreamWaitEvent(c->streams[i], c->fork, 0);
       const int64_t before = g_launches.load(std::memory_order_relaxed);
-      rc = host_pipeline(c, n, q, dq, s_in, alpha, ddq, s_out, status, B, p, ns);
+      rc = host_pipeline(c, n, q, dq, s_in, alpha, ddq, s_out, status, B, p, ns, out_ddq, out_s, out_status);
       c->key_launches = static_cast<int>(g_launches.exchange(before, std::memory_order_relaxed) - before);   // captured, not run
       for (int i = 1; i < ns; ++i) {
         cudaEventRecord(c->join[i], c->streams[i]);

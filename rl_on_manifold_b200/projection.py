@@ -313,11 +313,14 @@ class HostContext:
     """Host-buffer entry point (`atacom_iiwa_step_host`): NumPy / pinned-tensor in, NumPy out,
     copies inside the call — what a caller of the NumPy reference binds."""
 
-    MODES = {"auto": _lib.HOST_AUTO, "staged": _lib.HOST_STAGED, "zero_copy": _lib.HOST_ZERO_COPY}
+    MODES = {"auto": _lib.HOST_AUTO, "staged": _lib.HOST_STAGED, "zero_copy": _lib.HOST_ZERO_COPY,
+             "hybrid": _lib.HOST_HYBRID}
 
     def __init__(self, max_B, chunks=2, mode="auto"):
-        """mode: 'staged' (device staging buffers + copy engines, replayed as a CUDA graph), 'zero_copy' (the
-        kernel works on the caller's page-locked buffers over PCIe) or 'auto' (zero-copy when possible)."""
+        """mode: 'staged' (device staging buffers + copy engines), 'hybrid' (inputs through the copy engines,
+        outputs stored by the kernels straight into the caller's page-locked buffers), 'zero_copy' (one kernel
+        works on the caller's page-locked buffers over PCIe) or 'auto' (zero-copy when possible, else staged).
+        The pipeline of a call is replayed as a CUDA graph while the same buffers are passed."""
         self._ctx = ctypes.c_void_p()
         _lib.check(_lib.lib.atacom_host_ctx_create(ctypes.byref(self._ctx), max_B, chunks))
         _lib.check(_lib.lib.atacom_host_ctx_set_mode(self._ctx, self.MODES[mode]))

@@ -245,7 +245,7 @@ def test_empty_and_tiny_batches(cuda_device):
         assert torch.isfinite(ddq).all()
 
 
-@pytest.mark.parametrize("mode", ["staged", "zero_copy", "auto"])
+@pytest.mark.parametrize("mode", ["staged", "zero_copy", "hybrid", "auto"])
 def test_host_buffer_entry_point(cuda_device, mode):
     """atacom_iiwa_step_host: host arrays in, host arrays out, bit-identical to the device-resident call on
     both data paths (copy engines + CUDA graph replay; kernel working on the mapped host buffers)."""
@@ -265,7 +265,7 @@ def test_host_buffer_entry_point(cuda_device, mode):
     # a different batch size / buffer invalidates the cached pipeline
     ctx.iiwa_step(6, *[t[:1234] for t in h], ddq_h[:1234], s_h[:1234], p)
     assert torch.equal(ddq_h[:1234], ddq.cpu()[:1234])
-    if mode != "zero_copy":                  # pageable host memory goes through the staged path
+    if mode in ("staged", "auto"):           # pageable host memory goes through the staged path
         hp = [t.cpu().numpy().copy() for t in (q, dq, s, alpha)]
         out_ddq, out_s = np.zeros((B, 6), np.float32), np.zeros((B, 11), np.float32)
         ctx.iiwa_step(6, *hp, out_ddq, out_s, p)
