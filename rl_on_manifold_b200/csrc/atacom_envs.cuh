@@ -503,9 +503,14 @@ struct DualSink {
   const DualConsts<HP>& Kd;
   YS& Y;
   HP r[at_least_1<C>::value], dg[at_least_1<NDIAG>::value];
-  ATACOM_HD DualSink(const DualConsts<HP>& Kd_, YS& Y_, const HP* sh) : Kd(Kd_), Y(Y_) {
+  ATACOM_HD DualSink(const DualConsts<HP>& Kd_, YS& Y_) : Kd(Kd_), Y(Y_) {
     ATACOM_UNROLL
-    for (int i = 0; i < C; ++i) r[i] = (i >= F) ? HP(0.5) * Kd.K_c[i] * sh[i >= F ? i - F : 0] * sh[i >= F ? i - F : 0] : HP(0);
+    for (int i = 0; i < C; ++i) r[i] = HP(0);
+  }
+  // the slack term of c (atacom.py:195), added once the slacks are at hand
+  ATACOM_HD void add_slack_terms(const HP* sh) {
+    ATACOM_UNROLL
+    for (int i = F; i < C; ++i) r[i] += HP(0.5) * Kd.K_c[i] * sh[i - F] * sh[i - F];
   }
   ATACOM_HD void put_c(int i, HP v) { r[i] += Kd.K_c[i] * v; }
   ATACOM_HD void put_Jdq(int i, HP v) { r[i] += Kd.wJ[i] * v; }
@@ -520,18 +525,24 @@ struct DualSink {
 // the fp32 outputs is carried in HP.  An environment the dual path defers (two or more slack pivots)
 // comes back flagged ST_DENSE_PATH with no outputs written: the caller reruns it on the general fp32
 // path.
-template <class Env, typename T, typename HP, class YS, class LS>
-ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q, const T* dq,
-                            const T* s, const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+// `fetch(s, alpha)` is called AFTER the constraint functor has run and must fill the slack row (G values) and
+// the action row (n values, zero-padded): the kinematics need neither, so a kernel can have them copied in
+// the background (bulk copy into shared memory) while the kinematics run on q and dq.
+template <class Env, typename T, typename HP, class YS, class LS, class Fetch>
+ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q,
+                                 const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg) {
   using D = typename Env::D;
   constexpr int NDIAG = Env::NDIAG;
   constexpr int n = D::n, G = D::G, N = D::N, k = D::k;
+  const bool ec = P.variant == VARIANT_EC;
+  DualSink<T, HP, D, NDIAG, YS> sink(Kd, Y);
+  Env::template eval<T, HP>(P, q, dq, sink);
+  T s[at_least_1<G>::value], alpha[n];
+  fetch(s, alpha);
   HP sh[at_least_1<G>::value], ah[at_least_1<k>::value];
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
-  const bool ec = P.variant == VARIANT_EC;
-  DualSink<T, HP, D, NDIAG, YS> sink(Kd, Y, sh);
-  Env::template eval<T, HP>(P, q, dq, sink);
+  sink.add_slack_terms(sh);
   ATACOM_UNROLL
   for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
   T w_mn[N];
@@ -576,6 +587,19 @@ ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   }
   if (!finite) st |= ST_NONFINITE;
   return st;
+}
+
+template <class Env, typename T, typename HP, class YS, class LS>
+ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q, const T* dq,
+                            const T* s, const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+  using D = typename Env::D;
+  auto fetch = [&](T* s_row, T* a_row) {
+    ATACOM_UNROLL
+    for (int i = 0; i < D::G; ++i) s_row[i] = s[i];
+    ATACOM_UNROLL
+    for (int j = 0; j < D::n; ++j) a_row[j] = alpha[j];
+  };
+  return step_dual_lazy<Env, T, HP>(P, Kd, Y, Ls, q, dq, fetch, ddq, s_out, w_dbg);
 }
 
 // The general fp32 path (structured -> dense) from scratch, kept out of line: the rarely taken

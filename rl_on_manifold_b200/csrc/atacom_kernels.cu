@@ -41,6 +41,9 @@ namespace {
 // host memory: large PCIe requests, +30 % end to end); 2 (default): two instantiations, chosen per launch.
 #define ATACOM_STEP_STAGED_IO 2
 #endif
+#ifndef ATACOM_STEP_DEVICE_IO    // I/O mode of the device entry points: 0 (direct rows) or 3 (s, alpha in the background)
+#define ATACOM_STEP_DEVICE_IO 0
+#endif
 #ifndef ATACOM_X_BULK_LOAD      // experiments: which half of the I/O the bulk instantiation moves with cp.async.bulk
 #define ATACOM_X_BULK_LOAD 1
 #endif
@@ -217,7 +220,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // spreads evenly over the SMs in as few waves as possible — 65 536 environments are one block of 448 per SM.
 // No block barrier anywhere on the main path: warps drift apart on purpose (while one waits for its loads
 // another is in the FP64-heavy part of the projection).  Timing model and measurements: DESIGN.md §6.
-template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: direct loads, bulk stores
+template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: direct loads, bulk stores,
+                              // 3: q, dq direct; s, alpha bulk-copied in the background of the kinematics
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
                                                                     const __grid_constant__ DualConsts<double> Kd) {
@@ -243,6 +247,8 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   const int na = ec ? n : k;
   uint64_t* bar = reinterpret_cast<uint64_t*>(atacom_smem + SC::MAX_WARPS * SC::WARP_BYTES) + warp;
   const bool bulk = IO == 1 && a.aligned16 && (wenv0 + 32 <= a.B);
+  bool lazy = false;
+  float* lz = reinterpret_cast<float*>(region + (SC::SHARED ? sizeof(double) * SC::DU::Y_SIZE * 32 : 0));
   float* sq = reinterpret_cast<float*>(region);
   float* sdq = sq + 32 * n;
   float* ss = sdq + 32 * n;
@@ -268,16 +274,32 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     for (int i = 0; i < G; ++i) s[i] = ss[lane * G1 + i];
     __syncwarp();     // the region is scratch from here on
   } else {
+    // s and alpha are not needed before the projection: in mode 3 the bulk-copy engine brings the warp's two
+    // slabs into the (still idle) L part of its region while the kinematics run on q and dq
+    if (IO == 3 && G > 0) {
+      lazy = a.aligned16 && (wenv0 + 32 <= a.B);
+      if (lazy) {
+        if (lane == 0) {
+          mbar_init(bar, 1);
+          mbar_expect_tx(bar, 128u * static_cast<uint32_t>(G + na));
+          bulk_g2s(lz, a.s_in + wenv0 * G, 128u * G, bar);
+          if (na > 0) bulk_g2s(lz + 32 * G, a.alpha + wenv0 * na, 128u * static_cast<uint32_t>(na), bar);
+        }
+        __syncwarp();
+      }
+    }
     row_load<n>(a.q, e, q);
     row_load<n>(a.dq, e, dq);
-    if (G > 0) row_load<G1>(a.s_in, e, s);
-    if (ec) {
-      row_load<n>(a.alpha, e, al);
-    } else {
-      float ak[K1];
-      if (k > 0) row_load<K1>(a.alpha, e, ak);
+    if (!lazy) {
+      if (G > 0) row_load<G1>(a.s_in, e, s);
+      if (ec) {
+        row_load<n>(a.alpha, e, al);
+      } else {
+        float ak[K1];
+        if (k > 0) row_load<K1>(a.alpha, e, ak);
 #pragma unroll
-      for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
+        for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
+      }
     }
   }
 
@@ -286,7 +308,21 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   using DU = Dual<double, D, Env::NDIAG>;
   typename SC::YS Ys = SC::y(region, lane);
   typename SC::LS Ls = SC::l(region, lane);
-  uint8_t st = step_dual<Env, float, double>(P, Kd, Ys, Ls, q, dq, s, al, ddq, so, dbg);
+  auto fetch = [&](float* s_row, float* a_row) {
+    if (IO == 3 && lazy) {
+      mbar_wait(bar, 0);
+#pragma unroll
+      for (int i = 0; i < G; ++i) s[i] = lz[lane * G1 + i];
+#pragma unroll
+      for (int j = 0; j < n; ++j) al[j] = j < na ? lz[32 * G + lane * na + j] : 0.f;
+      __syncwarp();     // every lane has its rows: the L part of the region may be overwritten
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) s_row[i] = s[i];
+#pragma unroll
+    for (int j = 0; j < n; ++j) a_row[j] = al[j];
+  };
+  uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg);
   if (st & ST_DENSE_PATH) st = ST_DENSE_PATH | step_general_outlined<Env, float, double>(P, q, dq, s, al, ddq, so, dbg);
 #else
   RawConstraints<float, double, D> R;
@@ -302,7 +338,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   const int64_t e2 = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid2;
   const int64_t wenv2 = e2 - lane2;
   if (e2 < a.B && a.status) a.status[e2] = st;
-  if (IO != 0 && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
+  if ((IO == 1 || IO == 2) && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
     float* oq = reinterpret_cast<float*>(atacom_smem + (tid2 >> 5) * SC::WARP_BYTES);
     float* os = oq + 32 * n;
     __syncwarp();     // every lane is done with its scratch
@@ -803,7 +839,7 @@ bool configure_step_kernel() {
   return state == 1;
 }
 
-template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : 0)>
+template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : ATACOM_STEP_DEVICE_IO)>
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
                 float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0,
@@ -1304,7 +1340,8 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
             cudaMalloc(&c->status, max_B) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
-  ok = ok && configure_step_kernel<IiwaEnv<6>, 0>() && configure_step_kernel<IiwaEnv<7>, 0>() &&
+  ok = ok && configure_step_kernel<IiwaEnv<6>, ATACOM_STEP_DEVICE_IO>() &&
+       configure_step_kernel<IiwaEnv<7>, ATACOM_STEP_DEVICE_IO>() &&
        configure_step_kernel<IiwaEnv<6>, HOST_IO>() && configure_step_kernel<IiwaEnv<7>, HOST_IO>() &&
        configure_step_kernel<IiwaEnv<6>, 2>() && configure_step_kernel<IiwaEnv<7>, 2>();   // not while capturing
   step_block_size(1);
