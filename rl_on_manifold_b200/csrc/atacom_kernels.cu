@@ -412,11 +412,13 @@ __global__ void __launch_bounds__(TPB) atacom_slack_init_kernel(const float* __r
 template <int n_, int F_, int G_>
 struct GenericDims { using D = Dims<n_, F_, G_>; };
 
+// The user's callbacks were evaluated batched in fp32; everything from there on runs in double (the
+// structured -> dense path instantiated for double), so the kernel adds nothing to the rounding of its inputs.
 template <int n_, int F_, int G_>
 __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __restrict__ c,
                                                              const float* __restrict__ J,
                                                              const float* __restrict__ b, StepArgs a,
-                                                             ParamsT<float> P) {
+                                                             const __grid_constant__ ParamsT<double> P) {
   using D = Dims<n_, F_, G_>;
   constexpr int n = D::n, G = D::G, k = D::k, C = D::C, N = D::N;
   constexpr int G1 = at_least_1<G>::value;
@@ -424,13 +426,13 @@ __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __rest
   if (e >= a.B) return;
   const bool ec = P.variant == VARIANT_EC;
   const int na = ec ? n : k;
-  float dq[n], s[G1], al[n], ddq[n], so[G1];
+  double dq[n], s[G1], al[n], ddq[n], so[G1];
 #pragma unroll
   for (int j = 0; j < n; ++j) {
     dq[j] = a.dq[e * n + j];
-    al[j] = j < na ? a.alpha[e * na + j] : 0.f;
+    al[j] = j < na ? static_cast<double>(a.alpha[e * na + j]) : 0.0;
   }
-  RawConstraints<float, double, D> R;
+  RawConstraints<double, double, D> R;
 #pragma unroll
   for (int i = 0; i < C; ++i) {
     R.c[i] = c[e * C + i];
@@ -439,19 +441,23 @@ __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __rest
 #pragma unroll
     for (int j = 0; j < n; ++j) {
       R.J[i][j] = J[(e * C + i) * n + j];
-      jdq += static_cast<double>(R.J[i][j]) * static_cast<double>(dq[j]);
+      jdq += R.J[i][j] * dq[j];
     }
     R.Jdq[i] = jdq;
   }
 #pragma unroll
   for (int i = 0; i < G; ++i) s[i] = a.s_in[e * G + i];
-  float* dbg = a.w_dbg ? a.w_dbg + e * (2 * N) : nullptr;
-  const uint8_t st = step_from_raw<float, double, D, 0>(P, R, dq, s, al, ddq, so, dbg);
+  double dbg[2 * N];
+  const uint8_t st = step_from_raw<double, double, D, 0>(P, R, dq, s, al, ddq, so, a.w_dbg ? dbg : nullptr);
   if (a.status) a.status[e] = st;
 #pragma unroll
-  for (int j = 0; j < n; ++j) a.ddq[e * n + j] = ddq[j];
+  for (int j = 0; j < n; ++j) a.ddq[e * n + j] = static_cast<float>(ddq[j]);
 #pragma unroll
-  for (int i = 0; i < G; ++i) a.s_out[e * G + i] = so[i];
+  for (int i = 0; i < G; ++i) a.s_out[e * G + i] = static_cast<float>(so[i]);
+  if (a.w_dbg) {
+#pragma unroll
+    for (int i = 0; i < 2 * N; ++i) a.w_dbg[e * (2 * N) + i] = static_cast<float>(dbg[i]);
+  }
 }
 
 // ------------------------------------------------------------------ PointReachAtacom.step
@@ -469,8 +475,9 @@ struct PointArgs {
   int64_t B;
 };
 
+// fp32 in HBM, double inside (the structured -> dense path instantiated for double)
 template <int G_>
-__global__ void __launch_bounds__(TPB) point_reach_step_kernel(PointArgs a, ParamsT<float> P) {
+__global__ void __launch_bounds__(TPB) point_reach_step_kernel(PointArgs a, const __grid_constant__ ParamsT<double> P) {
   using Env = PointReachEnv<G_>;
   constexpr int G = G_, N = 2 + G_;
   __shared__ __align__(16) float sq[round4_t<TPB * 2>::value];
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(TPB) point_reach_step_kernel(PointArgs a, Para
   __syncthreads();
   const int t = threadIdx.x;
   if (t < nvalid) {
-    float q[2], dq[2], p[2 * G], dp[2 * G], s[G], act[2], w[2], so[G];
+    double q[2], dq[2], p[2 * G], dp[2 * G], s[G], act[2], w[2], so[G];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       q[j] = sq[t * 2 + j];
@@ -505,13 +512,17 @@ __global__ void __launch_bounds__(TPB) point_reach_step_kernel(PointArgs a, Para
     }
 #pragma unroll
     for (int i = 0; i < G; ++i) s[i] = ss[t * G + i];
-    float* dbg = a.w_dbg ? a.w_dbg + (env0 + t) * (2 * N) : nullptr;
-    const uint8_t st = Env::template step<float, double>(P, q, dq, p, dp, s, act, w, so, dbg);
+    double dbg[2 * N];
+    const uint8_t st = Env::template step<double, double>(P, q, dq, p, dp, s, act, w, so, a.w_dbg ? dbg : nullptr);
     if (a.status) a.status[env0 + t] = st;
-    sq[t * 2] = w[0];
-    sq[t * 2 + 1] = w[1];
+    if (a.w_dbg) {
 #pragma unroll
-    for (int i = 0; i < G; ++i) ss[t * G + i] = so[i];
+      for (int i = 0; i < 2 * N; ++i) a.w_dbg[(env0 + t) * (2 * N) + i] = static_cast<float>(dbg[i]);
+    }
+    sq[t * 2] = static_cast<float>(w[0]);
+    sq[t * 2 + 1] = static_cast<float>(w[1]);
+#pragma unroll
+    for (int i = 0; i < G; ++i) ss[t * G + i] = static_cast<float>(so[i]);
   }
   __syncthreads();
   slab_store<2>(a.w, sq, env0, nvalid);
@@ -1127,7 +1138,8 @@ int atacom_point_reach_step(int n_objects, const float* q, const float* dq, cons
   if (!q || !dq || !obs_p || !obs_dp || !s_in || !action || !w || !s_out) return ATACOM_ERR_NULL_POINTER;
   PointArgs a{q, dq, obs_p, obs_dp, s_in, action, w, s_out, status, w_dbg, B};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define ATACOM_PR_STEP(G_) point_reach_step_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(a, as_params(p))
+  const ParamsT<double> Pd = widen_params<double>(as_params(p));
+#define ATACOM_PR_STEP(G_) point_reach_step_kernel<G_><<<blocks_for(B), TPB, 0, st>>>(a, Pd)
   switch (n_objects) {
     ATACOM_POINT_DISPATCH(1, ATACOM_PR_STEP)
     ATACOM_POINT_DISPATCH(2, ATACOM_PR_STEP)
@@ -1245,10 +1257,11 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
   StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0, 0, {}, nullptr, 0};
+  const ParamsT<double> Pd = widen_params<double>(as_params(p));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define X(n_, F_, G_)                                                                             \
   if (n == n_ && F == F_ && G == G_)                                                              \
-    atacom_generic_kernel<n_, F_, G_><<<blocks_for(B), TPB, 0, st>>>(c, J, b, a, as_params(p));
+    atacom_generic_kernel<n_, F_, G_><<<blocks_for(B), TPB, 0, st>>>(c, J, b, a, Pd);
   ATACOM_GENERIC_SHAPES(X)
 #undef X
   g_launches.fetch_add(1, std::memory_order_relaxed);

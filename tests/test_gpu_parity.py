@@ -158,8 +158,9 @@ def test_generic_constraint_set_golden(cuda_device, golden, tag):
     torch.cuda.synchronize()
     N = n + G
     ref_mn = golden[tag + "_act_a"] + golden[tag + "_act_err"]
-    # inputs and gains were rounded to fp32 on the way in: 5e-5 covers K_c * eps32 on the O(1) residual
-    assert helpers.rel_err(w_dbg[:, :N].cpu().numpy(), ref_mn).max() < 5e-5
+    # inputs and gains were rounded to fp32 on the way in (K_c * eps32 on the O(1) residual); the kernel itself
+    # runs in double.  Measured: <= 7e-7 on every shape
+    assert helpers.rel_err(w_dbg[:, :N].cpu().numpy(), ref_mn).max() < 5e-6
     fired = []
     for i in range(B):
         g = {k: golden["%s_%s" % (tag, k)][i] for k in ("c", "J", "b", "dq", "s", "alpha")}
@@ -168,8 +169,8 @@ def test_generic_constraint_set_golden(cuda_device, golden, tag):
         tr = [ao.atacom_step(spec, ev, g["dq"], g["s"], g["alpha"], basis=bs)["trace"] for bs in ("svd", "canonical")]
         fired.append(any(pv > 1e-9 for t_ in tr for (_, _, pv) in t_["dropped"]))
     keep = ~np.array(fired)
-    assert helpers.rel_err(w_dbg[:, N:].cpu().numpy()[keep], golden[tag + "_act_b"][keep]).max() < 5e-5
-    assert helpers.rel_err(ddq.cpu().numpy()[keep], golden[tag + "_ddq"][keep]).max() < 5e-5
+    assert helpers.rel_err(w_dbg[:, N:].cpu().numpy()[keep], golden[tag + "_act_b"][keep]).max() < 5e-6
+    assert helpers.rel_err(ddq.cpu().numpy()[keep], golden[tag + "_ddq"][keep]).max() < 5e-6
 
 
 def test_point_reach_golden_and_oracle(cuda_device, golden):
