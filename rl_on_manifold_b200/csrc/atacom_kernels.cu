@@ -224,7 +224,8 @@ template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: d
                               // 3: q, dq direct; s, alpha bulk-copied in the background of the kinematics
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
-                                                                    const __grid_constant__ DualConsts<double> Kd) {
+                                                                    const __grid_constant__ DualConsts<double> Kd,
+                                                                    const __grid_constant__ ParamsT<double> Pd) {
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
@@ -323,7 +324,27 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     for (int j = 0; j < n; ++j) a_row[j] = al[j];
   };
   uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg);
-  if (st & ST_DENSE_PATH) st = ST_DENSE_PATH | step_general_outlined<Env, float, double>(P, q, dq, s, al, ddq, so, dbg);
+  if (st & ST_DENSE_PATH) {
+    // two or more slack pivots: the general (structured -> dense) path, in double like everything else
+    double qd[n], dqd[n], sd[G1], ald[n], ddqd[n], sod[G1], dbgd[2 * N];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      qd[j] = q[j];
+      dqd[j] = dq[j];
+      ald[j] = al[j];
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) sd[i] = s[i];
+    st = ST_DENSE_PATH | step_general_outlined<Env, double, double>(Pd, qd, dqd, sd, ald, ddqd, sod, dbg ? dbgd : nullptr);
+#pragma unroll
+    for (int j = 0; j < n; ++j) ddq[j] = static_cast<float>(ddqd[j]);
+#pragma unroll
+    for (int i = 0; i < G; ++i) so[i] = static_cast<float>(sod[i]);
+    if (dbg) {
+#pragma unroll
+      for (int i = 0; i < 2 * N; ++i) dbg[i] = static_cast<float>(dbgd[i]);
+    }
+  }
 #else
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
@@ -885,7 +906,7 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   constexpr size_t smem = StepScratch<Env>::BYTES;
   if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
   atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
-      a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
+      a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G), widen_params<double>(as_params(p)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
 }
