@@ -44,12 +44,13 @@ def test_step_vs_oracle(cuda_device, family, B):
     N = ref["w"].shape[1]
     ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
     assert ok.mean() > 0.9
-    tol = tol32(ref["cond"])
+    # north-star tolerance 1e-5, no widening by cond(Jc): the kernels compute in double, what is left is the
+    # rounding of the fp32 outputs (measured <= 2e-7 on every family)
+    tol = 2e-6
     errs = dict(w_mn=helpers.rel_err(dbg[:, :N], ref["w_mn"]), w_null=helpers.rel_err(dbg[:, N:], ref["w_null"]),
                 ddq=helpers.rel_err(ddq, ref["ddq"], ref["w"]), s=helpers.rel_err(s_out, ref["s_new"]))
     for name, e in errs.items():
         assert (e < tol)[ok].all(), "%s: max %g" % (name, e[ok].max())
-        assert (e[ok] < TOL32).mean() > 0.95, name
     assert ((st & _lib.ST_NONFINITE) == 0).all()
     dropped = (st & _lib.ST_COLUMN_DROPPED) != 0
     assert (dropped[ok] >= ref["fired"][ok]).all()
@@ -66,8 +67,8 @@ def test_stratum_one_equals_reference_svd_basis(cuda_device, family):
     ddq, s_out, _, _ = _run(family, q, dq, s, alpha, _params(family), cuda_device, dbg=False)
     stratum1 = ~ref["fired"] & ~can["fired"] & ~ref["rank_def"]
     assert stratum1.mean() > 0.5
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[stratum1].all()
-    assert (helpers.rel_err(s_out, ref["s_new"]) < tol32(ref["cond"]))[stratum1].all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[stratum1].all()
+    assert (helpers.rel_err(s_out, ref["s_new"]) < 2e-6)[stratum1].all()
 
 
 @pytest.mark.parametrize("family", ["circle", "iiwa6"])
@@ -79,8 +80,8 @@ def test_error_correction_variant(cuda_device, family):
     p.variant = _lib.VARIANT_ERROR_CORRECTION
     ddq, s_out, _, _ = _run(family, q, dq, s, alpha, p, cuda_device, dbg=False)
     ok = ~ref["rank_def"]
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
-    assert (helpers.rel_err(s_out, ref["s_new"]) < tol32(ref["cond"]))[ok].all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[ok].all()
+    assert (helpers.rel_err(s_out, ref["s_new"]) < 2e-6)[ok].all()
 
 
 @pytest.mark.parametrize("family", ["planar", "iiwa6"])
@@ -91,7 +92,7 @@ def test_bias_mode_omega_cross_v(cuda_device, family):
     p.bias_mode = _lib.BIAS_OMEGA_X_V
     ddq, s_out, _, _ = _run(family, q, dq, s, alpha, p, cuda_device, dbg=False)
     ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[ok].all()
 
 
 @pytest.mark.parametrize("family", ["circle", "planar", "iiwa6", "iiwa7"])
@@ -124,7 +125,7 @@ def test_circle_reference_trajectory_golden(cuda_device, golden):
     # inputs are rounded to fp32 here, so compare against the oracle on the rounded inputs ...
     ref = helpers.oracle_batch("circle", f32(q), f32(dq), f32(s_ref[:-1]), f32(alpha), basis="svd")
     ok = ref["margin"] > 1e-3
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[ok].all()
     # ... and against the float64 trajectory itself at the accuracy of the fp32 rounding of its inputs
     assert np.abs(dbg[0, 3:] - golden["circleA_act_b"][0]).max() < 1e-5          # [0, 7, 14]
     assert np.median(np.abs(s_out - s_ref[1:])) < 1e-6
@@ -134,7 +135,7 @@ def test_circle_single_projection_golden(cuda_device, golden):
     g = {k: np.ascontiguousarray(golden["circleP_" + k], dtype=np.float32) for k in ("q", "dq", "s", "alpha")}
     ddq, s_out, _, st = _run("circle", g["q"], g["dq"], g["s"], g["alpha"], _params("circle"), cuda_device, dbg=False)
     ref = helpers.oracle_batch("circle", g["q"], g["dq"], g["s"], g["alpha"], basis="svd")
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"])).all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6).all()
     # the recorded fp64 outputs (u = ddq / acc_max) at fp32-input accuracy
     assert np.median(np.abs(ddq / 10.0 - golden["circleP_u"])) < 1e-5
     assert (s_out[golden["circleP_s"][:, 0] == 0.0] != 0).all()      # active constraint (s = 0) handled

@@ -54,15 +54,13 @@ def test_full_step_vs_oracle(harness, family, B, dtype):
     # a pivot candidate within 1e-4 (relative) of the tolerance may legitimately flip in fp32
     if dtype == np.float32:
         ok &= ref["margin"] > 1e-3
-    tol = TOL64 if dtype == np.float64 else tol32(ref["cond"])
+    tol = TOL64 if dtype == np.float64 else 2e-6      # double inside: fp32 output rounding is all that is left
     e_mn = helpers.rel_err(dbg[:, :N], ref["w_mn"])
     e_nl = helpers.rel_err(dbg[:, N:], ref["w_null"])
     e_dd = helpers.rel_err(ddq, ref["ddq"], ref["w"])
     e_s = helpers.rel_err(s_out, ref["s_new"])
     for name, e in (("w_mn", e_mn), ("w_null", e_nl), ("ddq", e_dd), ("s", e_s)):
         assert (e < tol)[ok].all(), "%s: %g (stratum I max %g)" % (name, e[ok].max(), e[ok & ~ref["fired"]].max())
-        if dtype == np.float32:
-            assert (e[ok] < TOL32).mean() > 0.95
     # status bits agree with the oracle's trace
     dropped = (st & _lib.ST_COLUMN_DROPPED) != 0
     assert (dropped[ok] >= ref["fired"][ok]).all()
@@ -79,8 +77,8 @@ def test_stratum_one_equals_reference_svd_basis(harness, family):
     ddq, s_out, dbg, st = helpers.harness_step(harness, family, _params(family).flat(), q, dq, s, alpha, np.float32)
     stratum1 = ~ref["fired"] & ~can["fired"] & ~ref["rank_def"]
     assert stratum1.sum() > 0.5 * len(stratum1)
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[stratum1].all()
-    assert (helpers.rel_err(s_out, ref["s_new"]) < tol32(ref["cond"]))[stratum1].all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[stratum1].all()
+    assert (helpers.rel_err(s_out, ref["s_new"]) < 2e-6)[stratum1].all()
 
 
 @pytest.mark.parametrize("family", ["circle", "iiwa6"])
@@ -94,8 +92,8 @@ def test_error_correction_variant(harness, family):
     p.variant = _lib.VARIANT_ERROR_CORRECTION
     ddq, s_out, dbg, st = helpers.harness_step(harness, family, p.flat(), q, dq, s, alpha, np.float32)
     ok = ~ref["rank_def"]
-    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < tol32(ref["cond"]))[ok].all()
-    assert (helpers.rel_err(s_out, ref["s_new"]) < tol32(ref["cond"]))[ok].all()
+    assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[ok].all()
+    assert (helpers.rel_err(s_out, ref["s_new"]) < 2e-6)[ok].all()
 
 
 @pytest.mark.parametrize("family", ["planar", "iiwa6", "iiwa7"])
