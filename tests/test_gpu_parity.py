@@ -277,3 +277,31 @@ def test_host_buffer_entry_point(cuda_device, mode):
         with pytest.raises(_lib.AtacomError):
             ctx.iiwa_step(6, *hp, np.zeros((B, 6), np.float32), np.zeros((B, 11), np.float32), p)
     ctx.close()
+
+
+def test_multi_wave_batch_and_nonfinite_inputs(cuda_device):
+    """A batch of several waves of blocks (300 001 environments: 670 blocks of 448 on 148 SMs) is bit-identical to
+    its pieces; a non-finite input row is flagged ST_NONFINITE and does not disturb its neighbours."""
+    dev = cuda_device
+    p = _lib.default_params("iiwa", 6)
+    B = 300001
+    q, dq, s, alpha = synthetic.device_batch("iiwa", B, 404, dev, 6, p)
+    status = torch.zeros(B, dtype=torch.uint8, device=dev)
+    ddq, s_out = projection.step("iiwa", q, dq, s, alpha, p, status=status)
+    for lo, hi in ((0, 65536), (65536, 200000), (200000, B)):
+        d2, s2 = projection.step("iiwa", *(t[lo:hi].contiguous() for t in (q, dq, s, alpha)), p)
+        assert torch.equal(d2, ddq[lo:hi]) and torch.equal(s2, s_out[lo:hi])
+    assert torch.isfinite(ddq).all() and ((status & _lib.ST_NONFINITE) == 0).all()
+    bad = [5, 1000, B - 1]
+    q2 = q.clone()
+    q2[bad[0], 2] = float("nan")
+    q2[bad[1], 0] = float("inf")
+    s3 = s.clone()
+    s3[bad[2], 4] = float("nan")
+    st2 = torch.zeros(B, dtype=torch.uint8, device=dev)
+    ddq2, s_out2 = projection.step("iiwa", q2, dq, s3, alpha, p, status=st2)
+    flagged = (st2 & _lib.ST_NONFINITE) != 0
+    assert flagged[bad].all() and int(flagged.sum()) == len(bad)
+    keep = torch.ones(B, dtype=torch.bool, device=dev)
+    keep[bad] = False
+    assert torch.equal(ddq2[keep], ddq[keep]) and torch.equal(s_out2[keep], s_out[keep])
