@@ -233,3 +233,29 @@ def test_env_rollout_equals_repeated_step(cuda_device, golden):
     np.testing.assert_allclose(env._state.cpu().numpy()[0], golden["collC_post"][29], atol=2e-5)
     np.testing.assert_allclose(env.s.cpu().numpy()[0], golden["collC_s"][30], atol=2e-5)
     np.testing.assert_allclose(rew.cpu().numpy()[:, 0], golden["collC_rewards"][:30], atol=1e-6)
+
+
+def test_batched_core_circle_experiment_loop(cuda_device):
+    """The experiment loop of examples/circle_exp.py (evaluate -> metrics -> learn) with a random agent over
+    1024 circle environments: dataset layout, episode boundaries, J / R, the constraint log."""
+    from rl_on_manifold_b200.rollout import BatchedCore, UniformAgent, compute_J, compute_metrics
+    B, H = 1024, 50
+    mdp = CircleEnvAtacom(horizon=H, gamma=0.99, n_envs=B, random_init=True, device=cuda_device)
+    mdp.seed(0)
+    agent = UniformAgent(mdp, seed=1)
+    core = BatchedCore(agent, mdp)
+    data = core.evaluate(n_episodes=2)
+    assert data["state"].shape == (2 * H, B, 4) and data["action"].shape == (2 * H, B, 1)
+    assert data["last"][H - 1].all() and data["last"][2 * H - 1].all() and int(data["last"].sum()) == 2 * B
+    assert not data["absorbing"].any()
+    # next_state of step t is the state of step t + 1 inside an episode
+    assert torch.equal(data["next_state"][:H - 1], data["state"][1:H])
+    J, R = compute_J(data, 0.99), compute_J(data, 1.0)
+    assert J.shape == (2, B) and (R >= J).all() and torch.isfinite(J).all()
+    ref = sum(0.99 ** t * data["reward"][t, 0].double() for t in range(H))
+    assert abs(float(J[0, 0]) - float(ref)) < 1e-9
+    mdp.get_constraints_logs()
+    Jm, Rm, c_avg, c_max, c_dq_max = compute_metrics(core, n_episodes=1)
+    assert c_max < 2e-2 and c_dq_max < 0.5 and 0 < Jm < Rm          # ATACOM keeps the agent on the manifold
+    core.learn(n_steps=30, n_steps_per_fit=10)
+    assert agent.n_fits == 3
