@@ -135,6 +135,18 @@ int atacom_iiwa_step_gather_sync(int n_ctrl_joints, const float* q, const float*
                                  const AtacomParams* p, void* stream, float* const* peer_ddq, int world,
                                  int64_t row_offset, uint32_t* const* peer_flags, uint32_t* local_sync, int rank);
 
+/* ---- K simulator sub-steps of one agent step in one launch (PyBullet-style environments) ----
+ * The base environment calls the hook once per simulator sub-step (env_base.py:161-165; MushroomRL's
+ * n_intermediate_steps = 4) while q, dq stay what the last step() set (atacom.py:111-112,123-126): K projections
+ * on the same (q, dq, alpha) that differ only through the slacks each call integrates (atacom.py:135).
+ * ddq: [K, B, n], row block k is the acceleration of sub-step k; s_out: [B, G] the slacks after the K-th call.
+ * workspace: device memory for atacom_iiwa_substeps_workspace_doubles(n) * B doubles (the kinematics' products
+ * are parked there after the first sub-step), or NULL (the kinematics are recomputed every sub-step). */
+int atacom_iiwa_substeps_workspace_doubles(int n_ctrl_joints);
+int atacom_iiwa_step_substeps(int n_ctrl_joints, int K, const float* q, const float* dq, const float* s_in,
+                              const float* alpha, float* ddq, float* s_out, uint8_t* status, double* workspace,
+                              int64_t B, const AtacomParams* p, void* stream);
+
 /* ---- AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149): s = sqrt(max(-2 g~, 0)) ----
  * mask (optional, may be NULL): uint8 [B]; only environments with mask != 0 are re-initialised. */
 int atacom_circle_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,

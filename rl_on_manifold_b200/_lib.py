@@ -82,6 +82,9 @@ SIGNATURES = {
     "atacom_iiwa_step_gather_sync": ([ctypes.c_int, _f, _f, _f, _f, _f, _f, _u8, _i64, _P, _stream,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _i64,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int], ctypes.c_int),
+    "atacom_iiwa_substeps_workspace_doubles": ([ctypes.c_int], ctypes.c_int),
+    "atacom_iiwa_step_substeps": ([ctypes.c_int, ctypes.c_int, _f, _f, _f, _f, _f, _f, _u8, ctypes.c_void_p, _i64, _P,
+                                   _stream], ctypes.c_int),
     "atacom_circle_slack_init": ([_f, _f, _f, _u8, _i64, _P, _stream], ctypes.c_int),
     "atacom_planar_slack_init": ([_f, _f, _f, _u8, _i64, _P, _stream], ctypes.c_int),
     "atacom_iiwa_slack_init": ([ctypes.c_int, _f, _f, _f, _u8, _i64, _P, _stream], ctypes.c_int),

@@ -37,6 +37,15 @@
 #define ATACOM_UNROLL
 #endif
 
+// rarely taken paths are kept out of line so that they do not set the register budget of the hot path
+#if defined(__CUDACC__)
+#define ATACOM_NOINLINE __host__ __device__ __noinline__
+#define ATACOM_ROLLED _Pragma("unroll 1")
+#else
+#define ATACOM_NOINLINE __attribute__((noinline))
+#define ATACOM_ROLLED
+#endif
+
 namespace atacom {
 
 // The per-environment code is one long fully unrolled instruction stream (> 100 KB of SASS); warps

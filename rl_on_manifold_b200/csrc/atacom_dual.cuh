@@ -29,8 +29,9 @@
 //  (7) if one pivot is still missing after the x columns (an active constraint took a
 //      direction away from x), the remaining null direction is  (nu, -A_g nu / s)  with nu
 //      supported on the two (F = 1) / one (F = 0) unpivoted x columns; the first slack column
-//      whose entry exceeds tol becomes the coordinate.  Two or more missing pivots, or F > 1,
-//      return ST_DENSE_PATH and the caller runs the general structured / dense path.
+//      whose entry exceeds tol becomes the coordinate; with two pivots missing the same is done in the
+//      remaining plane (two_slack_pivots); three or more missing pivots, or F > 1, take the out-of-line
+//      general routine (null_part_general: the oracle's own procedure in the reduced coordinates).
 //
 // All arithmetic is in R (double on the device: B200 runs FP64 at half the FP32 rate and the
 // dual Gram matrix squares cond(Jc)); ~1.0 kFLOP per iiwa environment, no data-dependent
@@ -95,6 +96,247 @@ struct Dual {
   static_assert(NDIAG <= n && NDIAG <= G, "diagonal rows: row GD + j has its single entry in column j");
   static constexpr ATACOM_HD int lidx(int i, int l) { return i * (i - 1) / 2 + l; }   // strictly lower part of L
   static constexpr int LI0 = m * (m - 1) / 2;                                        // then 1 / diag(L)
+
+  // (7c) Any number of slack pivots (and any F): the null part once more, literally the way the oracle does it
+  // (oracle/nullspace.py:canonical_null_basis + tol_rref), but in the reduced coordinates (t, z_d) where the
+  // projector is I - W^T W with W = L^-1 [B, S_d] — still nothing divided by a slack.  Rolled loops over a
+  // (n + GD)^2 matrix in local memory: ~2 k FLOP, small code; taken when three or more constraints are active at
+  // once.  Column c of Jc corresponds to the reduced vector sc * e_idx: x_c -> sigma_c e_{t_c}, dense slack i ->
+  // e_{z_i}, diagonal slack j -> -gamma_j e_{t_j}.
+  template <class YS, class LS>
+  static ATACOM_NOINLINE uint8_t null_part_general(YS& Y, LS& Ls, const R* s, const R* sig, const R* gam,
+                                                   const R* alpha, R tol, R* w_null) {
+    constexpr int NR = n + GD;
+    uint8_t status = 0;
+    R W[M1][NR], Pm[NR][NR], V[K1][NR], beta[K1];
+    ATACOM_ROLLED
+    for (int l = 0; l < m; ++l) {
+      ATACOM_ROLLED
+      for (int j = 0; j < n; ++j) W[l][j] = Y.get_dyn(l * n + j);
+      ATACOM_ROLLED
+      for (int i = 0; i < GD; ++i) W[l][n + i] = R(0);
+    }
+    ATACOM_ROLLED
+    for (int i = 0; i < GD; ++i) {   // column F + i of L^-1 times s_i (forward substitution)
+      const int c0 = F + i;
+      ATACOM_ROLLED
+      for (int l = c0; l < m; ++l) {
+        R acc = (l == c0) ? s[i] : R(0);
+        ATACOM_ROLLED
+        for (int p = c0; p < l; ++p) acc -= Ls.get_dyn(lidx(l, p)) * W[p][n + i];
+        W[l][n + i] = acc * Ls.get_dyn(LI0 + l);
+      }
+    }
+    ATACOM_ROLLED
+    for (int a = 0; a < NR; ++a) {
+      R wa[M1];
+      ATACOM_UNROLL
+      for (int l = 0; l < m; ++l) wa[l] = W[l][a];
+      ATACOM_ROLLED
+      for (int b = a; b < NR; ++b) {
+        R acc = (a == b) ? R(1) : R(0);
+        ATACOM_UNROLL
+        for (int l = 0; l < m; ++l) acc -= wa[l] * W[l][b];
+        Pm[a][b] = acc;
+        Pm[b][a] = acc;
+      }
+    }
+    int npiv = 0;
+    ATACOM_ROLLED
+    for (int c = 0; c < N; ++c) {
+      int idx;
+      R sc;
+      if (c < n) {
+        idx = c;
+        sc = sig[c];
+      } else if (c - n < GD) {
+        idx = c;          // n + i
+        sc = R(1);
+      } else {
+        idx = c - n - GD;
+        sc = -gam[idx];
+      }
+      R part = R(0);     // sum over the rows pivoted so far of beta_r V[r][c]
+      ATACOM_ROLLED
+      for (int r = 0; r < npiv; ++r) part += beta[r] * sc * V[r][idx];
+      const R d = sc * sc * Pm[idx][idx];
+      if (npiv < k && d > tol * tol && d > R(DUAL_TINY)) {
+        const R inv = dual_rsqrt(d);
+        ATACOM_ROLLED
+        for (int a = 0; a < NR; ++a) V[npiv][a] = Pm[a][idx] * sc * inv;
+        ATACOM_ROLLED
+        for (int a = 0; a < NR; ++a) {
+          const R va = V[npiv][a];
+          ATACOM_UNROLL
+          for (int b = 0; b < NR; ++b) Pm[a][b] -= va * V[npiv][b];
+        }
+        beta[npiv] = (alpha[npiv] - part) * inv;
+        w_null[c] = alpha[npiv];
+        if (c >= n) status |= ST_SLACK_PIVOT;
+        ++npiv;
+      } else {
+        if (npiv < k) status |= ST_COLUMN_DROPPED;
+        w_null[c] = part;   // dropped: the rows pivoted before it; untested (npiv == k): every row
+      }
+    }
+    if (npiv < k) status |= ST_RANK_DEFICIENT;
+    return status;
+  }
+
+  // (7b) Two pivots missing after the x columns (two active constraints took two directions away from x; k >= 2).
+  // The remaining null space is two-dimensional: tau supported on the F + 2 unpivoted columns with B_f tau = 0,
+  // spanned by tau1, tau2; the full vectors are n_j = (sigma tau_j, -gamma tau_j, -(B tau_j) / s) with Gram matrix
+  // g.  The component of the projected unit vector of slack column i in that plane has norm^2
+  // [a_i b_i] g^-1 [a_i b_i]^T, (a_i, b_i) the z_i entries of n_1, n_2: the first column above tol^2 is the first
+  // pivot (row q1), the direction of the plane with zero z_i1 entry is what is left for the second (row q2).
+  template <class YS, class LS>
+  static ATACOM_HD uint8_t two_slack_pivots(YS& Y, LS& Ls, const R* s, const R* alpha, R tol, const R* gam,
+                                            const bool* take, int npiv, uint8_t status, R* w_null) {
+    int u1 = 0, u2 = 0, u3 = 0;
+    {
+      int cnt = 0;
+      ATACOM_UNROLL
+      for (int c = 0; c < n; ++c) {
+        u1 = (!take[c] && cnt == 0) ? c : u1;
+        u2 = (!take[c] && cnt == 1) ? c : u2;
+        u3 = (!take[c] && cnt == 2) ? c : u3;
+        cnt += take[c] ? 0 : 1;
+      }
+    }
+    R t1[3] = {R(1), R(0), R(0)}, t2[3] = {R(0), R(1), R(0)};   // coordinates at u1, u2, u3 (F = 0: unit vectors)
+    if (F == 1) {
+      const R v1 = Y.get_dyn(u1), v2 = Y.get_dyn(u2), v3 = Y.get_dyn(u3);   // equality row of Y ~ B_f
+      const R m1 = num<R>::abs(v1), m2 = num<R>::abs(v2), m3 = num<R>::abs(v3);
+      const bool p3 = m3 >= m1 && m3 >= m2, p2 = !p3 && m2 >= m1;
+      // the largest entry is the one solved for
+      t1[0] = p3 ? v3 : (p2 ? v2 : -v2);
+      t1[1] = p3 ? R(0) : (p2 ? -v1 : v1);
+      t1[2] = p3 ? -v1 : R(0);
+      t2[0] = p3 ? R(0) : (p2 ? R(0) : -v3);
+      t2[1] = p3 ? v3 : (p2 ? -v3 : R(0));
+      t2[2] = p3 ? -v2 : (p2 ? v2 : v1);
+    }
+    // n_1, n_2 as vectors over PC components: the 3 tau coordinates (the x and z_diag entries of a joint have
+    // joint norm |tau_j|, sigma^2 + gamma^2 = 1) and the GD dense slack entries.  A slack that is (nearly) zero
+    // makes its entry huge, so the Gram determinant and everything derived from it is formed from 2 x 2
+    // minors and differences (Lagrange identity) — never from g11 g22 - g12^2, which would cancel.
+    constexpr int PC = 3 + GD;
+    R U[PC], V[PC], ya[M1], yb[M1], ea[G1], eb[G1];
+    ATACOM_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      U[c] = t1[c];
+      V[c] = t2[c];
+    }
+    ATACOM_UNROLL
+    for (int l = 0; l < m; ++l) {   // B = L Y  =>  b_i . tau = sum_{l <= i} L[i][l] (Y[l] . tau)
+      const R y1 = Y.get_dyn(l * n + u1), y2 = Y.get_dyn(l * n + u2), y3 = (F == 1) ? Y.get_dyn(l * n + u3) : R(0);
+      ya[l] = y1 * t1[0] + y2 * t1[1] + y3 * t1[2];
+      yb[l] = y1 * t2[0] + y2 * t2[1] + y3 * t2[2];
+    }
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) {
+      if (i < GD) {
+        const int ri = F + (i < GD ? i : 0);
+        const R lii = Ls.get(LI0 + ri);
+        const R dii = (lii > R(0)) ? dual_rsqrt(lii * lii) : R(0);   // L[ri][ri] = 1 / li
+        R an = ya[ri] * dii, bn = yb[ri] * dii;
+        ATACOM_UNROLL
+        for (int l = 0; l < ri; ++l) {
+          const R lv = Ls.get(lidx(ri, l));
+          an += lv * ya[l];
+          bn += lv * yb[l];
+        }
+        const R s2 = s[i] * s[i];
+        const R rs = dual_rsqrt(s2 > R(DUAL_TINY) ? s2 : R(DUAL_TINY));   // 1 / |s_i|, s_i = 0 -> the limit
+        const R sg = s[i] < R(0) ? rs : -rs;
+        ea[i] = an * sg;
+        eb[i] = bn * sg;
+        U[3 + (i < GD ? i : 0)] = ea[i];
+        V[3 + (i < GD ? i : 0)] = eb[i];
+      } else {
+        const int j = i >= GD ? i - GD : 0;
+        const R ta = (j == u1) ? t1[0] : ((j == u2) ? t1[1] : ((F == 1 && j == u3) ? t1[2] : R(0)));
+        const R tb = (j == u1) ? t2[0] : ((j == u2) ? t2[1] : ((F == 1 && j == u3) ? t2[2] : R(0)));
+        ea[i] = -gam[j] * ta;
+        eb[i] = -gam[j] * tb;
+      }
+    }
+    R det = R(0);
+    ATACOM_UNROLL
+    for (int p = 0; p < PC; ++p) {
+      ATACOM_UNROLL
+      for (int q = p + 1; q < PC; ++q) {
+        const R mn = U[p] * V[q] - U[q] * V[p];
+        det += mn * mn;
+      }
+    }
+    if (!(det > R(DUAL_TINY))) return status | ST_DENSE_PATH;
+    const R rd = dual_rsqrt(det);
+    const R idet = rd * rd;
+    // first pivot: the first slack column whose component in the plane exceeds tol:
+    // |a_i n_2 - b_i n_1|^2 / det > tol^2
+    int i1 = G;
+    R a1 = R(0), b1 = R(0), z1 = R(0);
+    ATACOM_UNROLL
+    for (int i = G - 1; i >= 0; --i) {
+      R nn = R(0);
+      ATACOM_UNROLL
+      for (int p = 0; p < PC; ++p) {
+        const R d = ea[i] * V[p] - eb[i] * U[p];
+        nn += d * d;
+      }
+      const bool hit = nn * idet > tol * tol;
+      i1 = hit ? i : i1;
+      a1 = hit ? ea[i] : a1;
+      b1 = hit ? eb[i] : b1;
+      z1 = hit ? w_null[n + i] : z1;
+    }
+    if (i1 == G) return status | ST_RANK_DEFICIENT;
+    // d = a1 n_2 - b1 n_1: the direction of the plane with zero z_i1 entry (second row, up to sign and norm);
+    // the first row is the unit vector of the plane orthogonal to it: q1 = (k1 n_1 + k2 n_2) with
+    // (k1, k2) = g^-1 (a1, b1) / p1 = ((n_2 . d), -(n_1 . d)) / (det p1),  p1^2 = |d|^2 / det
+    R nrm2 = R(0), vd = R(0), ud = R(0);
+    ATACOM_UNROLL
+    for (int p = 0; p < PC; ++p) {
+      const R d = a1 * V[p] - b1 * U[p];
+      nrm2 += d * d;
+      vd += V[p] * d;
+      ud += U[p] * d;
+    }
+    const R rn = dual_rsqrt(nrm2 > R(DUAL_TINY) ? nrm2 : R(DUAL_TINY));
+    const R ip1 = rn * (det * rd);                 // 1 / p1 = sqrt(det) / |d|
+    const R k1 = vd * idet * ip1, k2 = -ud * idet * ip1;
+    int i2 = G;
+    R f2 = R(0), z2 = R(0), q12 = R(0);
+    ATACOM_UNROLL
+    for (int i = G - 1; i >= 0; --i) {
+      const R fi = (b1 * ea[i] - a1 * eb[i]) * rn;     // entry of the second row (up to its sign)
+      const R qi = k1 * ea[i] + k2 * eb[i];            // entry of the first row
+      const bool hit = (i > i1) && (num<R>::abs(fi) > tol);
+      i2 = hit ? i : i2;
+      f2 = hit ? fi : f2;
+      z2 = hit ? w_null[n + i] : z2;
+      q12 = hit ? qi : q12;
+      ea[i] = qi;     // from here on: first-row entries in ea, second-row entries in eb
+      eb[i] = fi;
+    }
+    if (i2 == G) return status | ST_RANK_DEFICIENT;
+    R al1 = R(0), al2 = R(0);
+    ATACOM_UNROLL
+    for (int l = 0; l < k; ++l) {
+      al1 = (l == npiv) ? alpha[l] : al1;
+      al2 = (l == npiv + 1) ? alpha[l] : al2;
+    }
+    const R bt1 = (al1 - z1) * ip1;
+    const R rf = dual_rsqrt(f2 * f2);
+    const R bt2 = (al2 - z2 - bt1 * q12) * (f2 * rf * rf);   // / f2: beta of the second row times the sign of its pivot
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) {
+      const R v = w_null[n + i];
+      w_null[n + i] = (i < i1) ? v : ((i == i1) ? al1 : ((i < i2) ? v + bt1 * ea[i] : ((i == i2) ? al2 : v + bt1 * ea[i] + bt2 * eb[i])));
+    }
+    return status | ST_SLACK_PIVOT | ST_COLUMN_DROPPED;
+  }
 
   // Y: on entry the m x n dense rows of A (row-major, equalities first), overwritten; Ls: scratch for L.
   // dg: NDIAG diagonal entries, s: G, r: C (rows ordered equality, dense inequality, diagonal
@@ -341,8 +583,28 @@ struct Dual {
     for (int i = 0; i < GD; ++i) w_null[n + i] = -s[i] * yv[F + i];
     if (npiv == k) return status;
 
-    // ---- (7) one slack column becomes a tangent-space coordinate
-    if (k - npiv > 1 || F > 1) return status | ST_DENSE_PATH;
+    // ---- (7) slack columns become tangent-space coordinates
+    if (k - npiv == 2 && F <= 1) {
+      const uint8_t st2 = two_slack_pivots(Y, Ls, s, alpha, tol, gam, take, npiv, status, w_null);
+      if (!(st2 & ST_DENSE_PATH)) return st2;     // (a degenerate plane falls through to the general routine)
+    }
+    if (k - npiv > 1 || F > 1) {
+      // private copies: only these (not the register-resident operands of the hot path) get their address taken
+      R s2[G1], sg2[n], gm2[n], al2[K1], wn2[N];
+      ATACOM_UNROLL
+      for (int i = 0; i < G; ++i) s2[i] = s[i];
+      ATACOM_UNROLL
+      for (int j = 0; j < n; ++j) {
+        sg2[j] = sig[j];
+        gm2[j] = gam[j];
+      }
+      ATACOM_UNROLL
+      for (int l = 0; l < k; ++l) al2[l] = alpha[l];
+      const uint8_t st2 = null_part_general(Y, Ls, s2, sg2, gm2, al2, tol, wn2);
+      ATACOM_UNROLL
+      for (int i = 0; i < N; ++i) w_null[i] = wn2[i];
+      return (status & ST_RANK_DEFICIENT) | st2;
+    }
     // remaining null direction in the free coordinates: tau supported on the unpivoted columns with
     // B_f tau = 0; its entries are x_j = sigma_j tau_j, z_diag,j = -gamma_j tau_j, z_dense,i = -(b_i . tau) / s_i.
     // The equality row of Y is B_f / L_00: same direction.

@@ -328,11 +328,6 @@ struct IiwaEnv {
 // ----------------------------------------------------------------------------- projection dispatch
 // Dense Householder path, kept out of line: it is the rarely taken fallback of the structured path and
 // must not set the register budget of the kernels that inline the fast path.
-#if defined(__CUDACC__)
-#define ATACOM_NOINLINE __host__ __device__ __noinline__
-#else
-#define ATACOM_NOINLINE __attribute__((noinline))
-#endif
 template <typename T, class D>
 ATACOM_NOINLINE uint8_t project_dense_outlined(const T* Af, const T* Ag, const T* s, const T* r, const T* alpha,
                                                T tol, bool want_null, T* w_mn, T* w_null) {
@@ -522,32 +517,26 @@ struct DualSink {
 };
 
 // The whole step around the dual projection (atacom_dual.cuh): everything between the fp32 inputs and
-// the fp32 outputs is carried in HP.  An environment the dual path defers (two or more slack pivots)
-// comes back flagged ST_DENSE_PATH with no outputs written: the caller reruns it on the general fp32
-// path.
+// the fp32 outputs is carried in HP.
 // `fetch(s, alpha)` is called AFTER the constraint functor has run and must fill the slack row (G values) and
 // the action row (n values, zero-padded): the kinematics need neither, so a kernel can have them copied in
 // the background (bulk copy into shared memory) while the kinematics run on q and dq.
-template <class Env, typename T, typename HP, class YS, class LS, class Fetch>
-ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q,
-                                 const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg) {
+// Projection + assembly + slack integration + acceleration truncation on operands that are already in place:
+// Y holds the K-scaled dense Jacobian rows, dg the diagonal rows, r the right-hand side (slack terms included),
+// sh the current slacks.  s_new = s + dt w_z in HP (atacom.py:135); ddq clipped (atacom.py:117-121).
+template <class Env, typename T, typename HP, class YS, class LS>
+ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const HP* dg, const HP* r,
+                            const HP* sh, const T* alpha, const T* dq, T* ddq, HP* s_new, T* w_dbg) {
   using D = typename Env::D;
   constexpr int NDIAG = Env::NDIAG;
   constexpr int n = D::n, G = D::G, N = D::N, k = D::k;
   const bool ec = P.variant == VARIANT_EC;
-  DualSink<T, HP, D, NDIAG, YS> sink(Kd, Y);
-  Env::template eval<T, HP>(P, q, dq, sink);
-  T s[at_least_1<G>::value], alpha[n];
-  fetch(s, alpha);
-  HP sh[at_least_1<G>::value], ah[at_least_1<k>::value];
-  ATACOM_UNROLL
-  for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
-  sink.add_slack_terms(sh);
+  HP ah[at_least_1<k>::value];
   ATACOM_UNROLL
   for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
   T w_mn[N];
   HP w_null[N];
-  uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, sink.dg, sh, sink.r, ah, Kd.tol, !ec, w_mn, w_null);
+  uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null);
   if (st & ST_DENSE_PATH) return st;
   if (ec) {
     ATACOM_UNROLL
@@ -557,9 +546,8 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) {
     const HP wz = cvt<HP>(w_mn[n + i]) + w_null[n + i];
-    const T so = cvt<T>(sh[i] + wz * Kd.dt);                      // atacom.py:135
-    s_out[i] = so;
-    finite = finite && (so - so == T(0));
+    s_new[i] = sh[i] + wz * Kd.dt;                                // atacom.py:135
+    finite = finite && (s_new[i] - s_new[i] == HP(0));
   }
   ATACOM_UNROLL
   for (int j = 0; j < n; ++j) {
@@ -586,6 +574,27 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
     }
   }
   if (!finite) st |= ST_NONFINITE;
+  return st;
+}
+
+template <class Env, typename T, typename HP, class YS, class LS, class Fetch>
+ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q,
+                                 const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg) {
+  using D = typename Env::D;
+  constexpr int NDIAG = Env::NDIAG;
+  constexpr int n = D::n, G = D::G;
+  DualSink<T, HP, D, NDIAG, YS> sink(Kd, Y);
+  Env::template eval<T, HP>(P, q, dq, sink);
+  T s[at_least_1<G>::value], alpha[n];
+  fetch(s, alpha);
+  HP sh[at_least_1<G>::value], sn[at_least_1<G>::value];
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
+  sink.add_slack_terms(sh);
+  const uint8_t st = dual_tail<Env, T, HP>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg);
+  if (st & ST_DENSE_PATH) return st;
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
   return st;
 }
 

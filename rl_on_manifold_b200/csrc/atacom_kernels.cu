@@ -224,8 +224,7 @@ template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: d
                               // 3: q, dq direct; s, alpha bulk-copied in the background of the kinematics
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
-                                                                    const __grid_constant__ DualConsts<double> Kd,
-                                                                    const __grid_constant__ ParamsT<double> Pd) {
+                                                                    const __grid_constant__ DualConsts<double> Kd) {
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
@@ -323,28 +322,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < n; ++j) a_row[j] = al[j];
   };
-  uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg);
-  if (st & ST_DENSE_PATH) {
-    // two or more slack pivots: the general (structured -> dense) path, in double like everything else
-    double qd[n], dqd[n], sd[G1], ald[n], ddqd[n], sod[G1], dbgd[2 * N];
-#pragma unroll
-    for (int j = 0; j < n; ++j) {
-      qd[j] = q[j];
-      dqd[j] = dq[j];
-      ald[j] = al[j];
-    }
-#pragma unroll
-    for (int i = 0; i < G; ++i) sd[i] = s[i];
-    st = ST_DENSE_PATH | step_general_outlined<Env, double, double>(Pd, qd, dqd, sd, ald, ddqd, sod, dbg ? dbgd : nullptr);
-#pragma unroll
-    for (int j = 0; j < n; ++j) ddq[j] = static_cast<float>(ddqd[j]);
-#pragma unroll
-    for (int i = 0; i < G; ++i) so[i] = static_cast<float>(sod[i]);
-    if (dbg) {
-#pragma unroll
-      for (int i = 0; i < 2 * N; ++i) dbg[i] = static_cast<float>(dbgd[i]);
-    }
-  }
+  const uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg);
 #else
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
@@ -403,6 +381,112 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
         }
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------ fused simulator sub-steps
+// PyBullet-style environments call the hook once per simulator sub-step (env_base.py:161-165, 4 per agent step)
+// while q and dq stay what the last step() set (atacom.py:111-112, 123-126): the K projections of one agent step
+// share the kinematics and differ only through the slacks, which each call integrates (atacom.py:135).  One
+// launch does all K: the functor runs once, its products (K-scaled dense Jacobian rows, diagonal rows, the
+// slack-free part of the right-hand side) are parked in a caller-provided workspace ([WS][B] doubles, L2-resident
+// at these sizes) and reloaded for sub-steps 2..K; the slacks are carried in double.  Without a workspace the
+// functor is simply re-run.  ddq: [K, B, n], one row per sub-step (each goes to the simulator's inverse dynamics).
+struct SubstepArgs {
+  const float* q;
+  const float* dq;
+  const float* s_in;
+  const float* alpha;
+  float* ddq;
+  float* s_out;
+  uint8_t* status;
+  double* ws;
+  int64_t B;
+  int32_t K;
+};
+
+template <class Env, bool PARK>
+__global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_substeps_kernel(const __grid_constant__ SubstepArgs a,
+                                                                        const __grid_constant__ ParamsT<float> P,
+                                                                        const __grid_constant__ DualConsts<double> Kd) {
+  using D = typename Env::D;
+  using SC = StepScratch<Env>;
+  using DU = typename SC::DU;
+  constexpr int n = D::n, G = D::G, k = D::k, C = D::C, F = D::F, NDIAG = Env::NDIAG;
+  constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value, ND1 = at_least_1<NDIAG>::value;
+  const int64_t e_raw = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = e_raw < a.B;
+  const int64_t e = valid ? e_raw : a.B - 1;
+  const bool ec = P.variant == VARIANT_EC;
+  extern __shared__ __align__(128) unsigned char atacom_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* region = atacom_smem + warp * SC::WARP_BYTES;
+  typename SC::YS Ys = SC::y(region, lane);
+  typename SC::LS Ls = SC::l(region, lane);
+
+  // what stays live across the sub-steps is kept small on purpose (slacks, dq, alpha): shared memory takes
+  // 204 of the SM's 256 KB, so a register spill inside the loop would go all the way to L2
+  float dq[n], al[n];
+  double sh[G1], sn[G1];
+  row_load<n>(a.dq, e, dq);
+  {
+    float s[G1];
+    if (G > 0) row_load<G1>(a.s_in, e, s);
+#pragma unroll
+    for (int i = 0; i < G; ++i) sh[i] = s[i];
+  }
+  if (ec) {
+    row_load<n>(a.alpha, e, al);
+  } else {
+    float ak[K1];
+    if (k > 0) row_load<K1>(a.alpha, e, ak);
+#pragma unroll
+    for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
+  }
+  double* wp = a.ws + e;          // this environment's column of the [WS][B] workspace (PARK only)
+  uint8_t status = 0;
+  for (int step = 0; step < a.K; ++step) {
+    double dg[ND1], r[at_least_1<C>::value];
+    if (PARK && step > 0) {
+#pragma unroll
+      for (int i = 0; i < DU::Y_SIZE; ++i) Ys.set(i, wp[static_cast<int64_t>(i) * a.B]);
+#pragma unroll
+      for (int j = 0; j < NDIAG; ++j) dg[j] = wp[static_cast<int64_t>(DU::Y_SIZE + j) * a.B];
+#pragma unroll
+      for (int i = 0; i < C; ++i) r[i] = wp[static_cast<int64_t>(DU::Y_SIZE + NDIAG + i) * a.B];
+    } else {
+      float q[n];
+      row_load<n>(a.q, e, q);
+      DualSink<float, double, D, NDIAG, typename SC::YS> sink(Kd, Ys);
+      Env::template eval<float, double>(P, q, dq, sink);
+#pragma unroll
+      for (int j = 0; j < NDIAG; ++j) dg[j] = sink.dg[j];
+#pragma unroll
+      for (int i = 0; i < C; ++i) r[i] = sink.r[i];
+      if (PARK && a.K > 1 && valid) {   // only this thread reads these entries back: no fence needed
+#pragma unroll
+        for (int i = 0; i < DU::Y_SIZE; ++i) wp[static_cast<int64_t>(i) * a.B] = Ys.get(i);
+#pragma unroll
+        for (int j = 0; j < NDIAG; ++j) wp[static_cast<int64_t>(DU::Y_SIZE + j) * a.B] = dg[j];
+#pragma unroll
+        for (int i = 0; i < C; ++i) wp[static_cast<int64_t>(DU::Y_SIZE + NDIAG + i) * a.B] = r[i];
+      }
+    }
+#pragma unroll
+    for (int i = F; i < C; ++i) r[i] += 0.5 * Kd.K_c[i] * sh[i - F] * sh[i - F];      // atacom.py:195
+    float ddq[n];
+    const uint8_t st = dual_tail<Env, float, double>(P, Kd, Ys, Ls, dg, r, sh, al, dq, ddq, sn, nullptr);
+    status |= st;
+#pragma unroll
+    for (int i = 0; i < G; ++i) sh[i] = sn[i];
+    if (valid) row_store<n>(a.ddq + static_cast<int64_t>(step) * a.B * n, e, ddq);
+  }
+  if (valid) {
+    float so[G1];
+#pragma unroll
+    for (int i = 0; i < G; ++i) so[i] = static_cast<float>(sh[i]);
+    if (G > 0) row_store<G1>(a.s_out, e, so);
+    if (a.status) a.status[e] = status;
   }
 }
 
@@ -680,10 +764,7 @@ __global__ void __launch_bounds__(TPB) circle_rollout_kernel(const __grid_consta
     double ddq[2], so[1];
     LocalStore<double, DU::Y_SIZE> Ys;
     LocalStore<double, DU::L_SIZE> Ls;
-    uint8_t stp = step_dual<Env, double, double>(P, Kd, Ys, Ls, st, st + 2, s, al, ddq, so, nullptr);
-    if (stp & ST_DENSE_PATH)
-      stp = ST_DENSE_PATH | step_general_outlined<Env, double, double>(P, st, st + 2, s, al, ddq, so, nullptr);
-    status |= stp;
+    status |= step_dual<Env, double, double>(P, Kd, Ys, Ls, st, st + 2, s, al, ddq, so, nullptr);
     s[0] = so[0];
     double r2 = 0.0;
 #pragma unroll
@@ -906,7 +987,7 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   constexpr size_t smem = StepScratch<Env>::BYTES;
   if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
   atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
-      a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G), widen_params<double>(as_params(p)));
+      a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
 }
@@ -922,6 +1003,19 @@ int launch_slack_init(const float* q, const float* dq, float* s, const uint8_t* 
                                                                                             as_params(p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch();
+}
+
+template <class Env, bool PARK>
+int launch_substeps(const SubstepArgs& a, const ParamsT<float>& P, unsigned grid, int tpb, cudaStream_t st) {
+  static int cfg = 0;   // per instantiation
+  if (cfg == 0)
+    cfg = cudaFuncSetAttribute(atacom_substeps_kernel<Env, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(StepScratch<Env>::BYTES)) == cudaSuccess ? 1 : -1;
+  if (cfg < 0) return ATACOM_ERR_CUDA;
+  using D = typename Env::D;
+  atacom_substeps_kernel<Env, PARK><<<grid, tpb, StepScratch<Env>::BYTES, st>>>(
+      a, P, make_dual_consts<float, double>(P, D::F, D::G));
+  return ATACOM_OK;
 }
 
 template <class Env>
@@ -1127,6 +1221,34 @@ int atacom_iiwa_step_gather_sync(int n, const float* q, const float* dq, const f
                                         world, row_offset, peer_flags, local_sync, rank);
   }
   return ATACOM_ERR_BAD_DIMS;
+}
+
+int atacom_iiwa_substeps_workspace_doubles(int n) {
+  if (n == 6) return Dual<double, IiwaEnv<6>::D, 6>::Y_SIZE + 6 + IiwaEnv<6>::D::C;
+  if (n == 7) return Dual<double, IiwaEnv<7>::D, 7>::Y_SIZE + 7 + IiwaEnv<7>::D::C;
+  return 0;
+}
+
+int atacom_iiwa_step_substeps(int n, int K, const float* q, const float* dq, const float* s_in, const float* alpha,
+                              float* ddq, float* s_out, uint8_t* status, double* workspace, int64_t B,
+                              const AtacomParams* p, void* stream) {
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if ((n != 6 && n != 7) || K < 1 || K > 64) return ATACOM_ERR_BAD_DIMS;
+  if (B == 0) return ATACOM_OK;
+  if (!q || !dq || !s_in || !alpha || !ddq || !s_out) return ATACOM_ERR_NULL_POINTER;
+  SubstepArgs a{q, dq, s_in, alpha, ddq, s_out, status, workspace, B, K};
+  const int tpb = step_block_size(B);
+  const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const ParamsT<float>& P = as_params(p);
+  rc = n == 6 ? (workspace && K > 1 ? launch_substeps<IiwaEnv<6>, true>(a, P, grid, tpb, st)
+                                    : launch_substeps<IiwaEnv<6>, false>(a, P, grid, tpb, st))
+              : (workspace && K > 1 ? launch_substeps<IiwaEnv<7>, true>(a, P, grid, tpb, st)
+                                    : launch_substeps<IiwaEnv<7>, false>(a, P, grid, tpb, st));
+  if (rc != ATACOM_OK) return rc;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
 }
 
 int atacom_circle_slack_init(const float* q, const float* dq, float* s, const uint8_t* mask, int64_t B,

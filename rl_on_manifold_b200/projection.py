@@ -120,6 +120,35 @@ def iiwa_step_gather(q, dq, s, alpha, params, peer_ptrs, world, row_offset, *, n
     return s_out
 
 
+def iiwa_substeps(q, dq, s, alpha, params, K, *, n_ctrl_joints=6, ddq=None, s_out=None, status=None,
+                  workspace=None, use_workspace=True):
+    """K calls of step_action_function on the same (q, dq, alpha) in one launch — the K simulator sub-steps of one
+    agent step of a PyBullet-style environment (env_base.py:161-165).  Returns (ddq [K, B, n], s_out [B, G])."""
+    n, F, G = family_dims("iiwa", n_ctrl_joints)
+    B = q.shape[0]
+    _check(q, "q", B, n)
+    _check(dq, "dq", B, n)
+    _check(s, "s", B, G)
+    _check(alpha, "alpha", B, _alpha_dim(params, n, F))
+    if ddq is None:
+        ddq = torch.empty(K, B, n, device=q.device, dtype=torch.float32)
+    if tuple(ddq.shape) != (K, B, n) or not ddq.is_contiguous() or not ddq.is_cuda or ddq.dtype != torch.float32:
+        raise ValueError("ddq: expected a contiguous CUDA float32 tensor of shape [%d, %d, %d]" % (K, B, n))
+    if s_out is None:
+        s_out = torch.empty_like(s)
+    _check(s_out, "s_out", B, G)
+    if status is not None:
+        _check(status, "status", B, None, torch.uint8)
+    if workspace is None and use_workspace and K > 1:
+        workspace = torch.empty(_lib.lib.atacom_iiwa_substeps_workspace_doubles(n) * B, device=q.device,
+                                dtype=torch.float64)
+    with torch.cuda.device(q.device):
+        rc = _lib.lib.atacom_iiwa_step_substeps(n, K, _ptr(q), _ptr(dq), _ptr(s), _ptr(alpha), _ptr(ddq), _ptr(s_out),
+                                                _ptr(status), _ptr(workspace), B, ctypes.byref(params), _stream(q))
+    _lib.check(rc)
+    return ddq, s_out
+
+
 def slack_init(family, q, dq, params, *, n_ctrl_joints=6, s=None, mask=None):
     """AtacomEnvWrapper._compute_slack_variables (atacom.py:145-149)."""
     n, F, G = family_dims(family, n_ctrl_joints)

@@ -99,16 +99,6 @@ static void run_step(int64_t B, const double* params, const T* q, const T* dq, c
       LocalStore<double, DU::L_SIZE> Ls;
       uint8_t st = step_dual<Env, T, double>(P, Kd, Ys, Ls, q + b * D::n, dq + b * D::n, s + b * D::G, al,
                                              ddq + b * D::n, s_out + b * D::G, w_dbg + b * 2 * D::N);
-      if (st & ST_DENSE_PATH) {   // as in the kernel: the general path in double
-        const ParamsT<double> Pd = widen_params<double>(P);
-        double qd[D::n], dqd[D::n], sd[D::G > 0 ? D::G : 1], ald[D::n], ddqd[D::n], sod[D::G > 0 ? D::G : 1], dbgd[2 * D::N];
-        for (int j = 0; j < D::n; ++j) { qd[j] = q[b * D::n + j]; dqd[j] = dq[b * D::n + j]; ald[j] = al[j]; }
-        for (int i = 0; i < D::G; ++i) sd[i] = s[b * D::G + i];
-        st = ST_DENSE_PATH | step_general_outlined<Env, double, double>(Pd, qd, dqd, sd, ald, ddqd, sod, dbgd);
-        for (int j = 0; j < D::n; ++j) ddq[b * D::n + j] = static_cast<T>(ddqd[j]);
-        for (int i = 0; i < D::G; ++i) s_out[b * D::G + i] = static_cast<T>(sod[i]);
-        for (int i = 0; i < 2 * D::N; ++i) w_dbg[b * 2 * D::N + i] = static_cast<T>(dbgd[i]);
-      }
       status[b] = st;
     }
   }

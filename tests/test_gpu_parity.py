@@ -305,3 +305,47 @@ def test_multi_wave_batch_and_nonfinite_inputs(cuda_device):
     keep = torch.ones(B, dtype=torch.bool, device=dev)
     keep[bad] = False
     assert torch.equal(ddq2[keep], ddq[keep]) and torch.equal(s_out2[keep], s_out[keep])
+
+
+@pytest.mark.parametrize("nj", [6, 7])
+def test_fused_substeps_equal_repeated_steps(cuda_device, nj):
+    """atacom_iiwa_step_substeps: the K = 4 hook calls of one agent step of a PyBullet-style environment
+    (same q, dq, alpha; slacks integrated by every call) in one launch == 4 launches of the step kernel, and the
+    oracle called 4 times; parked kinematics (workspace) == recomputed kinematics, bit for bit."""
+    dev = cuda_device
+    p = _lib.default_params("iiwa", nj)
+    B, K = 3000, 4
+    q, dq, s, alpha = synthetic.device_batch("iiwa", B, 21, dev, nj, p)
+    status = torch.zeros(B, dtype=torch.uint8, device=dev)
+    ddq_f, s_f = projection.iiwa_substeps(q, dq, s, alpha, p, K, n_ctrl_joints=nj, status=status)
+    ddq_r, s_r = projection.iiwa_substeps(q, dq, s, alpha, p, K, n_ctrl_joints=nj, use_workspace=False)
+    assert torch.equal(ddq_f, ddq_r) and torch.equal(s_f, s_r)
+    ss = s.clone()
+    for kk in range(K):
+        d1, ss = projection.step("iiwa", q, dq, ss, alpha, p, n_ctrl_joints=nj)
+        # the fused kernel carries the slacks in double between the calls, the loop rounds them to fp32
+        diff = ((ddq_f[kk] - d1).abs() / d1.abs().clamp(min=1.0)).max(1).values
+        assert diff.median() < 1e-6 and (diff < 1e-4).float().mean() > 0.99
+    assert ((s_f - ss).abs() / ss.abs().clamp(min=1.0)).median() < 1e-6
+    # against the float64 oracle, on a sample
+    fam = "iiwa%d" % nj
+    spec = helpers.oracle_spec(fam)
+    qn, dqn, sn, an = (t.cpu().numpy().astype(np.float64) for t in (q, dq, s, alpha))
+    worst = 0.0
+    for i in range(0, B, 97):
+        ev = helpers.oracle_eval(fam, qn[i], dqn[i])
+        si = sn[i].copy()
+        for kk in range(K):
+            o = ao.atacom_step(spec, ev, dqn[i], si, an[i], basis="canonical")
+            tr = o["trace"]
+            cand = [pv for (_, _, pv) in tr["pivots"] + tr["dropped"]]
+            if o["rank"] < spec.C or min(abs(pv - spec.tol) / spec.tol for pv in cand) < 1e-3:
+                break
+            worst = max(worst, np.abs(ddq_f[kk, i].cpu().numpy() - o["ddq"]).max() / max(1.0, np.abs(o["w"]).max()))
+            si = o["s_new"]
+        else:
+            worst = max(worst, np.abs(s_f[i].cpu().numpy() - si).max())
+    # later sub-steps see slacks that went through one projection with K_c dt = 1: fp32 output rounding of
+    # sub-step k is an input perturbation of sub-step k + 1
+    assert worst < 2e-5, worst
+    assert ((status & (_lib.ST_NONFINITE | _lib.ST_DENSE_PATH)) == 0).all()
