@@ -127,19 +127,22 @@ struct Dual {
         W[l][n + i] = acc * Ls.get_dyn(LI0 + l);
       }
     }
+    // outer loops rolled (code size), inner loops unrolled (the local-memory loads of a row are in flight together)
     ATACOM_ROLLED
     for (int a = 0; a < NR; ++a) {
-      R wa[M1];
+      R wa[M1], row[NR];
       ATACOM_UNROLL
       for (int l = 0; l < m; ++l) wa[l] = W[l][a];
-      ATACOM_ROLLED
-      for (int b = a; b < NR; ++b) {
-        R acc = (a == b) ? R(1) : R(0);
+      ATACOM_UNROLL
+      for (int b = 0; b < NR; ++b) row[b] = R(0);
+      ATACOM_UNROLL
+      for (int l = 0; l < m; ++l) {
         ATACOM_UNROLL
-        for (int l = 0; l < m; ++l) acc -= wa[l] * W[l][b];
-        Pm[a][b] = acc;
-        Pm[b][a] = acc;
+        for (int b = 0; b < NR; ++b) row[b] -= wa[l] * W[l][b];
       }
+      ATACOM_UNROLL
+      for (int b = 0; b < NR; ++b) Pm[a][b] = row[b];
+      Pm[a][a] += R(1);
     }
     int npiv = 0;
     ATACOM_ROLLED
@@ -162,8 +165,8 @@ struct Dual {
       const R d = sc * sc * Pm[idx][idx];
       if (npiv < k && d > tol * tol && d > R(DUAL_TINY)) {
         const R inv = dual_rsqrt(d);
-        ATACOM_ROLLED
-        for (int a = 0; a < NR; ++a) V[npiv][a] = Pm[a][idx] * sc * inv;
+        ATACOM_UNROLL
+        for (int a = 0; a < NR; ++a) V[npiv][a] = Pm[idx][a] * sc * inv;     // Pm is symmetric: a row, not a column
         ATACOM_ROLLED
         for (int a = 0; a < NR; ++a) {
           const R va = V[npiv][a];
@@ -182,6 +185,97 @@ struct Dual {
     if (npiv < k) status |= ST_RANK_DEFICIENT;
     return status;
   }
+
+#if defined(__CUDACC__)
+  // (7c'), device only: the same procedure run by all 32 lanes of the warp for ONE of its environments (the
+  // "owner"), with the matrices in a small scratch in shared memory — a few microseconds instead of ~70 us for
+  // the serial routine, whose local-memory accesses are one dependent chain (a single such environment would set
+  // the duration of the whole launch).  Every lane of the warp must call it (converged).  Yo / Lo point at the
+  // owner's columns of the [entry][lane] scratch arrays (stride 32); sc holds, filled in by the owner beforehand:
+  // sigma and gamma (COOP_SG0: n + n), the slacks (COOP_S0: G) and alpha (COOP_A0: k).  Returns the status bits
+  // and leaves the owner's w_null (N values) in sc[COOP_WN0 ...].
+  static constexpr int COOP_NR = n + GD;
+  static constexpr int COOP_W0 = 0;                                   // W (m x NR), later V (k x NR)
+  static constexpr int COOP_P0 = (m > k ? m : k) * (n + GD);          // Pm (NR x NR)
+  static constexpr int COOP_WN0 = COOP_P0 + (n + GD) * (n + GD);      // w_null (N)
+  static constexpr int COOP_SG0 = COOP_WN0 + N;                       // sigma (n), gamma (n)
+  static constexpr int COOP_S0 = COOP_SG0 + 2 * n;                    // slacks (G)
+  static constexpr int COOP_A0 = COOP_S0 + G;                         // alpha (k)
+  static constexpr int COOP_DOUBLES = COOP_A0 + k;
+  static_assert(COOP_NR <= 32, "one lane per reduced coordinate");
+  static __device__ __noinline__ uint8_t null_part_general_warp(const volatile R* Yo, const volatile R* Lo, R tol,
+                                                                volatile R* sc) {
+    constexpr int NR = COOP_NR;
+    const int lane = threadIdx.x & 31;
+    uint8_t status = 0;
+    // W = [Y, L^-1 S_d]: the x part element-wise, one dense slack column per lane (forward substitution)
+    for (int e = lane; e < m * n; e += 32) sc[COOP_W0 + (e / n) * NR + (e % n)] = Yo[e * 32];
+    if (lane < GD) {
+      const R si = sc[COOP_S0 + lane];
+      const int c0 = F + lane;
+      for (int l = 0; l < m; ++l) {
+        R acc = R(0);
+        if (l >= c0) {
+          acc = (l == c0) ? si : R(0);
+          for (int p = c0; p < l; ++p) acc -= Lo[lidx(l, p) * 32] * sc[COOP_W0 + p * NR + n + lane];
+          acc *= Lo[(LI0 + l) * 32];
+        }
+        sc[COOP_W0 + l * NR + n + lane] = acc;
+      }
+    }
+    __syncwarp();
+    for (int e = lane; e < NR * NR; e += 32) {          // projector of the reduced coordinates: I - W^T W
+      const int a = e / NR, b = e % NR;
+      R acc = (a == b) ? R(1) : R(0);
+      for (int l = 0; l < m; ++l) acc -= sc[COOP_W0 + l * NR + a] * sc[COOP_W0 + l * NR + b];
+      sc[COOP_P0 + e] = acc;
+    }
+    __syncwarp();
+    R beta[K1];
+    ATACOM_UNROLL
+    for (int l = 0; l < K1; ++l) beta[l] = R(0);
+    int npiv = 0;
+    for (int c = 0; c < N; ++c) {      // uniform control flow: every lane reads the same values, takes the same decisions
+      int idx;
+      R scl;
+      if (c < n) {
+        idx = c;
+        scl = sc[COOP_SG0 + c];
+      } else if (c - n < GD) {
+        idx = c;
+        scl = R(1);
+      } else {
+        idx = c - n - GD;
+        scl = -sc[COOP_SG0 + n + idx];
+      }
+      R part = R(0);
+      ATACOM_UNROLL
+      for (int r = 0; r < k; ++r) part += (r < npiv) ? beta[r] * scl * sc[COOP_W0 + r * NR + idx] : R(0);
+      const R d = scl * scl * sc[COOP_P0 + idx * NR + idx];
+      if (npiv < k && d > tol * tol && d > R(DUAL_TINY)) {
+        const R inv = dual_rsqrt(d);
+        const R al = sc[COOP_A0 + npiv];
+        __syncwarp();                  // everyone has read row npiv of V's storage and the diagonal
+        if (lane < NR) sc[COOP_W0 + npiv * NR + lane] = sc[COOP_P0 + idx * NR + lane] * scl * inv;   // row npiv of V
+        __syncwarp();
+        for (int e = lane; e < NR * NR; e += 32)
+          sc[COOP_P0 + e] -= sc[COOP_W0 + npiv * NR + e / NR] * sc[COOP_W0 + npiv * NR + e % NR];
+        ATACOM_UNROLL
+        for (int l = 0; l < k; ++l) beta[l] = (l == npiv) ? (al - part) * inv : beta[l];
+        if (lane == 0) sc[COOP_WN0 + c] = al;
+        if (c >= n) status |= ST_SLACK_PIVOT;
+        ++npiv;
+        __syncwarp();
+      } else {
+        if (npiv < k) status |= ST_COLUMN_DROPPED;
+        if (lane == 0) sc[COOP_WN0 + c] = part;   // dropped: the rows pivoted before it; untested: every row
+      }
+    }
+    __syncwarp();
+    if (npiv < k) status |= ST_RANK_DEFICIENT;
+    return status;
+  }
+#endif
 
   // (7b) Two pivots missing after the x columns (two active constraints took two directions away from x; k >= 2).
   // The remaining null space is two-dimensional: tau supported on the F + 2 unpivoted columns with B_f tau = 0,
@@ -341,9 +435,11 @@ struct Dual {
   // Y: on entry the m x n dense rows of A (row-major, equalities first), overwritten; Ls: scratch for L.
   // dg: NDIAG diagonal entries, s: G, r: C (rows ordered equality, dense inequality, diagonal
   // inequality), alpha: k.  w_mn (type W), w_null (type R): N each.
+  // defer_general: do not run the general routine here but return ST_DENSE_PATH as a request, with sigma and gamma
+  // in w_null[0 .. 2n) — the caller then runs it with the whole warp (null_part_general_warp) and overwrites w_null.
   template <class YS, class LS, typename W>
   static ATACOM_HD uint8_t project(YS& Y, LS& Ls, const R* dg, const R* s, const R* r, const R* alpha, R tol,
-                                   bool want_null, W* w_mn, R* w_null) {
+                                   bool want_null, W* w_mn, R* w_null, bool defer_general = false) {
     uint8_t status = 0;
 
     // ---- (1) diagonal rows -> coordinates t_j
@@ -589,6 +685,16 @@ struct Dual {
       if (!(st2 & ST_DENSE_PATH)) return st2;     // (a degenerate plane falls through to the general routine)
     }
     if (k - npiv > 1 || F > 1) {
+      if (defer_general) {   // hand sigma and gamma to the caller in w_null (N >= 2 n is the caller's condition)
+        if (N >= 2 * n) {
+          ATACOM_UNROLL
+          for (int j = 0; j < n; ++j) {
+            w_null[j < N ? j : 0] = sig[j];
+            w_null[n + j < N ? n + j : 0] = gam[j];
+          }
+        }
+        return (status & ST_RANK_DEFICIENT) | ST_DENSE_PATH;
+      }
       // private copies: only these (not the register-resident operands of the hot path) get their address taken
       R s2[G1], sg2[n], gm2[n], al2[K1], wn2[N];
       ATACOM_UNROLL

@@ -113,6 +113,11 @@ struct StepArgs {
   uint32_t* peer_flags[ATACOM_MAX_PEERS];   // rank w's flag array [world]
   uint32_t* local_sync;                     // this rank: { blocks done, step sequence number }
   int32_t rank;
+  // ordered admission of the bulk loads (IO mode 1 over mapped host memory): { warps loaded, warps finished,
+  // next block ticket }, all zero between launches; at most gate_window warps have their loads in flight, in
+  // ticket order, so the first blocks compute and store while the last ones are still waiting for PCIe
+  int32_t gate_window;
+  uint32_t* gate;
 };
 
 // ------------------------------------------------------------------ row access
@@ -167,7 +172,8 @@ struct StepScratch {
   static constexpr size_t SCRATCH = SHARED ? sizeof(double) * (DU::Y_SIZE + DU::L_SIZE) * 32 : 0;
   static constexpr size_t STAGE = sizeof(float) * 32 * (3 * ED::n + ED::G);   // q, dq, alpha, s
   static constexpr size_t WARP_BYTES = ((SCRATCH > STAGE ? SCRATCH : STAGE) + 127) / 128 * 128;
-  static constexpr size_t BYTES = WARP_BYTES * MAX_WARPS + sizeof(uint64_t) * MAX_WARPS;   // + one mbarrier per warp
+  static constexpr size_t TICKET_OFFSET = WARP_BYTES * MAX_WARPS + sizeof(uint64_t) * MAX_WARPS;
+  static constexpr size_t BYTES = TICKET_OFFSET + 16;   // + one mbarrier per warp + the block's ticket
   using YS = typename std::conditional<SHARED, SharedStore<double, 32>, LocalStore<double, DU::Y_SIZE>>::type;
   using LS = typename std::conditional<SHARED, SharedStore<double, 32>, LocalStore<double, DU::L_SIZE>>::type;
   static __device__ __forceinline__ YS y(unsigned char* region, int lane) {
@@ -228,7 +234,19 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   using D = typename Env::D;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
-  const int64_t e_raw = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(128) unsigned char atacom_smem[];
+  using SC = StepScratch<Env>;
+  // Block index.  With ordered admission the blocks number themselves in the order they start (a ticket), so a
+  // warp only ever waits for warps of blocks that are already running — no assumption on the dispatch order.
+  unsigned bid = blockIdx.x;
+  const bool gated = IO == 1 && a.gate != nullptr;
+  if (gated) {
+    volatile uint32_t* tk = reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::TICKET_OFFSET);
+    if (threadIdx.x == 0) *tk = atomicAdd(a.gate + 2, 1u);
+    __syncthreads();
+    bid = *tk;
+  }
+  const int64_t e_raw = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
   const bool valid = e_raw < a.B;
   // threads past the end recompute the last environment and discard it, so that every thread of the
   // block reaches the phase barriers inside the projection
@@ -239,8 +257,6 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   // and every lane picks its own rows up from there; any other warp (tail of the batch, unaligned views) has
   // each thread load its rows directly.
   float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
-  extern __shared__ __align__(128) unsigned char atacom_smem[];
-  using SC = StepScratch<Env>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* region = atacom_smem + warp * SC::WARP_BYTES;
   const int64_t wenv0 = e_raw - lane;
@@ -255,6 +271,19 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   float* sa = ss + 32 * G;
   if (bulk && ATACOM_X_BULK_LOAD) {
     if (lane == 0) {
+      if (gated) {
+        // admission: warp number `order` may load once fewer than gate_window warps ahead of it are outstanding
+        const unsigned order = bid * (blockDim.x >> 5) + static_cast<unsigned>(warp);
+        const unsigned window = static_cast<unsigned>(a.gate_window);
+        if (order >= window) {
+          unsigned seen;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gate) : "memory");
+            if (seen + window > order) break;
+            __nanosleep(64);
+          }
+        }
+      }
       mbar_init(bar, 1);
       mbar_expect_tx(bar, 4u * 32u * static_cast<uint32_t>(2 * n + G + na));
       bulk_g2s(sq, a.q + wenv0 * n, 128u * n, bar);
@@ -264,6 +293,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     }
     __syncwarp();
     mbar_wait(bar, 0);
+    if (gated && lane == 0) atomicAdd(a.gate, 1u);     // this warp's inputs have landed: admit the next one
 #pragma unroll
     for (int j = 0; j < n; ++j) {
       q[j] = sq[lane * n + j];
@@ -274,6 +304,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     for (int i = 0; i < G; ++i) s[i] = ss[lane * G1 + i];
     __syncwarp();     // the region is scratch from here on
   } else {
+    if (gated && lane == 0) atomicAdd(a.gate, 1u);     // direct loads (tail, unaligned views) are not rationed
     // s and alpha are not needed before the projection: in mode 3 the bulk-copy engine brings the warp's two
     // slabs into the (still idle) L part of its region while the kinematics run on q and dq
     if (IO == 3 && G > 0) {
@@ -334,7 +365,9 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   unsigned tid2;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid2));
   const int lane2 = tid2 & 31;
-  const int64_t e2 = static_cast<int64_t>(blockIdx.x) * blockDim.x + tid2;
+  unsigned bid2 = blockIdx.x;
+  if (IO == 1 && a.gate != nullptr) bid2 = *reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::TICKET_OFFSET);
+  const int64_t e2 = static_cast<int64_t>(bid2) * blockDim.x + tid2;
   const int64_t wenv2 = e2 - lane2;
   if (e2 < a.B && a.status) a.status[e2] = st;
   if ((IO == 1 || IO == 2) && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
@@ -359,6 +392,15 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     if (a.ddq) row_store<n>(a.ddq, e2, ddq);
     if (G > 0) row_store<G1>(a.s_out, e2, so);
     for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e2, ddq);
+  }
+  // Ordered admission: the last warp of the launch (every ticket taken, every gate passed) zeroes the counters.
+  if (IO == 1 && a.gate != nullptr && lane2 == 0) {
+    const unsigned done = atomicAdd(a.gate + 1, 1u);
+    if (done == gridDim.x * (blockDim.x >> 5) - 1u) {
+      atomicExch(a.gate, 0u);
+      atomicExch(a.gate + 2, 0u);
+      atomicExch(a.gate + 1, 0u);
+    }
   }
   // Fused gather, cross-rank barrier: the last block of this launch publishes the step to every rank and waits
   // for every rank's flag of the same step, so kernel completion on a rank means its gather buffer is complete.
@@ -956,7 +998,8 @@ template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : ATACOM_STEP_DEVI
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
                 float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0,
-                uint32_t* const* peer_flags = nullptr, uint32_t* local_sync = nullptr, int rank = 0) {
+                uint32_t* const* peer_flags = nullptr, uint32_t* local_sync = nullptr, int rank = 0,
+                uint32_t* gate = nullptr, int gate_window = 0) {
   int rc = check_common(B, p);
   if (rc) return rc;
   using D = typename Env::D;
@@ -965,7 +1008,11 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   if (!q || !dq || (!ddq && n_peers == 0) || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
-  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0, {}, nullptr, rank};
+  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0, {}, nullptr, rank, 0, nullptr};
+  if (IO == 1 && gate != nullptr && gate_window > 0) {
+    a.gate = gate;
+    a.gate_window = gate_window;
+  }
   if (local_sync) {
     if (!peer_flags || n_peers < 1 || rank < 0 || rank >= n_peers) return ATACOM_ERR_BAD_PARAM;
     for (int w = 0; w < n_peers; ++w) {
@@ -1430,6 +1477,9 @@ struct AtacomHostCtx {
   int key_n, key_launches;
   AtacomParams key_params;
   int mode;
+  // zero-copy path: counters of the ordered admission of the bulk loads and the number of warps admitted at once
+  uint32_t* gate;
+  int zc_window;
 };
 
 // Device-visible alias of a page-locked, mapped host pointer (nullptr if it is not one).
@@ -1493,7 +1543,12 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   bool ok = cudaMalloc(&c->q, q_bytes) == cudaSuccess && cudaMalloc(&c->dq, q_bytes) == cudaSuccess &&
             cudaMalloc(&c->alpha, q_bytes) == cudaSuccess && cudaMalloc(&c->ddq, q_bytes) == cudaSuccess &&
             cudaMalloc(&c->s_in, g_bytes) == cudaSuccess && cudaMalloc(&c->s_out, g_bytes) == cudaSuccess &&
-            cudaMalloc(&c->status, max_B) == cudaSuccess;
+            cudaMalloc(&c->status, max_B) == cudaSuccess && cudaMalloc(&c->gate, 16) == cudaSuccess &&
+            cudaMemset(c->gate, 0, 16) == cudaSuccess;
+  // 128 warps = 448 KB of reads in flight: enough to keep PCIe busy, few enough that the loads arrive block after
+  // block (measured sweep in DESIGN.md section 6).  ATACOM_ZC_WINDOW overrides; 0 = all loads at once.
+  c->zc_window = 128;
+  if (const char* f = getenv("ATACOM_ZC_WINDOW")) c->zc_window = atoi(f) > 0 ? atoi(f) : 0;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
   ok = ok && configure_step_kernel<IiwaEnv<6>, ATACOM_STEP_DEVICE_IO>() &&
@@ -1529,7 +1584,7 @@ int atacom_host_ctx_destroy(AtacomHostCtx* c) {
   if (!c) return ATACOM_OK;
   if (c->exec) cudaGraphExecDestroy(c->exec);
   cudaFree(c->q); cudaFree(c->dq); cudaFree(c->alpha); cudaFree(c->ddq);
-  cudaFree(c->s_in); cudaFree(c->s_out); cudaFree(c->status);
+  cudaFree(c->s_in); cudaFree(c->s_out); cudaFree(c->status); cudaFree(c->gate);
   for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->streams[i]);
   cudaEventDestroy(c->fork);
   for (int i = 0; i < 4; ++i) cudaEventDestroy(c->join[i]);
@@ -1569,8 +1624,10 @@ int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* 
     float *zddq = static_cast<float*>(d[4]), *zso = static_cast<float*>(d[5]);
     uint8_t* zst = static_cast<uint8_t*>(d[6]);
     constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
-    rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0])
-                : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0]);
+    rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0],
+                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window)
+                : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0],
+                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window);
     if (rc != ATACOM_OK) return rc;
     if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;

@@ -279,6 +279,32 @@ def test_host_buffer_entry_point(cuda_device, mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("window", ["0", "3", "192"])
+@pytest.mark.parametrize("n", [6, 7])
+def test_zero_copy_ordered_admission(cuda_device, monkeypatch, window, n):
+    """Zero-copy host path with the bulk loads admitted `window` warps at a time in ticket order (0: all at once):
+    bit-identical to the device-resident call, status included, on one wave (65 536 environments), on several waves
+    (150 001 — blocks that start late only ever wait for blocks already running) and on repeated launches (the
+    last warp of a launch re-arms the counters)."""
+    monkeypatch.setenv("ATACOM_ZC_WINDOW", window)
+    p = _lib.default_params("iiwa", n)
+    for B in (65536, 150001):
+        q, dq, s, alpha = synthetic.device_batch("iiwa", B, 91, cuda_device, n, p)
+        st = torch.zeros(B, dtype=torch.uint8, device=cuda_device)
+        ddq, s_out = projection.step("iiwa", q, dq, s, alpha, p, n_ctrl_joints=n, status=st)
+        ctx = projection.HostContext(B, chunks=1, mode="zero_copy")
+        h = [t.cpu().pin_memory() for t in (q, dq, s, alpha)]
+        ddq_h = torch.empty(B, n).pin_memory()
+        s_h = torch.empty(B, 5 + n).pin_memory()
+        st_h = torch.zeros(B, dtype=torch.uint8).pin_memory()
+        for rep in range(3):
+            ddq_h.zero_()
+            s_h.zero_()
+            ctx.iiwa_step(n, *h, ddq_h, s_h, p, status=st_h)
+            assert torch.equal(ddq_h, ddq.cpu()) and torch.equal(s_h, s_out.cpu()) and torch.equal(st_h, st.cpu())
+        ctx.close()
+
+
 def test_multi_wave_batch_and_nonfinite_inputs(cuda_device):
     """A batch of several waves of blocks (300 001 environments: 670 blocks of 448 on 148 SMs) is bit-identical to
     its pieces; a non-finite input row is flagged ST_NONFINITE and does not disturb its neighbours."""

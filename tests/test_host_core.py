@@ -189,7 +189,7 @@ def test_point_reach_vs_oracle_and_golden(harness, golden):
 
 
 @pytest.mark.parametrize("family", ["circle", "planar", "iiwa6", "iiwa7"])
-@pytest.mark.parametrize("case", ["one_zero", "one_tiny", "two_zero", "two_small", "all_large"])
+@pytest.mark.parametrize("case", ["one_zero", "one_tiny", "two_zero", "two_small", "three_zero", "all_large"])
 def test_dual_projection_edge_cases(harness, family, case):
     """The dual path (atacom_dual.cuh) of the step kernels at the corners of its domain: an exactly active
     constraint (s_i = 0, what reset produces for a violated constraint, atacom.py:145-149), a nearly active one
@@ -203,9 +203,9 @@ def test_dual_projection_edge_cases(harness, family, case):
         if case == "all_large":
             s[i] = np.maximum(s[i], 0.5)
         else:
-            k_ = 2 if case.startswith("two") and G >= 2 else 1
+            k_ = 2 if case.startswith("two") and G >= 2 else (3 if case.startswith("three") and G >= 3 else 1)
             idx = rng.choice(G, k_, replace=False)
-            s[i, idx] = {"one_zero": 0.0, "one_tiny": 1e-7, "two_zero": 0.0, "two_small": 0.01}[case]
+            s[i, idx] = {"one_zero": 0.0, "one_tiny": 1e-7, "two_zero": 0.0, "two_small": 0.01, "three_zero": 0.0}[case]
     q, dq, alpha = (a.astype(np.float64) for a in (q, dq, alpha))
     ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
     pf = helpers.exact_params_flat(family, _params(family))
