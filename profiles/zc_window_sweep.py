@@ -1,4 +1,5 @@
-"""Zero-copy host path: sweep of the admission window (ATACOM_ZC_WINDOW, warps whose bulk loads may be in flight).
+"""Zero-copy host path: sweep of the admission window (ATACOM_ZC_WINDOW, warps whose bulk loads may be in flight)
+and of the block size of the launch (ATACOM_ZC_TPB, 0 = the device path's choice).
 
 Run on a GPU box:  python profiles/zc_window_sweep.py [B] > gpurun_out/zc_sweep.log
 Every setting is checked bit for bit against the device-buffer path (status included), then timed by wall clock
@@ -18,8 +19,11 @@ for n in (6, 7):
     host = [t.cpu().pin_memory() for t in (q, dq, s, alpha)]
     ddq_h = torch.empty(B, n).pin_memory()
     s_h = torch.empty(B, 5 + n).pin_memory()
-    for window in (0, 32, 64, 96, 128, 192, 256, 384, 512, 1024):
+    combos = [(w, 0) for w in (0, 32, 64, 96, 128, 192, 256, 384, 512, 1024)]
+    combos += [(w, t) for t in (224, 128, 64) for w in (64, 128, 256)]      # smaller blocks: shorter tail
+    for window, tpb in combos:
         os.environ["ATACOM_ZC_WINDOW"] = str(window)
+        os.environ["ATACOM_ZC_TPB"] = str(tpb)
         ctx = projection.HostContext(B, chunks=1, mode="zero_copy")
         ddq_h.zero_(); s_h.zero_()
         f = lambda: ctx.iiwa_step(n, *host, ddq_h, s_h, p)
@@ -36,6 +40,6 @@ for n in (6, 7):
             best = min(best, dt)
             tot += dt
         ok2 = torch.equal(ddq_h, ref[0].cpu()) and torch.equal(s_h, ref[1].cpu())
-        print("n=%d B=%d window %4d: mean %.1f us, best %.1f us -> %.1f M env-steps/s  bit-identical to device path: %s"
-              % (n, B, window, tot / 5 * 1e6, best * 1e6, B / best / 1e6, ok and ok2), flush=True)
+        print("n=%d B=%d window %4d block %3d: mean %.1f us, best %.1f us -> %.1f M env-steps/s  bit-identical to device path: %s"
+              % (n, B, window, tpb, tot / 5 * 1e6, best * 1e6, B / best / 1e6, ok and ok2), flush=True)
         ctx.close()

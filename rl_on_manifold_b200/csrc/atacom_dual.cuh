@@ -56,6 +56,21 @@ ATACOM_HD R dual_rsqrt(R x) {
   return R(1) / ::sqrt(x);
 #endif
 }
+// The same over the whole double range (the slack-pivot phases form 1 / |s_i| ~ 1e12 for an exactly active
+// constraint, and Gram determinants of such entries: 1e48 and beyond): the seed is MUFU.RSQ64H (~2^-20).
+template <typename R>
+ATACOM_HD R dual_rsqrt_wide(R x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(static_cast<double>(x)));
+  const double e = ::fma(-static_cast<double>(x) * y, y, 1.0);      // ~ 1e-6
+  y = ::fma(y, ::fma(0.375, e, 0.5) * e, y);                        // error O(e^3)
+  const double e2 = ::fma(-static_cast<double>(x) * y, y, 1.0);
+  return static_cast<R>(::fma(y, 0.5 * e2, y));
+#else
+  return R(1) / ::sqrt(x);
+#endif
+}
 constexpr double DUAL_TINY = 1e-24;   // floor of every rsqrt argument: squares of fp32 data below it are zero here
 
 // Per-environment scratch of the dual projection.  LocalStore: a plain array (registers / local
@@ -85,6 +100,13 @@ struct SharedStore {
   ATACOM_HD void set(int i, R x) { *static_cast<volatile R*>(base + i * STRIDE) = x; }
   ATACOM_HD R get_dyn(int i) const { return *static_cast<const volatile R*>(base + i * STRIDE); }
 };
+
+template <class S> struct is_shared_store { static constexpr bool value = false; };
+template <typename R, int STRIDE> struct is_shared_store<SharedStore<R, STRIDE>> { static constexpr bool value = true; };
+template <typename R, int STRIDE>
+ATACOM_HD R* shared_base(const SharedStore<R, STRIDE>& s) { return s.base; }
+template <typename R, int SIZE>
+ATACOM_HD R* shared_base(LocalStore<R, SIZE>&) { return nullptr; }
 
 template <typename R, class D, int NDIAG>
 struct Dual {
@@ -277,6 +299,27 @@ struct Dual {
   }
 #endif
 
+  // The serial general routine for a thread whose project<true>() call returned the request (sigma and gamma in
+  // w_null[0 .. 2n)): what the caller runs when too many lanes of its warp ask at once for the warp-cooperative
+  // routine to pay off.
+  template <class YS, class LS>
+  static ATACOM_HD uint8_t general_from_deferred(YS& Y, LS& Ls, const R* s, const R* alpha, R tol, R* w_null) {
+    R s2[G1], sg2[n], gm2[n], al2[K1], wn2[N];
+    ATACOM_UNROLL
+    for (int i = 0; i < G; ++i) s2[i] = s[i];
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) {
+      sg2[j] = w_null[j < N ? j : 0];
+      gm2[j] = w_null[n + j < N ? n + j : 0];
+    }
+    ATACOM_UNROLL
+    for (int l = 0; l < k; ++l) al2[l] = alpha[l];
+    const uint8_t st2 = null_part_general(Y, Ls, s2, sg2, gm2, al2, tol, wn2);
+    ATACOM_UNROLL
+    for (int i = 0; i < N; ++i) w_null[i] = wn2[i];
+    return st2;
+  }
+
   // (7b) Two pivots missing after the x columns (two active constraints took two directions away from x; k >= 2).
   // The remaining null space is two-dimensional: tau supported on the F + 2 unpivoted columns with B_f tau = 0,
   // spanned by tau1, tau2; the full vectors are n_j = (sigma tau_j, -gamma tau_j, -(B tau_j) / s) with Gram matrix
@@ -332,7 +375,7 @@ struct Dual {
       if (i < GD) {
         const int ri = F + (i < GD ? i : 0);
         const R lii = Ls.get(LI0 + ri);
-        const R dii = (lii > R(0)) ? dual_rsqrt(lii * lii) : R(0);   // L[ri][ri] = 1 / li
+        const R dii = (lii > R(0)) ? dual_rsqrt_wide(lii * lii) : R(0);   // L[ri][ri] = 1 / li
         R an = ya[ri] * dii, bn = yb[ri] * dii;
         ATACOM_UNROLL
         for (int l = 0; l < ri; ++l) {
@@ -365,7 +408,7 @@ struct Dual {
       }
     }
     if (!(det > R(DUAL_TINY))) return status | ST_DENSE_PATH;
-    const R rd = dual_rsqrt(det);
+    const R rd = dual_rsqrt_wide(det);
     const R idet = rd * rd;
     // first pivot: the first slack column whose component in the plane exceeds tol:
     // |a_i n_2 - b_i n_1|^2 / det > tol^2
@@ -397,7 +440,7 @@ struct Dual {
       vd += V[p] * d;
       ud += U[p] * d;
     }
-    const R rn = dual_rsqrt(nrm2 > R(DUAL_TINY) ? nrm2 : R(DUAL_TINY));
+    const R rn = dual_rsqrt_wide(nrm2 > R(DUAL_TINY) ? nrm2 : R(DUAL_TINY));
     const R ip1 = rn * (det * rd);                 // 1 / p1 = sqrt(det) / |d|
     const R k1 = vd * idet * ip1, k2 = -ud * idet * ip1;
     int i2 = G;
@@ -422,7 +465,7 @@ struct Dual {
       al2 = (l == npiv + 1) ? alpha[l] : al2;
     }
     const R bt1 = (al1 - z1) * ip1;
-    const R rf = dual_rsqrt(f2 * f2);
+    const R rf = dual_rsqrt_wide(f2 * f2);
     const R bt2 = (al2 - z2 - bt1 * q12) * (f2 * rf * rf);   // / f2: beta of the second row times the sign of its pivot
     ATACOM_UNROLL
     for (int i = 0; i < G; ++i) {
@@ -437,9 +480,9 @@ struct Dual {
   // inequality), alpha: k.  w_mn (type W), w_null (type R): N each.
   // defer_general: do not run the general routine here but return ST_DENSE_PATH as a request, with sigma and gamma
   // in w_null[0 .. 2n) — the caller then runs it with the whole warp (null_part_general_warp) and overwrites w_null.
-  template <class YS, class LS, typename W>
+  template <bool defer_general = false, class YS, class LS, typename W>
   static ATACOM_HD uint8_t project(YS& Y, LS& Ls, const R* dg, const R* s, const R* r, const R* alpha, R tol,
-                                   bool want_null, W* w_mn, R* w_null, bool defer_general = false) {
+                                   bool want_null, W* w_mn, R* w_null) {
     uint8_t status = 0;
 
     // ---- (1) diagonal rows -> coordinates t_j
@@ -685,7 +728,7 @@ struct Dual {
       if (!(st2 & ST_DENSE_PATH)) return st2;     // (a degenerate plane falls through to the general routine)
     }
     if (k - npiv > 1 || F > 1) {
-      if (defer_general) {   // hand sigma and gamma to the caller in w_null (N >= 2 n is the caller's condition)
+      if constexpr (defer_general) {   // hand sigma and gamma to the caller in w_null (N >= 2 n is the caller's condition)
         if (N >= 2 * n) {
           ATACOM_UNROLL
           for (int j = 0; j < n; ++j) {
@@ -694,7 +737,7 @@ struct Dual {
           }
         }
         return (status & ST_RANK_DEFICIENT) | ST_DENSE_PATH;
-      }
+      } else {
       // private copies: only these (not the register-resident operands of the hot path) get their address taken
       R s2[G1], sg2[n], gm2[n], al2[K1], wn2[N];
       ATACOM_UNROLL
@@ -710,6 +753,7 @@ struct Dual {
       ATACOM_UNROLL
       for (int i = 0; i < N; ++i) w_null[i] = wn2[i];
       return (status & ST_RANK_DEFICIENT) | st2;
+      }
     }
     // remaining null direction in the free coordinates: tau supported on the unpivoted columns with
     // B_f tau = 0; its entries are x_j = sigma_j tau_j, z_diag,j = -gamma_j tau_j, z_dense,i = -(b_i . tau) / s_i.
@@ -740,7 +784,7 @@ struct Dual {
       if (i < GD) {
         const int ri = F + (i < GD ? i : 0);
         const R lii = Ls.get(LI0 + ri);
-        R an = (lii > R(0)) ? yt[ri] * dual_rsqrt(lii * lii) : R(0);   // L[ri][ri] = 1 / li
+        R an = (lii > R(0)) ? yt[ri] * dual_rsqrt_wide(lii * lii) : R(0);   // L[ri][ri] = 1 / li
         ATACOM_UNROLL
         for (int l = 0; l < ri; ++l) an += Ls.get(lidx(ri, l)) * yt[l];
         const R s2 = s[i] * s[i];
@@ -752,7 +796,7 @@ struct Dual {
         e[i] = -gam[j] * ((j == u1) ? t1 : ((F == 1 && j == u2) ? t2 : R(0)));   // sigma^2 + gamma^2 = 1: already in nrm2
       }
     }
-    const R rn = dual_rsqrt(nrm2);
+    const R rn = dual_rsqrt_wide(nrm2);
     int ip = G;
     ATACOM_UNROLL
     for (int i = G - 1; i >= 0; --i) {
@@ -770,7 +814,7 @@ struct Dual {
     }
     ATACOM_UNROLL
     for (int l = 0; l < k; ++l) al = (l == npiv) ? alpha[l] : al;
-    const R ri = dual_rsqrt(ep * ep);
+    const R ri = dual_rsqrt_wide(ep * ep);
     const R bl = (al - zp) * (ep * ri * ri);   // (al - zp) / ep: beta of the new row times the sign of its pivot entry
     ATACOM_UNROLL
     for (int i = 0; i < G; ++i) {

@@ -438,6 +438,10 @@ ATACOM_HD uint8_t step_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP,
   return st;
 }
 
+#ifndef ATACOM_COOP_MAX_LANES      // more asking lanes than this in one warp: each runs the serial general routine
+#define ATACOM_COOP_MAX_LANES 6
+#endif
+
 // Gains the dual path multiplies in HP, converted and combined once on the host side of the launch:
 //   r_i = psi_i + K_c,i c_i  with  psi_i = (J dq)_i + K_i b_i,  c_i = c_i(q) + K_i (J dq)_i [+ s_i^2 / 2]
 //       = K_c,i c_i(q) + wJ_i (J dq)_i + wb_i b_i [+ K_c,i s_i^2 / 2]      (constraints.py:33-43, atacom.py:181,195)
@@ -526,7 +530,10 @@ struct DualSink {
 // sh the current slacks.  s_new = s + dt w_z in HP (atacom.py:135); ddq clipped (atacom.py:117-121).
 template <class Env, typename T, typename HP, class YS, class LS>
 ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const HP* dg, const HP* r,
-                            const HP* sh, const T* alpha, const T* dq, T* ddq, HP* s_new, T* w_dbg) {
+                            const HP* sh, const T* alpha, const T* dq, T* ddq, HP* s_new, T* w_dbg,
+                            HP* coop = nullptr, int coop_slots = 1, int coop_stride = 0) {
+  // coop: the first of the block's coop_slots scratch slots (coop_stride doubles apart) of the warp-cooperative
+  // general routine, on the device when Y and L live in shared memory
   using D = typename Env::D;
   constexpr int NDIAG = Env::NDIAG;
   constexpr int n = D::n, G = D::G, N = D::N, k = D::k;
@@ -536,7 +543,59 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
   T w_mn[N];
   HP w_null[N];
+#if defined(__CUDA_ARCH__)
+  // Three or more constraints active at once (the general null-space routine): with Y and L in shared memory the
+  // thread only asks for it, and the warp then decides.  Few askers (the realistic case: a handful of environments
+  // of a 65 536 batch): all 32 lanes run the routine together for each asking lane in turn, a few microseconds
+  // each — run serially by its thread it takes ~70 us, and a single such environment would set the duration of the
+  // whole launch.  Many askers: each runs the serial routine, all at once.  The warp is converged here (threads
+  // past the end of the batch recompute the last environment); a scratch slot is shared by the warps that map to
+  // it under the lock stored behind it.
+  constexpr bool COOP = is_shared_store<YS>::value && N >= 2 * n;
+  uint8_t st = Dual<HP, D, NDIAG>::template project<COOP>(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null);
+  if constexpr (COOP) {
+    using DU = Dual<HP, D, NDIAG>;
+    unsigned pend = __ballot_sync(0xffffffffu, (st & ST_DENSE_PATH) != 0);
+    if (pend != 0u && (coop == nullptr || __popc(pend) > ATACOM_COOP_MAX_LANES)) {
+      if (st & ST_DENSE_PATH) st = (st & ST_RANK_DEFICIENT) | DU::general_from_deferred(Y, Ls, sh, ah, Kd.tol, w_null);
+    } else if (pend != 0u) {
+      const int lane = static_cast<int>(threadIdx.x & 31u);
+      HP* slot = coop + static_cast<int>((threadIdx.x >> 5) % static_cast<unsigned>(coop_slots)) * coop_stride;
+      volatile HP* sc = slot;
+      unsigned* lock = reinterpret_cast<unsigned*>(slot + DU::COOP_DOUBLES);
+      if (lane == 0) {
+        while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(200);
+      }
+      __syncwarp();
+      __threadfence_block();
+      while (pend != 0u) {
+        const int owner = __ffs(pend) - 1;
+        pend &= pend - 1u;
+        if (lane == owner) {
+          ATACOM_UNROLL
+          for (int j = 0; j < 2 * n; ++j) sc[DU::COOP_SG0 + j] = w_null[j < N ? j : 0];
+          ATACOM_UNROLL
+          for (int i = 0; i < G; ++i) sc[DU::COOP_S0 + i] = sh[i];
+          ATACOM_UNROLL
+          for (int l = 0; l < k; ++l) sc[DU::COOP_A0 + l] = ah[l];
+        }
+        __syncwarp();
+        const uint8_t st2 = DU::null_part_general_warp(shared_base(Y) - lane + owner, shared_base(Ls) - lane + owner,
+                                                       Kd.tol, sc);
+        if (lane == owner) {
+          st = (st & ST_RANK_DEFICIENT) | st2;
+          ATACOM_UNROLL
+          for (int i = 0; i < N; ++i) w_null[i] = sc[DU::COOP_WN0 + i];
+        }
+        __syncwarp();
+      }
+      __threadfence_block();
+      if (lane == 0) atomicExch(lock, 0u);
+    }
+  }
+#else
   uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null);
+#endif
   if (st & ST_DENSE_PATH) return st;
   if (ec) {
     ATACOM_UNROLL
@@ -579,7 +638,8 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
 
 template <class Env, typename T, typename HP, class YS, class LS, class Fetch>
 ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q,
-                                 const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg) {
+                                 const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg, HP* coop = nullptr,
+                                 int coop_slots = 1, int coop_stride = 0) {
   using D = typename Env::D;
   constexpr int NDIAG = Env::NDIAG;
   constexpr int n = D::n, G = D::G;
@@ -591,7 +651,8 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   sink.add_slack_terms(sh);
-  const uint8_t st = dual_tail<Env, T, HP>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg);
+  const uint8_t st = dual_tail<Env, T, HP>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg, coop, coop_slots,
+                                           coop_stride);
   if (st & ST_DENSE_PATH) return st;
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);

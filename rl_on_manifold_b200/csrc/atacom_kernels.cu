@@ -172,8 +172,35 @@ struct StepScratch {
   static constexpr size_t SCRATCH = SHARED ? sizeof(double) * (DU::Y_SIZE + DU::L_SIZE) * 32 : 0;
   static constexpr size_t STAGE = sizeof(float) * 32 * (3 * ED::n + ED::G);   // q, dq, alpha, s
   static constexpr size_t WARP_BYTES = ((SCRATCH > STAGE ? SCRATCH : STAGE) + 127) / 128 * 128;
-  static constexpr size_t TICKET_OFFSET = WARP_BYTES * MAX_WARPS + sizeof(uint64_t) * MAX_WARPS;
-  static constexpr size_t BYTES = TICKET_OFFSET + 16;   // + one mbarrier per warp + the block's ticket
+  // Layout: a fixed header — the block's ticket, (iiwa) the scratch slots of the warp-cooperative general
+  // null-space routine (Dual::null_part_general_warp), each followed by its lock, one mbarrier per warp — then the
+  // regions of the warps the block actually has: a launch with smaller blocks asks for less and more blocks fit an
+  // SM.  As many slots as fit next to a full-size block (warp w uses slot w mod COOP_SLOTS): one per warp for
+  // iiwa-6, two for iiwa-7; the 448-thread blocks take the 228 KB carve-out either way.
+  static constexpr size_t SMEM_MAX = 227 * 1024;
+  static constexpr size_t TICKET_OFFSET = 0;
+  static constexpr size_t COOP_OFFSET = 16;
+  static constexpr size_t COOP_SLOT_BYTES = (sizeof(double) * DU::COOP_DOUBLES + 16 + 15) / 16 * 16;
+  static constexpr size_t COOP_SPARE = SMEM_MAX - 128 - COOP_OFFSET - sizeof(uint64_t) * MAX_WARPS - WARP_BYTES * MAX_WARPS;
+  static constexpr int COOP_SLOTS = !SHARED ? 0 : (COOP_SPARE / COOP_SLOT_BYTES >= size_t(MAX_WARPS) ? MAX_WARPS
+                                                   : static_cast<int>(COOP_SPARE / COOP_SLOT_BYTES));
+  static_assert(!SHARED || COOP_SLOTS >= 1, "no room for the cooperative scratch next to a full-size block");
+  static constexpr size_t BAR_OFFSET = COOP_OFFSET + COOP_SLOT_BYTES * COOP_SLOTS;
+  static constexpr size_t HEAD = (BAR_OFFSET + sizeof(uint64_t) * MAX_WARPS + 127) / 128 * 128;
+  static constexpr size_t BYTES = HEAD + WARP_BYTES * MAX_WARPS;
+  static_assert(BYTES <= SMEM_MAX, "step kernel scratch exceeds the shared memory of an SM");
+  static constexpr size_t bytes(int tpb) { return HEAD + WARP_BYTES * static_cast<size_t>((tpb + 31) / 32); }
+  static __device__ __forceinline__ unsigned char* region(unsigned char* smem, int warp) {
+    return smem + HEAD + warp * WARP_BYTES;
+  }
+  static constexpr int COOP_STRIDE = static_cast<int>(COOP_SLOT_BYTES / sizeof(double));
+  static __device__ __forceinline__ double* coop(unsigned char* smem) {     // slot 0
+    return SHARED ? reinterpret_cast<double*>(smem + COOP_OFFSET) : nullptr;
+  }
+  static __device__ __forceinline__ void coop_init(unsigned char* smem) {   // one thread, before a block barrier
+    for (int i = 0; i < COOP_SLOTS; ++i)
+      *reinterpret_cast<volatile unsigned*>(smem + COOP_OFFSET + i * COOP_SLOT_BYTES + sizeof(double) * DU::COOP_DOUBLES) = 0u;
+  }
   using YS = typename std::conditional<SHARED, SharedStore<double, 32>, LocalStore<double, DU::Y_SIZE>>::type;
   using LS = typename std::conditional<SHARED, SharedStore<double, 32>, LocalStore<double, DU::L_SIZE>>::type;
   static __device__ __forceinline__ YS y(unsigned char* region, int lane) {
@@ -240,12 +267,13 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   // warp only ever waits for warps of blocks that are already running — no assumption on the dispatch order.
   unsigned bid = blockIdx.x;
   const bool gated = IO == 1 && a.gate != nullptr;
-  if (gated) {
-    volatile uint32_t* tk = reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::TICKET_OFFSET);
-    if (threadIdx.x == 0) *tk = atomicAdd(a.gate + 2, 1u);
-    __syncthreads();
-    bid = *tk;
+  volatile uint32_t* tk = reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::TICKET_OFFSET);
+  if (threadIdx.x == 0) {
+    SC::coop_init(atacom_smem);
+    if (gated) *tk = atomicAdd(a.gate + 2, 1u);
   }
+  if (SC::SHARED || gated) __syncthreads();     // the only block barrier of the kernel, before any work
+  if (gated) bid = *tk;
   const int64_t e_raw = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
   const bool valid = e_raw < a.B;
   // threads past the end recompute the last environment and discard it, so that every thread of the
@@ -258,10 +286,10 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   // each thread load its rows directly.
   float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* region = atacom_smem + warp * SC::WARP_BYTES;
+  unsigned char* region = SC::region(atacom_smem, warp);
   const int64_t wenv0 = e_raw - lane;
   const int na = ec ? n : k;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(atacom_smem + SC::MAX_WARPS * SC::WARP_BYTES) + warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(atacom_smem + SC::BAR_OFFSET) + warp;
   const bool bulk = IO == 1 && a.aligned16 && (wenv0 + 32 <= a.B);
   bool lazy = false;
   float* lz = reinterpret_cast<float*>(region + (SC::SHARED ? sizeof(double) * SC::DU::Y_SIZE * 32 : 0));
@@ -353,7 +381,8 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < n; ++j) a_row[j] = al[j];
   };
-  const uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg);
+  const uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg, SC::coop(atacom_smem),
+                                                                SC::COOP_SLOTS, SC::COOP_STRIDE);
 #else
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
@@ -371,7 +400,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   const int64_t wenv2 = e2 - lane2;
   if (e2 < a.B && a.status) a.status[e2] = st;
   if ((IO == 1 || IO == 2) && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
-    float* oq = reinterpret_cast<float*>(atacom_smem + (tid2 >> 5) * SC::WARP_BYTES);
+    float* oq = reinterpret_cast<float*>(SC::region(atacom_smem, static_cast<int>(tid2 >> 5)));
     float* os = oq + 32 * n;
     __syncwarp();     // every lane is done with its scratch
 #pragma unroll
@@ -462,9 +491,13 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_substeps_kernel(const __
   const bool ec = P.variant == VARIANT_EC;
   extern __shared__ __align__(128) unsigned char atacom_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* region = atacom_smem + warp * SC::WARP_BYTES;
+  unsigned char* region = SC::region(atacom_smem, warp);
   typename SC::YS Ys = SC::y(region, lane);
   typename SC::LS Ls = SC::l(region, lane);
+  if (SC::SHARED) {
+    if (threadIdx.x == 0) SC::coop_init(atacom_smem);
+    __syncthreads();
+  }
 
   // what stays live across the sub-steps is kept small on purpose (slacks, dq, alpha): shared memory takes
   // 204 of the SM's 256 KB, so a register spill inside the loop would go all the way to L2
@@ -517,7 +550,8 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_substeps_kernel(const __
 #pragma unroll
     for (int i = F; i < C; ++i) r[i] += 0.5 * Kd.K_c[i] * sh[i - F] * sh[i - F];      // atacom.py:195
     float ddq[n];
-    const uint8_t st = dual_tail<Env, float, double>(P, Kd, Ys, Ls, dg, r, sh, al, dq, ddq, sn, nullptr);
+    const uint8_t st = dual_tail<Env, float, double>(P, Kd, Ys, Ls, dg, r, sh, al, dq, ddq, sn, nullptr,
+                                                     SC::coop(atacom_smem), SC::COOP_SLOTS, SC::COOP_STRIDE);
     status |= st;
 #pragma unroll
     for (int i = 0; i < G; ++i) sh[i] = sn[i];
@@ -999,7 +1033,7 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
                 float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0,
                 uint32_t* const* peer_flags = nullptr, uint32_t* local_sync = nullptr, int rank = 0,
-                uint32_t* gate = nullptr, int gate_window = 0) {
+                uint32_t* gate = nullptr, int gate_window = 0, int tpb_override = 0) {
   int rc = check_common(B, p);
   if (rc) return rc;
   using D = typename Env::D;
@@ -1029,9 +1063,9 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     bits |= reinterpret_cast<uintptr_t>(peers[w]) | static_cast<uintptr_t>((gather_row0 * D::n * 4) & 15);
   }
   a.aligned16 = (bits & 15) == 0;
-  const int tpb = step_block_size(B);
+  const int tpb = (tpb_override >= 32 && tpb_override <= STEP_MAX_TPB) ? tpb_override / 32 * 32 : step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
-  constexpr size_t smem = StepScratch<Env>::BYTES;
+  const size_t smem = StepScratch<Env>::bytes(tpb);
   if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
   atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
       a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
@@ -1060,7 +1094,7 @@ int launch_substeps(const SubstepArgs& a, const ParamsT<float>& P, unsigned grid
                                static_cast<int>(StepScratch<Env>::BYTES)) == cudaSuccess ? 1 : -1;
   if (cfg < 0) return ATACOM_ERR_CUDA;
   using D = typename Env::D;
-  atacom_substeps_kernel<Env, PARK><<<grid, tpb, StepScratch<Env>::BYTES, st>>>(
+  atacom_substeps_kernel<Env, PARK><<<grid, tpb, StepScratch<Env>::bytes(tpb), st>>>(
       a, P, make_dual_consts<float, double>(P, D::F, D::G));
   return ATACOM_OK;
 }
@@ -1479,7 +1513,7 @@ struct AtacomHostCtx {
   int mode;
   // zero-copy path: counters of the ordered admission of the bulk loads and the number of warps admitted at once
   uint32_t* gate;
-  int zc_window;
+  int zc_window, zc_tpb;
 };
 
 // Device-visible alias of a page-locked, mapped host pointer (nullptr if it is not one).
@@ -1549,6 +1583,8 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   // block (measured sweep in DESIGN.md section 6).  ATACOM_ZC_WINDOW overrides; 0 = all loads at once.
   c->zc_window = 128;
   if (const char* f = getenv("ATACOM_ZC_WINDOW")) c->zc_window = atoi(f) > 0 ? atoi(f) : 0;
+  c->zc_tpb = 0;   // block size of the zero-copy launch (0: the device path's choice); ATACOM_ZC_TPB overrides
+  if (const char* f = getenv("ATACOM_ZC_TPB")) c->zc_tpb = atoi(f);
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
   ok = ok && configure_step_kernel<IiwaEnv<6>, ATACOM_STEP_DEVICE_IO>() &&
@@ -1625,9 +1661,9 @@ int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* 
     uint8_t* zst = static_cast<uint8_t*>(d[6]);
     constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
     rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0],
-                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window)
+                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window, c->zc_tpb)
                 : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0],
-                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window);
+                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window, c->zc_tpb);
     if (rc != ATACOM_OK) return rc;
     if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;

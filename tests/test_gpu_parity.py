@@ -59,6 +59,37 @@ def test_step_vs_oracle(cuda_device, family, B):
                                       errs["s"][ok].max(), (errs["ddq"][ok] < TOL32).mean()))
 
 
+@pytest.mark.parametrize("family", ["planar", "iiwa6", "iiwa7"])
+@pytest.mark.parametrize("active", [2, 3, 4])
+def test_several_active_constraints(cuda_device, family, active):
+    """Two, three or four constraints exactly active at once (s_i = 0: that many slack pivots).  Two stay on the
+    thread's own closed form; three or more take the general null-space routine, which the iiwa kernels run
+    warp-cooperatively (Dual::null_part_general_warp: every lane of the warp works on one environment at a time,
+    under the block's scratch lock).  Every environment of the batch asks for it here, so lock hand-over between
+    warps and the per-lane loop are exercised; against the float64 oracle with the canonical basis."""
+    if family == "planar" and active == 4:
+        pytest.skip("planar: four of six active constraints leave Jc without full row rank")
+    B = 320
+    q, dq, s, alpha = helpers.synthetic_cpu(family, B, seed=21)
+    n, F, G = helpers.DIMS[family]
+    rng = np.random.default_rng(8)
+    for i in range(B):
+        s[i, rng.choice(G, active, replace=False)] = 0.0
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
+    ddq, s_out, dbg, st = _run(family, q, dq, s, alpha, _params(family), cuda_device)
+    N = n + G
+    ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
+    assert ok.sum() > 0.3 * B
+    assert ((st & (_lib.ST_NONFINITE | _lib.ST_DENSE_PATH)) == 0)[ok].all()
+    assert ((st & _lib.ST_RANK_DEFICIENT) == 0)[ok].all()
+    assert ((st & _lib.ST_SLACK_PIVOT) != 0)[ok].mean() > 0.5
+    for name, got, want in (("w_mn", dbg[:, :N], ref["w_mn"]), ("w_null", dbg[:, N:], ref["w_null"]),
+                            ("s", s_out, ref["s_new"])):
+        e = helpers.rel_err(got, want)
+        assert (e[ok] < 2e-6).all(), (name, active, e[ok].max())
+    assert np.isfinite(ddq).all() and np.isfinite(s_out).all()
+
+
 @pytest.mark.parametrize("family", ["circle", "planar", "iiwa6"])
 def test_stratum_one_equals_reference_svd_basis(cuda_device, family):
     q, dq, s, alpha = helpers.synthetic_cpu(family, 512, seed=99)
