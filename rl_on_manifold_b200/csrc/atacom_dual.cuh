@@ -149,22 +149,19 @@ struct Dual {
         W[l][n + i] = acc * Ls.get_dyn(LI0 + l);
       }
     }
-    // outer loops rolled (code size), inner loops unrolled (the local-memory loads of a row are in flight together)
     ATACOM_ROLLED
     for (int a = 0; a < NR; ++a) {
-      R wa[M1], row[NR];
+      R wa[M1];
       ATACOM_UNROLL
       for (int l = 0; l < m; ++l) wa[l] = W[l][a];
-      ATACOM_UNROLL
-      for (int b = 0; b < NR; ++b) row[b] = R(0);
-      ATACOM_UNROLL
-      for (int l = 0; l < m; ++l) {
+      ATACOM_ROLLED
+      for (int b = a; b < NR; ++b) {
+        R acc = (a == b) ? R(1) : R(0);
         ATACOM_UNROLL
-        for (int b = 0; b < NR; ++b) row[b] -= wa[l] * W[l][b];
+        for (int l = 0; l < m; ++l) acc -= wa[l] * W[l][b];
+        Pm[a][b] = acc;
+        Pm[b][a] = acc;
       }
-      ATACOM_UNROLL
-      for (int b = 0; b < NR; ++b) Pm[a][b] = row[b];
-      Pm[a][a] += R(1);
     }
     int npiv = 0;
     ATACOM_ROLLED
@@ -187,8 +184,8 @@ struct Dual {
       const R d = sc * sc * Pm[idx][idx];
       if (npiv < k && d > tol * tol && d > R(DUAL_TINY)) {
         const R inv = dual_rsqrt(d);
-        ATACOM_UNROLL
-        for (int a = 0; a < NR; ++a) V[npiv][a] = Pm[idx][a] * sc * inv;     // Pm is symmetric: a row, not a column
+        ATACOM_ROLLED
+        for (int a = 0; a < NR; ++a) V[npiv][a] = Pm[a][idx] * sc * inv;
         ATACOM_ROLLED
         for (int a = 0; a < NR; ++a) {
           const R va = V[npiv][a];
@@ -297,6 +294,7 @@ struct Dual {
     if (npiv < k) status |= ST_RANK_DEFICIENT;
     return status;
   }
+
 #endif
 
   // The serial general routine for a thread whose project<true>() call returned the request (sigma and gamma in

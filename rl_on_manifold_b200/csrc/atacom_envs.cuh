@@ -556,9 +556,9 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   if constexpr (COOP) {
     using DU = Dual<HP, D, NDIAG>;
     unsigned pend = __ballot_sync(0xffffffffu, (st & ST_DENSE_PATH) != 0);
-    if (pend != 0u && (coop == nullptr || __popc(pend) > ATACOM_COOP_MAX_LANES)) {
+    if (__builtin_expect(pend != 0u, 0) && (coop == nullptr || __popc(pend) > ATACOM_COOP_MAX_LANES)) {
       if (st & ST_DENSE_PATH) st = (st & ST_RANK_DEFICIENT) | DU::general_from_deferred(Y, Ls, sh, ah, Kd.tol, w_null);
-    } else if (pend != 0u) {
+    } else if (__builtin_expect(pend != 0u, 0)) {
       const int lane = static_cast<int>(threadIdx.x & 31u);
       HP* slot = coop + static_cast<int>((threadIdx.x >> 5) % static_cast<unsigned>(coop_slots)) * coop_stride;
       volatile HP* sc = slot;

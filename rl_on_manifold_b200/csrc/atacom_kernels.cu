@@ -182,8 +182,11 @@ struct StepScratch {
   static constexpr size_t COOP_OFFSET = 16;
   static constexpr size_t COOP_SLOT_BYTES = (sizeof(double) * DU::COOP_DOUBLES + 16 + 15) / 16 * 16;
   static constexpr size_t COOP_SPARE = SMEM_MAX - 128 - COOP_OFFSET - sizeof(uint64_t) * MAX_WARPS - WARP_BYTES * MAX_WARPS;
-  static constexpr int COOP_SLOTS = !SHARED ? 0 : (COOP_SPARE / COOP_SLOT_BYTES >= size_t(MAX_WARPS) ? MAX_WARPS
-                                                   : static_cast<int>(COOP_SPARE / COOP_SLOT_BYTES));
+#ifndef ATACOM_COOP_SLOTS_MAX
+#define ATACOM_COOP_SLOTS_MAX (ATACOM_STEP_MAX_TPB / 32)
+#endif
+  static constexpr int COOP_SLOTS = !SHARED ? 0 : (COOP_SPARE / COOP_SLOT_BYTES >= size_t(ATACOM_COOP_SLOTS_MAX)
+                                                   ? ATACOM_COOP_SLOTS_MAX : static_cast<int>(COOP_SPARE / COOP_SLOT_BYTES));
   static_assert(!SHARED || COOP_SLOTS >= 1, "no room for the cooperative scratch next to a full-size block");
   static constexpr size_t BAR_OFFSET = COOP_OFFSET + COOP_SLOT_BYTES * COOP_SLOTS;
   static constexpr size_t HEAD = (BAR_OFFSET + sizeof(uint64_t) * MAX_WARPS + 127) / 128 * 128;
@@ -272,7 +275,7 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     SC::coop_init(atacom_smem);
     if (gated) *tk = atomicAdd(a.gate + 2, 1u);
   }
-  if (SC::SHARED || gated) __syncthreads();     // the only block barrier of the kernel, before any work
+  if (SC::SHARED || gated) __syncthreads();     // the only block barrier of the kernel, before any work (measured free)
   if (gated) bid = *tk;
   const int64_t e_raw = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
   const bool valid = e_raw < a.B;
@@ -1579,11 +1582,13 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
             cudaMalloc(&c->s_in, g_bytes) == cudaSuccess && cudaMalloc(&c->s_out, g_bytes) == cudaSuccess &&
             cudaMalloc(&c->status, max_B) == cudaSuccess && cudaMalloc(&c->gate, 16) == cudaSuccess &&
             cudaMemset(c->gate, 0, 16) == cudaSuccess;
-  // 128 warps = 448 KB of reads in flight: enough to keep PCIe busy, few enough that the loads arrive block after
+  // 96 warps = 336 KB of reads in flight: enough to keep PCIe busy, few enough that the loads arrive block after
   // block (measured sweep in DESIGN.md section 6).  ATACOM_ZC_WINDOW overrides; 0 = all loads at once.
-  c->zc_window = 128;
+  c->zc_window = 96;
   if (const char* f = getenv("ATACOM_ZC_WINDOW")) c->zc_window = atoi(f) > 0 ? atoi(f) : 0;
-  c->zc_tpb = 0;   // block size of the zero-copy launch (0: the device path's choice); ATACOM_ZC_TPB overrides
+  // block size of the zero-copy launch: small blocks, so that what is left to compute after the last bytes have
+  // crossed PCIe is short (0: the device path's choice); ATACOM_ZC_TPB overrides
+  c->zc_tpb = 128;
   if (const char* f = getenv("ATACOM_ZC_TPB")) c->zc_tpb = atoi(f);
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
