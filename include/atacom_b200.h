@@ -52,7 +52,8 @@ enum {
   ATACOM_ST_COLUMN_DROPPED = 2, /* the tolerance branch of rref fired (null_space_coordinate.py:60) */
   ATACOM_ST_SLACK_PIVOT = 4,    /* a slack column became a tangent coordinate                       */
   ATACOM_ST_NONFINITE = 8,
-  ATACOM_ST_DENSE_PATH = 16     /* structured fast path deferred to the dense Householder path      */
+  ATACOM_ST_DENSE_PATH = 16     /* generic / point-reach kernels: the structured fast path deferred to the dense
+                                   Householder path (the step kernels of the four families never set it)       */
 };
 
 enum { ATACOM_VARIANT_ATACOM = 0, ATACOM_VARIANT_ERROR_CORRECTION = 1 };
@@ -222,9 +223,13 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
  *   ATACOM_HOST_HYBRID     inputs through the copy engines, outputs stored by the kernels straight into the
  *                          caller's buffers over PCIe (the OUTPUT buffers must be page-locked and mapped:
  *                          cudaHostAlloc / cudaHostRegister / torch pin_memory());
- *   ATACOM_HOST_ZERO_COPY  one kernel reads and writes the caller's buffers directly (all of them mapped);
+ *   ATACOM_HOST_ZERO_COPY  one kernel reads and writes the caller's buffers directly (all of them mapped); its
+ *                          bulk loads are admitted a window of warps at a time in block-start order, so the first
+ *                          blocks compute and store while the last still wait for PCIe (environment overrides for
+ *                          experiments: ATACOM_ZC_WINDOW warps, 0 = all at once; ATACOM_ZC_TPB threads per block);
  *   ATACOM_HOST_AUTO       (default) zero-copy when every buffer of the call is mapped, else staged.
- * Measured on PCIe gen5 x16, 65 536 iiwa environments per call: zero-copy 230 us, staged 262 us, hybrid 265 us. */
+ * Measured on PCIe gen5 x16, 65 536 iiwa environments per call: zero-copy 188 us (231 us with all loads issued at
+ * once), staged 262 us, hybrid 265 us. */
 typedef struct AtacomHostCtx AtacomHostCtx;
 enum { ATACOM_HOST_AUTO = 0, ATACOM_HOST_STAGED = 1, ATACOM_HOST_ZERO_COPY = 2, ATACOM_HOST_HYBRID = 3 };
 int atacom_host_ctx_create(AtacomHostCtx** ctx, int64_t max_B, int chunks);
