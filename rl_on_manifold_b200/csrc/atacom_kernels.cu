@@ -50,6 +50,9 @@ namespace {
 #ifndef ATACOM_X_BULK_STORE
 #define ATACOM_X_BULK_STORE 1
 #endif
+#ifndef ATACOM_PDL_DEFAULT
+#define ATACOM_PDL_DEFAULT 1
+#endif
 #ifndef ATACOM_STEP_MAXNREG
 #define ATACOM_STEP_MAXNREG 128   // 448 threads = 14 warps, 4 on two of the SM sub-partitions: 16384 / (4 x 32) registers each
 #endif
@@ -271,8 +274,12 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   unsigned bid = blockIdx.x;
   const bool gated = IO == 1 && a.gate != nullptr;
   volatile uint32_t* tk = reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::TICKET_OFFSET);
+  // programmatic dependent launch (no-ops otherwise): let the next kernel's blocks queue up behind this one's,
+  // and do not touch global memory before the previous kernel has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) SC::coop_init(atacom_smem);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) {
-    SC::coop_init(atacom_smem);
     if (gated) *tk = atomicAdd(a.gate + 2, 1u);
   }
   if (SC::SHARED || gated) __syncthreads();     // the only block barrier of the kernel, before any work (measured free)
@@ -998,6 +1005,16 @@ int step_block_size(int64_t B) {
   return static_cast<int>(tpb);
 }
 
+// Programmatic dependent launch of the step kernels (ATACOM_PDL = 0 | 1 overrides the default).
+bool step_pdl_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* f = getenv("ATACOM_PDL");
+    mode = f ? (atoi(f) != 0 ? 1 : 0) : ATACOM_PDL_DEFAULT;
+  }
+  return mode == 1;
+}
+
 // Fused gather: rows to the peers as per-warp bulk stores (large NVLink writes) or as per-thread row stores.
 // ATACOM_GATHER_IO = rows | bulk overrides the default (experiments).
 bool gather_bulk_stores() {
@@ -1070,6 +1087,29 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   const size_t smem = StepScratch<Env>::bytes(tpb);
   if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
+  if (step_pdl_enabled() && IO != 1 && local_sync == nullptr) {
+    // Programmatic dependent launch: the blocks of this launch may start — one by one, as the blocks of the
+    // previous kernel in the stream leave their SMs — and set up while that kernel drains; they touch global
+    // memory only after griddepcontrol.wait, i.e. once it has completed and flushed.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(static_cast<unsigned>(tpb));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const ParamsT<float> Pk = as_params(p);
+    const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
+    if (cudaLaunchKernelEx(&cfg, atacom_step_kernel<Env, IO>, a, Pk, Kd) != cudaSuccess) {
+      cudaGetLastError();
+      return ATACOM_ERR_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ATACOM_OK;
+  }
   atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
       a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
   g_launches.fetch_add(1, std::memory_order_relaxed);
