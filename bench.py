@@ -322,6 +322,8 @@ def ours(args):
             if world == 1 and graph_ms < total_ms:
                 total_ms = graph_ms
                 launch_mode = "CUDA graph of %d launches, one replay" % args.steps
+                if os.environ.get("ATACOM_PDL", "1") != "0":
+                    launch_mode += ", programmatic dependent launch"
         except Exception as exc:                         # pragma: no cover
             launch_mode += " (graph capture failed: %s)" % type(exc).__name__
         if world > 1 and fused is not None:

@@ -1087,7 +1087,7 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   const size_t smem = StepScratch<Env>::bytes(tpb);
   if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
-  if (step_pdl_enabled() && IO != 1 && local_sync == nullptr) {
+  if (step_pdl_enabled() && IO != 1 && n_peers == 0) {   // (fused gather: measured neutral to slightly slower, left out)
     // Programmatic dependent launch: the blocks of this launch may start — one by one, as the blocks of the
     // previous kernel in the stream leave their SMs — and set up while that kernel drains; they touch global
     // memory only after griddepcontrol.wait, i.e. once it has completed and flushed.
