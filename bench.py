@@ -420,7 +420,10 @@ def ours(args):
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=traffic, peak_source=peak_src, kernel="atacom_step_kernel<IiwaEnv<6>>",
-                          kernel_us=k_ms * 1e3, frac_of_8TBs_nominal=achieved / 8000.0),
+                          kernel_us=k_ms * 1e3, frac_of_8TBs_nominal=achieved / 8000.0,
+                          note="nominal bound; the kernel is FP64-issue and latency bound (~4 k warp-instructions "
+                               "per 32 environments against 5.8 KB of traffic; ncu: FP64 pipe 32 % busy, 0.38 "
+                               "instructions per cycle per scheduler, DRAM 4 %): DESIGN.md section 6"),
             clocks=clocks,
         )
         if cpu_baseline is not None:
