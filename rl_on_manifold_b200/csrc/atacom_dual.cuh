@@ -42,22 +42,24 @@
 
 namespace atacom {
 
-// 1 / sqrt(x) for x inside the fp32 range (every use below is guarded): fp32 MUFU.RSQ seed and one
-// third-order correction in R, 8 instructions and no slow path; ::rsqrt(double) costs ~27 with a call.
+// 1 / sqrt(x): MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-20, the whole double range — no conversion to fp32 and
+// back, which cost two F2F per call and 1.8 % of the step kernel) and one third-order correction in R: 6
+// instructions, no slow path; ::rsqrt(double) costs ~27 with a call.  Arguments are floored at DUAL_TINY by the callers.
 template <typename R>
 ATACOM_HD R dual_rsqrt(R x) {
 #if defined(__CUDA_ARCH__)
-  float yf;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(cvt<float>(x)));
-  const R y = cvt<R>(yf);
-  const R e = ::fma(-x * y, y, R(1));               // 1 - x y^2 ~ 1e-7
+  double yd;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yd) : "d"(static_cast<double>(x)));
+  const R y = static_cast<R>(yd);
+  const R e = ::fma(-x * y, y, R(1));               // 1 - x y^2 ~ 1e-6
   return ::fma(y, ::fma(R(0.375), e, R(0.5)) * e, y);   // y (1 + e/2 + 3 e^2 / 8): error O(e^3)
 #else
   return R(1) / ::sqrt(x);
 #endif
 }
-// The same over the whole double range (the slack-pivot phases form 1 / |s_i| ~ 1e12 for an exactly active
-// constraint, and Gram determinants of such entries: 1e48 and beyond): the seed is MUFU.RSQ64H (~2^-20).
+// The same with a second (first-order) correction, for the slack-pivot phases: they form 1 / |s_i| ~ 1e12 for an
+// exactly active constraint and Gram determinants of such entries (1e48 and beyond — the fp32-seeded rsqrt this
+// replaced overflowed there), and what they compute is compared against a tolerance.
 template <typename R>
 ATACOM_HD R dual_rsqrt_wide(R x) {
 #if defined(__CUDA_ARCH__)
