@@ -541,8 +541,7 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   HP ah[at_least_1<k>::value];
   ATACOM_UNROLL
   for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
-  T w_mn[N];
-  HP w_null[N];
+  HP w_mn[N], w_null[N];      // (w_mn in HP: kept in fp32 it cost two conversions per entry and bought no registers)
 #if defined(__CUDA_ARCH__)
   // Three or more constraints active at once (the general null-space routine): with Y and L in shared memory the
   // thread only asks for it, and the warp then decides.  Few askers (the realistic case: a handful of environments
@@ -628,7 +627,7 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   if (w_dbg) {
     ATACOM_UNROLL
     for (int i = 0; i < N; ++i) {
-      w_dbg[i] = w_mn[i];
+      w_dbg[i] = cvt<T>(w_mn[i]);
       w_dbg[N + i] = cvt<T>(w_null[i]);
     }
   }
