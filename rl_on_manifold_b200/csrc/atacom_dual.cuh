@@ -30,8 +30,10 @@
 //      direction away from x), the remaining null direction is  (nu, -A_g nu / s)  with nu
 //      supported on the two (F = 1) / one (F = 0) unpivoted x columns; the first slack column
 //      whose entry exceeds tol becomes the coordinate; with two pivots missing the same is done in the
-//      remaining plane (two_slack_pivots); three or more missing pivots, or F > 1, take the out-of-line
-//      general routine (null_part_general: the oracle's own procedure in the reduced coordinates).
+//      remaining plane (two_slack_pivots); three or more missing pivots, or F > 1, take the general
+//      routine, the oracle's own procedure in the reduced coordinates: null_part_general (out of line,
+//      one thread) or, where Y and L live in shared memory, null_part_general_warp (the 32 lanes of the
+//      warp on one environment at a time; the caller of project<true>() arranges it).
 //
 // All arithmetic is in R (double on the device: B200 runs FP64 at half the FP32 rate and the
 // dual Gram matrix squares cond(Jc)); ~1.0 kFLOP per iiwa environment, no data-dependent

@@ -671,17 +671,6 @@ ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   return step_dual_lazy<Env, T, HP>(P, Kd, Y, Ls, q, dq, fetch, ddq, s_out, w_dbg);
 }
 
-// The general fp32 path (structured -> dense) from scratch, kept out of line: the rarely taken
-// fallback of the dual path must not set the register budget of the kernels that inline the latter.
-template <class Env, typename T, typename HP>
-ATACOM_NOINLINE uint8_t step_general_outlined(const ParamsT<T>& P, const T* q, const T* dq, const T* s,
-                                              const T* alpha, T* ddq, T* s_out, T* w_dbg) {
-  using D = typename Env::D;
-  RawConstraints<T, HP, D> R;
-  Env::template eval<T, HP>(P, q, dq, R);
-  return step_from_raw<T, HP, D, Env::NDIAG>(P, R, dq, s, alpha, ddq, s_out, w_dbg);
-}
-
 // atacom.py:145-149
 template <typename T, typename HP, class D, typename JT>
 ATACOM_HD void slack_from_raw(const ParamsT<T>& P, const RawConstraints<T, HP, D, JT>& R, T* s) {
