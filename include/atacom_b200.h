@@ -9,8 +9,10 @@
  *
  * Conventions
  *  - all array pointers are caller-owned DEVICE memory, fp32, contiguous row-major [B, dim];
- *    arithmetic: constraint values / kinematics in FP64 (the reference multiplies the residual
- *    c + K J dq + s^2/2, a cancellation of O(1) terms, by K_c ~ 100-240), projection algebra in FP32;
+ *    arithmetic: constraint values / kinematics and the whole projection in FP64 (the reference
+ *    multiplies the residual c + K J dq + s^2/2, a cancellation of O(1) terms, by K_c ~ 100-240, and the
+ *    dual Gram matrix squares cond(Jc)); fp32 only for the I/O, the acceleration limits and (in the
+ *    JDOT_QDOT mode) the velocity-product recursion;
  *    `*_host` entry points take HOST pointers instead and do the copies themselves;
  *  - `stream` is a cudaStream_t (NULL = default stream); calls are asynchronous on it; there is no
  *    global mutable state, so calls on different streams are independent;
@@ -57,6 +59,10 @@ enum {
 };
 
 enum { ATACOM_VARIANT_ATACOM = 0, ATACOM_VARIANT_ERROR_CORRECTION = 1 };
+/* b(q, dq) of the Cartesian rows.  OMEGA_X_V (default of the *_default_params): what the reference executes —
+ * pinocchio's classical frame acceleration after a FIRST-order forwardKinematics, data.a = 0, i.e. omega x v
+ * (iiwa_hit_atacom.py:87-89,122-128; atacom_air_hockey.py:94-96).  JDOT_QDOT: the full dJ/dt dq the paper
+ * defines (constraints.py:19-20), opt-in. */
 enum { ATACOM_BIAS_JDOT_QDOT = 0, ATACOM_BIAS_OMEGA_X_V = 1 };
 
 /* Constructor arguments of AtacomEnvWrapper (atacom/atacom.py:10-71) resolved to arrays, plus the
@@ -213,7 +219,7 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
                         float* w_dbg, int64_t B, const AtacomParams* p, void* stream);
 
 /* ---- host-buffer entry points (what a NumPy caller of the reference binds) ----
- * Same semantics as atacom_iiwa_step but every array pointer is HOST memory (pinned memory makes
+ * Same semantics as the device entry points but every array pointer is HOST memory (pinned memory makes
  * the copies asynchronous).  The context owns the device staging buffers and streams; the batch is
  * cut into `chunks` pieces whose H2D copy, kernel and D2H copy overlap.
  *
@@ -238,6 +244,29 @@ int atacom_host_ctx_destroy(AtacomHostCtx* ctx);
 int atacom_iiwa_step_host(AtacomHostCtx* ctx, int n_ctrl_joints, const float* q, const float* dq,
                           const float* s_in, const float* alpha, float* ddq, float* s_out, uint8_t* status,
                           int64_t B, const AtacomParams* p);
+/* The other families, same context, same argument meaning as their device entry points (w_dbg omitted):
+ *   circle / planar: what a NumPy caller of CircleEnvAtacom (circle_atacom.py) / AirHockeyPlanarAtacom
+ *   (atacom_air_hockey.py) binds — all four data paths;
+ *   point_reach: PointReachAtacom.step (collision_avoidance_atacom.py:29-48); generic: any ConstraintsSet whose
+ *   callbacks the caller evaluated batched in NumPy (constraints.py:46-82) — staged data path only
+ *   (ATACOM_HOST_AUTO or ATACOM_HOST_STAGED; the other modes return ATACOM_ERR_BAD_PARAM). */
+int atacom_circle_step_host(AtacomHostCtx* ctx, const float* q, const float* dq, const float* s_in,
+                            const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
+                            const AtacomParams* p);
+int atacom_planar_step_host(AtacomHostCtx* ctx, const float* q, const float* dq, const float* s_in,
+                            const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
+                            const AtacomParams* p);
+int atacom_point_reach_step_host(AtacomHostCtx* ctx, int n_objects, const float* q, const float* dq,
+                                 const float* obs_p, const float* obs_dp, const float* s_in, const float* action,
+                                 float* w, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p);
+int atacom_generic_step_host(AtacomHostCtx* ctx, int n, int F, int G, const float* c, const float* J,
+                             const float* b, const float* dq, const float* s_in, const float* alpha, float* ddq,
+                             float* s_out, uint8_t* status, int64_t B, const AtacomParams* p);
+
+/* Device-side waits (ordered admission of the zero-copy path, in-kernel barrier of atacom_iiwa_step_gather_sync)
+ * are bounded by a clock budget (~2 s): a wait that exceeds it gives up and is counted.  *count = number of
+ * such time-outs on the current device since the library was loaded (0 in a healthy run).  Synchronises. */
+int atacom_spin_timeouts(unsigned* count);
 
 #ifdef __cplusplus
 }

@@ -135,7 +135,7 @@ def iiwa_spec(n=6, Kc=240.0, dt=1.0 / 240.0):
                 K_c=Kc, K_q=4.0 * acc_max / vel_max, vel_max=vel_max, acc_max=acc_max, dt=dt)
 
 
-def iiwa_eval(q, dq, bias="jdot_qdot"):
+def iiwa_eval(q, dq, bias="omega_x_v"):
     """iiwa_hit_atacom.py:70-139.  q, dq have n = 6 or 7 entries; joints beyond n sit at 0
     (`_get_pino_value` pads with zeros, :65-68)."""
     n = len(q)
@@ -178,7 +178,7 @@ def planar_spec(Kc=240.0, dt=1.0 / 240.0, params=None):
                 K_q=2.0 * acc_max / vel_max, vel_max=vel_max, acc_max=acc_max, dt=dt)
 
 
-def planar_eval(q, dq, bias="jdot_qdot", params=None):
+def planar_eval(q, dq, bias="omega_x_v", params=None):
     """atacom_air_hockey.py:78-107 for a planar 3R arm."""
     pr = dict(PLANAR_DEFAULTS, **(params or {}))
     l = np.asarray(pr["links"])

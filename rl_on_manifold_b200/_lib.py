@@ -105,6 +105,13 @@ SIGNATURES = {
     "atacom_host_ctx_destroy": ([ctypes.c_void_p], ctypes.c_int),
     "atacom_iiwa_step_host": ([ctypes.c_void_p, ctypes.c_int, _f, _f, _f, _f, _f, _f, _u8, _i64, _P],
                               ctypes.c_int),
+    "atacom_circle_step_host": ([ctypes.c_void_p, _f, _f, _f, _f, _f, _f, _u8, _i64, _P], ctypes.c_int),
+    "atacom_planar_step_host": ([ctypes.c_void_p, _f, _f, _f, _f, _f, _f, _u8, _i64, _P], ctypes.c_int),
+    "atacom_point_reach_step_host": ([ctypes.c_void_p, ctypes.c_int, _f, _f, _f, _f, _f, _f, _f, _f, _u8, _i64, _P],
+                                     ctypes.c_int),
+    "atacom_generic_step_host": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f, _f, _f, _f, _f, _f,
+                                  _f, _f, _u8, _i64, _P], ctypes.c_int),
+    "atacom_spin_timeouts": ([ctypes.POINTER(ctypes.c_uint)], ctypes.c_int),
 }
 
 for _name, (_args, _res) in SIGNATURES.items():
@@ -128,6 +135,13 @@ def version():
 
 def launch_count():
     return int(lib.atacom_launch_count())
+
+
+def spin_timeouts():
+    """Device-side waits that ran out of their clock budget on the current device (0 in a healthy run)."""
+    n = ctypes.c_uint(0)
+    check(lib.atacom_spin_timeouts(ctypes.byref(n)))
+    return int(n.value)
 
 
 def default_params(family, n_ctrl_joints=6):

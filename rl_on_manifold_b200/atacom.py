@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, projection
+from .constraints import ConstraintsSet
 from .mdp import Box
 
 
@@ -34,8 +35,10 @@ class AtacomEnvWrapper:
                  family=None, n_ctrl_joints=None, params=None):
         self.env = base_env
         self.dims = {'q': dim_q, 'f': 0, 'g': 0}
-        self.f = f
-        self.g = g
+        # the reference accepts a bare ViabilityConstraint as well as a ConstraintsSet (atacom.py:18-19)
+        self.f = ConstraintsSet.wrap(f, dim_q)
+        self.g = ConstraintsSet.wrap(g, dim_q)
+        f, g = self.f, self.g
         self.time_step = time_step
         self._logger = None
 
@@ -132,11 +135,17 @@ class AtacomEnvWrapper:
     def seed(self, seed):
         self.env.seed(seed)
 
-    def reset(self, state=None):
-        self.state = self._as_batch(self.env.reset(state))
+    def reset(self, state=None, mask=None):
+        """atacom.py:93-98.  `mask` (bool [B], batched extension): only those environments start a new episode —
+        the base env re-initialises their rows and `_compute_slack_variables` their slacks (the kernels' mask)."""
+        if mask is None:
+            self.state = self._as_batch(self.env.reset(state))
+        else:
+            mask = torch.as_tensor(mask, device=self.device).bool()
+            self.state = self._as_batch(self.env.reset(state, mask=mask))
         self.q = self._get_q(self.state).contiguous()
         self.dq = self._get_dq(self.state).contiguous()
-        self._compute_slack_variables()
+        self._compute_slack_variables(None if mask is None else mask.to(torch.uint8).contiguous())
         return self._ret(self.state)
 
     def render(self):
@@ -260,14 +269,22 @@ class AtacomEnvWrapper:
         self.constr_logs.append(torch.stack([c_i.max(1).values, c_dq_i.max(1).values], 1))
 
     def get_constraints_logs(self):
+        """(c_avg, c_max, c_dq_max) of the epoch (atacom.py:207-216).  Under env-index sharding (`self.shard` set
+        to a sharding.EnvShard) the three numbers cover the GLOBAL batch: one all-reduce per epoch — SUM on the
+        sum and the count, MAX on the two maxima (sharding.reduce_constraint_logs)."""
         if not hasattr(self.env, "get_constraints_logs"):
             logs = torch.stack(self.constr_logs, 0)                       # [T, B, 2]
-            c_avg = float(logs[..., 0].mean())
+            total, count = float(logs[..., 0].double().sum()), logs[..., 0].numel()
             c_max = float(logs[..., 0].max())
             c_dq_max = float(logs[..., 1].max())
             self.constr_logs.clear()
-            return c_avg, c_max, c_dq_max
+            if self.shard is not None:
+                from .sharding import reduce_constraint_logs
+                total, count, c_max, c_dq_max = reduce_constraint_logs(total, count, c_max, c_dq_max, self.shard.group)
+            return total / max(count, 1), c_max, c_dq_max
         return self.env.get_constraints_logs()
+
+    shard = None            # sharding.EnvShard when this wrapper holds one rank's slice of a global batch
 
     # ------------------------------------------------------------------ helpers
     _numpy_io = False

@@ -24,8 +24,18 @@ class ViabilityConstraint:
         self.K = np.ones(dim_out) * K if np.isscalar(K) else np.asarray(K, dtype=np.float64)
         assert self.K.shape[0] == dim_out
 
+    @property
+    def has_callbacks(self):
+        return self.fun_origin is not None and self.J is not None and self.b_state is not None
+
+    def _need_callbacks(self):
+        if not self.has_callbacks:
+            raise ValueError("this ViabilityConstraint has no fun / J / b callbacks: it belongs to a ConstraintsSet "
+                             "with a built-in device functor (family=...), whose rows the fused kernels evaluate")
+
     # batched versions of constraints.py:33-43
     def fun(self, q, dq, origin_constr=False):
+        self._need_callbacks()
         c = self.fun_origin(q)
         if origin_constr:
             return c
@@ -33,10 +43,12 @@ class ViabilityConstraint:
         return c + K * torch.einsum("bmn,bn->bm", self.J(q), dq)
 
     def K_J(self, q):
+        self._need_callbacks()
         K = torch.as_tensor(self.K, dtype=q.dtype, device=q.device)
         return K[None, :, None] * self.J(q)
 
     def b(self, q, dq):
+        self._need_callbacks()
         K = torch.as_tensor(self.K, dtype=q.dtype, device=q.device)
         return torch.einsum("bmn,bn->bm", self.J(q), dq) + K * self.b_state(q, dq)
 
@@ -51,6 +63,15 @@ class ConstraintsSet:
         self.dim_out = 0
         self.family = family
 
+    @staticmethod
+    def wrap(c, dim_q):
+        """A bare ViabilityConstraint as a one-element set (the reference takes either, atacom.py:18-19)."""
+        if c is None or isinstance(c, ConstraintsSet):
+            return c
+        cs = ConstraintsSet(dim_q, family=getattr(c, "family", None))
+        cs.add_constraint(c)
+        return cs
+
     def add_constraint(self, c: ViabilityConstraint):
         assert c.dim_q == self.dim_q
         self.dim_out += c.dim_out
@@ -62,8 +83,7 @@ class ConstraintsSet:
 
     @property
     def has_callbacks(self):
-        return all(c.fun_origin is not None and c.J is not None and c.b_state is not None
-                   for c in self.constraints_list)
+        return all(c.has_callbacks for c in self.constraints_list)
 
     def raw(self, q, dq):
         """(c [B,m], J [B,m,n], b_state [B,m]) stacked over the constraints: the generic kernel's inputs."""

@@ -563,7 +563,7 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
       volatile HP* sc = slot;
       unsigned* lock = reinterpret_cast<unsigned*>(slot + DU::COOP_DOUBLES);
       if (lane == 0) {
-        while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(200);
+        while (atomicCAS(lock, 0u, 1u) != 0u) __nanosleep(200);   // holders are warps of this block and always release
       }
       __syncwarp();
       __threadfence_block();

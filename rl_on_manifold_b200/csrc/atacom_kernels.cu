@@ -7,6 +7,7 @@
 // (device-resident arrays) or through that region with the bulk-copy engine (mapped host arrays,
 // peer buffers of the fused gather).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdlib>
@@ -56,9 +57,29 @@ namespace {
 #ifndef ATACOM_STEP_MAXNREG
 #define ATACOM_STEP_MAXNREG 128   // 448 threads = 14 warps, 4 on two of the SM sub-partitions: 16384 / (4 x 32) registers each
 #endif
+#ifndef ATACOM_SPIN_BUDGET
+#define ATACOM_SPIN_BUDGET (4000000000ll)   // clock64 ticks (~2 s) a device-side wait may take before it gives up
+#endif
 constexpr int TPB = ATACOM_TPB;
 constexpr int STEP_MAX_TPB = ATACOM_STEP_MAX_TPB;
+constexpr int MAX_DEVICES = 64;
 std::atomic<int64_t> g_launches{0};
+// Device-side waits (ordered admission, in-kernel cross-rank barrier) are bounded: a wait that exceeds
+// ATACOM_SPIN_BUDGET gives up, counts itself here and the kernel carries on (admission: unrationed loads, results
+// unaffected; barrier: the step is not published to / awaited from the late rank).  atacom_spin_timeouts() reads it.
+__device__ unsigned g_spin_timeouts = 0;
+
+// NVTX range around a host-side section (step launch, gather launch, host pipeline); a no-op without a profiler
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  return dev;
+}
 
 // ------------------------------------------------------------------ staging helpers
 template <int DIM>
@@ -315,9 +336,14 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
         const unsigned window = static_cast<unsigned>(a.gate_window);
         if (order >= window) {
           unsigned seen;
+          const long long t0 = clock64();
           for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gate) : "memory");
             if (seen + window > order) break;
+            if (clock64() - t0 > ATACOM_SPIN_BUDGET) {   // watchdog: load unrationed rather than hang
+              atomicAdd(&g_spin_timeouts, 1u);
+              break;
+            }
             __nanosleep(64);
           }
         }
@@ -454,11 +480,19 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
         __threadfence_system();
         for (int w = 0; w < a.n_peers; ++w)
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[w] + a.rank), "r"(seq) : "memory");
-        for (int w = 0; w < a.n_peers; ++w) {
+        const long long t0 = clock64();
+        bool late = false;
+        for (int w = 0; w < a.n_peers && !late; ++w) {
           unsigned seen;
-          do {
+          for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.peer_flags[a.rank] + w) : "memory");
-          } while (static_cast<int>(seen - seq) < 0);
+            if (static_cast<int>(seen - seq) >= 0) break;
+            if (clock64() - t0 > ATACOM_SPIN_BUDGET) {   // watchdog: a rank that skipped the launch must not hang the others
+              atomicAdd(&g_spin_timeouts, 1u);
+              late = true;
+              break;
+            }
+          }
         }
       }
     }
@@ -983,14 +1017,13 @@ inline unsigned blocks_for(int64_t B) { return static_cast<unsigned>((B + TPB - 
 
 // Block size of the step kernels: spread B environments over the SMs in as few equal waves as possible.
 int step_block_size(int64_t B) {
-  static int sm_count = 0;
+  static std::atomic<int> sm_counts[MAX_DEVICES];   // per device: a process may drive several GPUs
+  const int dev = current_device();
+  int sm_count = sm_counts[dev].load(std::memory_order_relaxed);
   if (sm_count == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      sm_count = v;
-    else
-      sm_count = 148;
+    int v = 0;
+    sm_count = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+    sm_counts[dev].store(sm_count, std::memory_order_relaxed);
   }
   if (const char* f = getenv("ATACOM_STEP_TPB")) {   // experiments only
     const int v = atoi(f);
@@ -1035,17 +1068,19 @@ int check_common(int64_t B, const AtacomParams* p) {
   return ATACOM_OK;
 }
 
-// Opt the kernel in to its dynamic shared memory (once per process and instantiation).
+// Opt the kernel in to its dynamic shared memory: the attribute belongs to the (function, device) pair, so
+// once per instantiation AND device (a process that first runs on cuda:0 and then on cuda:1 needs both).
 template <class Env, int IO>
 bool configure_step_kernel() {
-  static int state = 0;   // 0: not yet, 1: done, -1: failed
-  if (state == 0) {
+  static std::atomic<int> states[MAX_DEVICES];   // 0: not yet, 1: done, -1: failed
+  std::atomic<int>& state = states[current_device()];
+  if (state.load(std::memory_order_acquire) == 0) {
     constexpr size_t smem = StepScratch<Env>::BYTES;
-    state = (smem <= 48 * 1024 ||
-             cudaFuncSetAttribute(atacom_step_kernel<Env, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)) == cudaSuccess) ? 1 : -1;
+    state.store((smem <= 48 * 1024 ||
+                 cudaFuncSetAttribute(atacom_step_kernel<Env, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)) == cudaSuccess) ? 1 : -1, std::memory_order_release);
   }
-  return state == 1;
+  return state.load(std::memory_order_acquire) == 1;
 }
 
 template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : ATACOM_STEP_DEVICE_IO)>
@@ -1131,11 +1166,13 @@ int launch_slack_init(const float* q, const float* dq, float* s, const uint8_t* 
 
 template <class Env, bool PARK>
 int launch_substeps(const SubstepArgs& a, const ParamsT<float>& P, unsigned grid, int tpb, cudaStream_t st) {
-  static int cfg = 0;   // per instantiation
-  if (cfg == 0)
-    cfg = cudaFuncSetAttribute(atacom_substeps_kernel<Env, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(StepScratch<Env>::BYTES)) == cudaSuccess ? 1 : -1;
-  if (cfg < 0) return ATACOM_ERR_CUDA;
+  static std::atomic<int> cfgs[MAX_DEVICES];   // per instantiation and device
+  std::atomic<int>& cfg = cfgs[current_device()];
+  if (cfg.load(std::memory_order_acquire) == 0)
+    cfg.store(cudaFuncSetAttribute(atacom_substeps_kernel<Env, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(StepScratch<Env>::BYTES)) == cudaSuccess ? 1 : -1,
+              std::memory_order_release);
+  if (cfg.load(std::memory_order_acquire) < 0) return ATACOM_ERR_CUDA;
   using D = typename Env::D;
   atacom_substeps_kernel<Env, PARK><<<grid, tpb, StepScratch<Env>::bytes(tpb), st>>>(
       a, P, make_dual_consts<float, double>(P, D::F, D::G));
@@ -1159,7 +1196,9 @@ void fill_common(AtacomParams* p) {
   for (size_t i = 0; i < sizeof(*p) / 4; ++i) reinterpret_cast<uint32_t*>(p)[i] = 0;
   p->rref_tol = 0.05f;  // atacom.py:128
   p->variant = ATACOM_VARIANT_ATACOM;
-  p->bias_mode = ATACOM_BIAS_JDOT_QDOT;
+  // what the reference executes: first-order forwardKinematics leaves data.a at zero, so
+  // getFrameClassicalAcceleration returns omega x v (iiwa_hit_atacom.py:87-89,122-128; atacom_air_hockey.py:94-96)
+  p->bias_mode = ATACOM_BIAS_OMEGA_X_V;
   p->clip_acc = 1;
 }
 
@@ -1535,23 +1574,47 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   return check_launch();
 }
 
+}  // extern "C"
+
 // ------------------------------------------------------------------ host-buffer entry points
-// The call a user of the NumPy reference binds: host arrays in, host arrays out.  The batch is cut into
-// chunks that pipeline H2D copy -> kernel -> D2H copy over a few streams.  The whole pipeline of one call
+// The call a user of the NumPy reference binds: host arrays in, host arrays out, for every family.  The batch is
+// cut into chunks that pipeline H2D copy -> kernel -> D2H copy over a few streams.  The whole pipeline of one call
 // (every copy and every launch) is captured once into a CUDA graph and replayed while the caller keeps
 // passing the same buffers, batch size and parameters: one driver call per step instead of ~30.
+constexpr int HOST_MAX_IN = 8, HOST_MAX_OUT = 3;
+
+struct HostArr {
+  const void* h;      // caller's host array [B, dim] (null: absent optional array)
+  size_t row_bytes;   // dim * sizeof(element)
+};
+
+// One call, family-independent: its arrays and how to launch the family's kernel on a chunk of them.
+struct HostCall {
+  int key[4];                        // family id and shape parameters
+  int n_in, n_out;
+  HostArr in[HOST_MAX_IN], out[HOST_MAX_OUT];
+  // kernel launch on rows [e0, e0 + nb) given the bases of the (device-visible) arrays; `din` / `dout` follow
+  // in[] / out[]; chunk starts are multiples of TPB, so every chunk's rows keep the 16-byte alignment of the base
+  int (*launch)(const HostCall& c, void* const* din, void* const* dout, int64_t e0, int64_t nb, const AtacomParams* p,
+                cudaStream_t st);
+  // zero-copy launch (one kernel on the mapped aliases of the caller's buffers), or null when the family has none
+  int (*zero_copy)(const HostCall& c, void* const* din, void* const* dout, int64_t B, const AtacomParams* p,
+                   struct AtacomHostCtx* ctx);
+};
+
 struct AtacomHostCtx {
   int64_t max_B;
   int chunks;
-  float *q, *dq, *s_in, *alpha, *ddq, *s_out;
-  uint8_t* status;
+  unsigned char* arena;      // device staging area, grown on demand (never while capturing)
+  size_t arena_bytes;
   cudaStream_t streams[4];
   cudaEvent_t fork, join[4];
   // cached graph and the call it was captured for
   cudaGraphExec_t exec;
-  const void* key_ptr[7];
+  int key[4];
+  const void* key_ptr[HOST_MAX_IN + HOST_MAX_OUT];
   int64_t key_B;
-  int key_n, key_launches;
+  int key_launches;
   AtacomParams key_params;
   int mode;
   // zero-copy path: counters of the ordered admission of the bulk loads and the number of warps admitted at once
@@ -1569,15 +1632,23 @@ static void* mapped_alias(const void* h) {
   return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
-// out_ddq / out_s / out_status non-null: device aliases of the caller's (mapped) output buffers — the kernels
-// store their results there directly (bulk stores over PCIe) and the D2H copies disappear.
-static int host_pipeline(AtacomHostCtx* c, int n, const float* q, const float* dq, const float* s_in,
-                         const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
-                         const AtacomParams* p, int n_streams, float* out_ddq = nullptr, float* out_s = nullptr,
-                         uint8_t* out_status = nullptr) {
-  const int G = 5 + n;
-  const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? n : n - 1;
-  // chunk boundaries are multiples of TPB so every chunk's rows stay 16-byte aligned
+static size_t round256(size_t v) { return (v + 255) / 256 * 256; }
+
+// The staged pipeline of one call; `dout_direct` non-null (hybrid): device aliases of the caller's mapped output
+// buffers — the kernels store their results there directly (over PCIe) and the D2H copies disappear.
+static int host_pipeline(AtacomHostCtx* c, const HostCall& call, int64_t B, const AtacomParams* p, int n_streams,
+                         void* const* dout_direct) {
+  void* din[HOST_MAX_IN];
+  void* dout[HOST_MAX_OUT];
+  size_t off = 0;
+  for (int i = 0; i < call.n_in; ++i) {
+    din[i] = call.in[i].h ? c->arena + off : nullptr;
+    off += round256(call.in[i].row_bytes * static_cast<size_t>(B));
+  }
+  for (int i = 0; i < call.n_out; ++i) {
+    dout[i] = call.out[i].h ? (dout_direct ? dout_direct[i] : c->arena + off) : nullptr;
+    off += round256(call.out[i].row_bytes * static_cast<size_t>(B));
+  }
   int64_t per = (B + c->chunks - 1) / c->chunks;
   per = (per + TPB - 1) / TPB * TPB;
   int rc = ATACOM_OK;
@@ -1585,43 +1656,210 @@ static int host_pipeline(AtacomHostCtx* c, int n, const float* q, const float* d
   for (int64_t e0 = 0; e0 < B && rc == ATACOM_OK; e0 += per, ++ci) {
     const int64_t nb = (B - e0) < per ? (B - e0) : per;
     cudaStream_t st = c->streams[ci % n_streams];
-    cudaMemcpyAsync(c->q + e0 * n, q + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->dq + e0 * n, dq + e0 * n, sizeof(float) * n * nb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->s_in + e0 * G, s_in + e0 * G, sizeof(float) * G * nb, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->alpha + e0 * na, alpha + e0 * na, sizeof(float) * na * nb, cudaMemcpyHostToDevice, st);
-    if (out_ddq) {
-      uint8_t* zst = status ? out_status + e0 : nullptr;
-      rc = n == 6 ? launch_step<IiwaEnv<6>, 2>(c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
-                                               out_ddq + e0 * n, out_s + e0 * G, zst, nullptr, nb, p, st)
-                  : launch_step<IiwaEnv<7>, 2>(c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
-                                               out_ddq + e0 * n, out_s + e0 * G, zst, nullptr, nb, p, st);
-      continue;
-    }
-    rc = atacom_iiwa_step(n, c->q + e0 * n, c->dq + e0 * n, c->s_in + e0 * G, c->alpha + e0 * na,
-                          c->ddq + e0 * n, c->s_out + e0 * G, status ? c->status + e0 : nullptr, nullptr, nb, p,
-                          st);
-    cudaMemcpyAsync(ddq + e0 * n, c->ddq + e0 * n, sizeof(float) * n * nb, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(s_out + e0 * G, c->s_out + e0 * G, sizeof(float) * G * nb, cudaMemcpyDeviceToHost, st);
-    if (status) cudaMemcpyAsync(status + e0, c->status + e0, nb, cudaMemcpyDeviceToHost, st);
+    for (int i = 0; i < call.n_in; ++i)
+      if (call.in[i].h)
+        cudaMemcpyAsync(static_cast<unsigned char*>(din[i]) + e0 * call.in[i].row_bytes,
+                        static_cast<const unsigned char*>(call.in[i].h) + e0 * call.in[i].row_bytes,
+                        call.in[i].row_bytes * nb, cudaMemcpyHostToDevice, st);
+    rc = call.launch(call, din, dout, e0, nb, p, st);
+    if (dout_direct) continue;
+    for (int i = 0; i < call.n_out; ++i)
+      if (call.out[i].h)
+        cudaMemcpyAsync(static_cast<unsigned char*>(const_cast<void*>(call.out[i].h)) + e0 * call.out[i].row_bytes,
+                        static_cast<unsigned char*>(dout[i]) + e0 * call.out[i].row_bytes, call.out[i].row_bytes * nb,
+                        cudaMemcpyDeviceToHost, st);
   }
   return rc;
 }
+
+static int host_call(AtacomHostCtx* c, const HostCall& call, int64_t B, const AtacomParams* p) {
+  if (!c || !p) return ATACOM_ERR_NULL_POINTER;
+  if (B < 0 || B > c->max_B) return ATACOM_ERR_BAD_DIMS;
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (B == 0) return ATACOM_OK;
+  NvtxRange range("atacom_step_host");
+  void* alias_out[HOST_MAX_OUT] = {};
+  void* const* dout_direct = nullptr;
+  if (c->mode == ATACOM_HOST_HYBRID) {
+    // hybrid: inputs through the copy engines (large PCIe reads), outputs stored by the kernels straight into
+    // the caller's mapped buffers — no D2H stage at the end of the pipeline
+    for (int i = 0; i < call.n_out; ++i) {
+      if (!call.out[i].h) continue;
+      alias_out[i] = mapped_alias(call.out[i].h);
+      if (!alias_out[i]) return ATACOM_ERR_BAD_PARAM;
+    }
+    dout_direct = alias_out;
+  }
+  if (c->mode == ATACOM_HOST_ZERO_COPY || c->mode == ATACOM_HOST_AUTO) {
+    // zero-copy: one launch on the device aliases of the caller's buffers; loads and stores cross PCIe
+    bool all = call.zero_copy != nullptr;
+    void* zin[HOST_MAX_IN] = {};
+    void* zout[HOST_MAX_OUT] = {};
+    for (int i = 0; i < call.n_in && all; ++i)
+      if (call.in[i].h) all = (zin[i] = mapped_alias(call.in[i].h)) != nullptr;
+    for (int i = 0; i < call.n_out && all; ++i)
+      if (call.out[i].h) all = (zout[i] = mapped_alias(call.out[i].h)) != nullptr;
+    if (!all && c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
+    if (all) {
+      rc = call.zero_copy(call, zin, zout, B, p, c);
+      if (rc != ATACOM_OK) return rc;
+      if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+      return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+    }
+  }
+  // staging area (grown outside any capture; a larger call invalidates the cached graph, whose nodes point into it)
+  size_t need = 0;
+  for (int i = 0; i < call.n_in; ++i) need += round256(call.in[i].row_bytes * static_cast<size_t>(B));
+  for (int i = 0; i < call.n_out; ++i) need += round256(call.out[i].row_bytes * static_cast<size_t>(B));
+  if (need > c->arena_bytes) {
+    if (c->exec) {
+      cudaGraphExecDestroy(c->exec);
+      c->exec = nullptr;
+    }
+    cudaStreamSynchronize(c->streams[0]);
+    cudaFree(c->arena);
+    c->arena = nullptr;
+    c->arena_bytes = 0;
+    if (cudaMalloc(&c->arena, need) != cudaSuccess) {
+      cudaGetLastError();
+      return ATACOM_ERR_CUDA;
+    }
+    c->arena_bytes = need;
+  }
+  const void* key[HOST_MAX_IN + HOST_MAX_OUT] = {};
+  for (int i = 0; i < call.n_in; ++i) key[i] = call.in[i].h;
+  for (int i = 0; i < call.n_out; ++i) key[HOST_MAX_IN + i] = call.out[i].h;
+  bool hit = c->exec != nullptr && c->key_B == B && memcmp(c->key, call.key, sizeof(c->key)) == 0 &&
+             memcmp(&c->key_params, p, sizeof(AtacomParams)) == 0 && memcmp(c->key_ptr, key, sizeof(key)) == 0;
+  if (!hit) {
+    if (c->exec) {
+      cudaGraphExecDestroy(c->exec);
+      c->exec = nullptr;
+    }
+    // capture: stream 0 is the origin, the others fork from it and join back
+    cudaGraph_t graph = nullptr;
+    const int ns = c->chunks < 4 ? c->chunks : 4;
+    bool ok = cudaStreamBeginCapture(c->streams[0], cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      cudaEventRecord(c->fork, c->streams[0]);
+      for (int i = 1; i < ns; ++i) cudaStreamWaitEvent(c->streams[i], c->fork, 0);
+      const int64_t before = g_launches.load(std::memory_order_relaxed);
+      rc = host_pipeline(c, call, B, p, ns, dout_direct);
+      c->key_launches = static_cast<int>(g_launches.exchange(before, std::memory_order_relaxed) - before);   // captured, not run
+      for (int i = 1; i < ns; ++i) {
+        cudaEventRecord(c->join[i], c->streams[i]);
+        cudaStreamWaitEvent(c->streams[0], c->join[i], 0);
+      }
+      ok = cudaStreamEndCapture(c->streams[0], &graph) == cudaSuccess && graph != nullptr && rc == ATACOM_OK;
+    }
+    if (ok) ok = cudaGraphInstantiate(&c->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      c->exec = nullptr;
+      return rc != ATACOM_OK ? rc : ATACOM_ERR_CUDA;
+    }
+    memcpy(c->key, call.key, sizeof(c->key));
+    memcpy(c->key_ptr, key, sizeof(key));
+    c->key_B = B;
+    c->key_params = *p;
+  }
+  if (cudaGraphLaunch(c->exec, c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+  g_launches.fetch_add(c->key_launches, std::memory_order_relaxed);   // kernel launches inside the replayed graph
+  if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+}
+
+// ---- the families' launches on a chunk.  Step families: in = { q, dq, s_in, alpha }, out = { ddq, s_out, status }.
+template <class T> static T* at_row(void* base, int64_t e0, size_t row_bytes) {
+  return base ? reinterpret_cast<T*>(static_cast<unsigned char*>(base) + e0 * row_bytes) : nullptr;
+}
+
+template <class Env, int IO>
+static int host_launch_step(const HostCall& c, void* const* din, void* const* dout, int64_t e0, int64_t nb,
+                            const AtacomParams* p, cudaStream_t st) {
+  return launch_step<Env, IO>(at_row<const float>(din[0], e0, c.in[0].row_bytes), at_row<const float>(din[1], e0, c.in[1].row_bytes),
+                              at_row<const float>(din[2], e0, c.in[2].row_bytes), at_row<const float>(din[3], e0, c.in[3].row_bytes),
+                              at_row<float>(dout[0], e0, c.out[0].row_bytes), at_row<float>(dout[1], e0, c.out[1].row_bytes),
+                              at_row<uint8_t>(dout[2], e0, 1), nullptr, nb, p, st);
+}
+
+template <class Env>
+static int host_zero_copy_step(const HostCall&, void* const* din, void* const* dout, int64_t B, const AtacomParams* p,
+                               AtacomHostCtx* ctx) {
+  constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+  return launch_step<Env, HOST_IO>(static_cast<const float*>(din[0]), static_cast<const float*>(din[1]),
+                                   static_cast<const float*>(din[2]), static_cast<const float*>(din[3]),
+                                   static_cast<float*>(dout[0]), static_cast<float*>(dout[1]),
+                                   static_cast<uint8_t*>(dout[2]), nullptr, B, p, ctx->streams[0], nullptr, 0, 0, nullptr,
+                                   nullptr, 0, ctx->gate, ctx->zc_window, ctx->zc_tpb);
+}
+
+template <class Env>
+static int step_host(AtacomHostCtx* c, int family_id, const float* q, const float* dq, const float* s_in,
+                     const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p) {
+  using D = typename Env::D;
+  if (!c || !p) return ATACOM_ERR_NULL_POINTER;
+  const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? D::n : D::k;
+  if (!q || !dq || !ddq || (D::G > 0 && (!s_in || !s_out)) || (na > 0 && !alpha)) return ATACOM_ERR_NULL_POINTER;
+  // every kernel instantiation the call may use opts in to its shared memory now, not while capturing
+  constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+  if (!configure_step_kernel<Env, ATACOM_STEP_DEVICE_IO>() || !configure_step_kernel<Env, HOST_IO>() ||
+      !configure_step_kernel<Env, 2>())
+    return ATACOM_ERR_CUDA;
+  step_block_size(1);
+  HostCall call = {};
+  call.key[0] = family_id;
+  call.key[1] = D::n;
+  call.key[2] = c->mode;
+  call.n_in = 4;
+  call.n_out = 3;
+  call.in[0] = {q, sizeof(float) * D::n};
+  call.in[1] = {dq, sizeof(float) * D::n};
+  call.in[2] = {D::G > 0 ? s_in : nullptr, sizeof(float) * D::G};
+  call.in[3] = {na > 0 ? alpha : nullptr, sizeof(float) * static_cast<size_t>(na)};
+  call.out[0] = {ddq, sizeof(float) * D::n};
+  call.out[1] = {D::G > 0 ? s_out : nullptr, sizeof(float) * D::G};
+  call.out[2] = {status, 1};
+  // staged: rows by direct loads / stores; hybrid: results leave as bulk stores over PCIe
+  call.launch = c->mode == ATACOM_HOST_HYBRID ? host_launch_step<Env, 2> : host_launch_step<Env, ATACOM_STEP_DEVICE_IO>;
+  call.zero_copy = host_zero_copy_step<Env>;
+  return host_call(c, call, B, p);
+}
+
+// point reach: in = { q, dq, obs_p, obs_dp, s_in, action }, out = { w, s_out, status }
+static int host_launch_point(const HostCall& c, void* const* din, void* const* dout, int64_t e0, int64_t nb,
+                             const AtacomParams* p, cudaStream_t st) {
+  return atacom_point_reach_step(c.key[1], at_row<const float>(din[0], e0, c.in[0].row_bytes),
+                                 at_row<const float>(din[1], e0, c.in[1].row_bytes), at_row<const float>(din[2], e0, c.in[2].row_bytes),
+                                 at_row<const float>(din[3], e0, c.in[3].row_bytes), at_row<const float>(din[4], e0, c.in[4].row_bytes),
+                                 at_row<const float>(din[5], e0, c.in[5].row_bytes), at_row<float>(dout[0], e0, c.out[0].row_bytes),
+                                 at_row<float>(dout[1], e0, c.out[1].row_bytes), at_row<uint8_t>(dout[2], e0, 1), nullptr, nb, p, st);
+}
+
+// generic ConstraintsSet: in = { c, J, b, dq, s_in, alpha }, out = { ddq, s_out, status }
+static int host_launch_generic(const HostCall& c, void* const* din, void* const* dout, int64_t e0, int64_t nb,
+                               const AtacomParams* p, cudaStream_t st) {
+  return atacom_generic_step(c.key[1], c.key[2], c.key[3], at_row<const float>(din[0], e0, c.in[0].row_bytes),
+                             at_row<const float>(din[1], e0, c.in[1].row_bytes), at_row<const float>(din[2], e0, c.in[2].row_bytes),
+                             at_row<const float>(din[3], e0, c.in[3].row_bytes), at_row<const float>(din[4], e0, c.in[4].row_bytes),
+                             at_row<const float>(din[5], e0, c.in[5].row_bytes), at_row<float>(dout[0], e0, c.out[0].row_bytes),
+                             at_row<float>(dout[1], e0, c.out[1].row_bytes), at_row<uint8_t>(dout[2], e0, 1), nullptr, nb, p, st);
+}
+
+extern "C" {
 
 int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   if (!out) return ATACOM_ERR_NULL_POINTER;
   if (max_B <= 0 || chunks < 1 || chunks > 64) return ATACOM_ERR_BAD_DIMS;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ATACOM_ERR_NO_DEVICE;
-  AtacomHostCtx* c = new (std::nothrow) AtacomHostCtx();
+  AtacomHostCtx* c = new (std::nothrow) AtacomHostCtx();   // value-initialised: every member starts out null
   if (!c) return ATACOM_ERR_CUDA;
   c->max_B = max_B;
   c->chunks = chunks;
-  const size_t q_bytes = sizeof(float) * ATACOM_MAX_Q * max_B, g_bytes = sizeof(float) * ATACOM_MAX_G * max_B;
-  bool ok = cudaMalloc(&c->q, q_bytes) == cudaSuccess && cudaMalloc(&c->dq, q_bytes) == cudaSuccess &&
-            cudaMalloc(&c->alpha, q_bytes) == cudaSuccess && cudaMalloc(&c->ddq, q_bytes) == cudaSuccess &&
-            cudaMalloc(&c->s_in, g_bytes) == cudaSuccess && cudaMalloc(&c->s_out, g_bytes) == cudaSuccess &&
-            cudaMalloc(&c->status, max_B) == cudaSuccess && cudaMalloc(&c->gate, 16) == cudaSuccess &&
-            cudaMemset(c->gate, 0, 16) == cudaSuccess;
+  bool ok = cudaMalloc(&c->gate, 16) == cudaSuccess && cudaMemset(c->gate, 0, 16) == cudaSuccess;
   // 96 warps = 336 KB of reads in flight: enough to keep PCIe busy, few enough that the loads arrive block after
   // block (measured sweep in DESIGN.md section 6).  ATACOM_ZC_WINDOW overrides; 0 = all loads at once.
   c->zc_window = 96;
@@ -1631,17 +1869,11 @@ int atacom_host_ctx_create(AtacomHostCtx** out, int64_t max_B, int chunks) {
   c->zc_tpb = 128;
   if (const char* f = getenv("ATACOM_ZC_TPB")) c->zc_tpb = atoi(f);
   for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess;
-  constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
-  ok = ok && configure_step_kernel<IiwaEnv<6>, ATACOM_STEP_DEVICE_IO>() &&
-       configure_step_kernel<IiwaEnv<7>, ATACOM_STEP_DEVICE_IO>() &&
-       configure_step_kernel<IiwaEnv<6>, HOST_IO>() && configure_step_kernel<IiwaEnv<7>, HOST_IO>() &&
-       configure_step_kernel<IiwaEnv<6>, 2>() && configure_step_kernel<IiwaEnv<7>, 2>();   // not while capturing
-  step_block_size(1);
   ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
-    delete c;
+    atacom_host_ctx_destroy(c);   // frees whatever was allocated
     return ATACOM_ERR_CUDA;
   }
   *out = c;
@@ -1664,97 +1896,92 @@ int atacom_host_ctx_set_mode(AtacomHostCtx* c, int mode) {
 int atacom_host_ctx_destroy(AtacomHostCtx* c) {
   if (!c) return ATACOM_OK;
   if (c->exec) cudaGraphExecDestroy(c->exec);
-  cudaFree(c->q); cudaFree(c->dq); cudaFree(c->alpha); cudaFree(c->ddq);
-  cudaFree(c->s_in); cudaFree(c->s_out); cudaFree(c->status); cudaFree(c->gate);
-  for (int i = 0; i < 4; ++i) cudaStreamDestroy(c->streams[i]);
-  cudaEventDestroy(c->fork);
-  for (int i = 0; i < 4; ++i) cudaEventDestroy(c->join[i]);
+  cudaFree(c->arena);     // cudaFree(nullptr) is a no-op
+  cudaFree(c->gate);
+  for (int i = 0; i < 4; ++i) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  if (c->fork) cudaEventDestroy(c->fork);
+  for (int i = 0; i < 4; ++i) if (c->join[i]) cudaEventDestroy(c->join[i]);
+  cudaGetLastError();
   delete c;
   return ATACOM_OK;
+}
+
+int atacom_circle_step_host(AtacomHostCtx* c, const float* q, const float* dq, const float* s_in, const float* alpha,
+                            float* ddq, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p) {
+  return step_host<CircleEnv>(c, 1, q, dq, s_in, alpha, ddq, s_out, status, B, p);
+}
+
+int atacom_planar_step_host(AtacomHostCtx* c, const float* q, const float* dq, const float* s_in, const float* alpha,
+                            float* ddq, float* s_out, uint8_t* status, int64_t B, const AtacomParams* p) {
+  return step_host<PlanarEnv>(c, 2, q, dq, s_in, alpha, ddq, s_out, status, B, p);
 }
 
 int atacom_iiwa_step_host(AtacomHostCtx* c, int n, const float* q, const float* dq, const float* s_in,
                           const float* alpha, float* ddq, float* s_out, uint8_t* status, int64_t B,
                           const AtacomParams* p) {
-  if (!c || !p || !q || !dq || !s_in || !alpha || !ddq || !s_out) return ATACOM_ERR_NULL_POINTER;
-  if (n != 6 && n != 7) return ATACOM_ERR_BAD_DIMS;
-  if (B < 0 || B > c->max_B) return ATACOM_ERR_BAD_DIMS;
-  int rc = check_common(B, p);
-  if (rc) return rc;
-  if (B == 0) return ATACOM_OK;
-  float* out_ddq = nullptr;
-  float* out_s = nullptr;
-  uint8_t* out_status = nullptr;
-  if (c->mode == ATACOM_HOST_HYBRID) {
-    // hybrid: inputs through the copy engines (large PCIe reads), outputs stored by the kernels straight into
-    // the caller's mapped buffers — no D2H stage at the end of the pipeline
-    out_ddq = static_cast<float*>(mapped_alias(ddq));
-    out_s = static_cast<float*>(mapped_alias(s_out));
-    out_status = status ? static_cast<uint8_t*>(mapped_alias(status)) : nullptr;
-    if (!out_ddq || !out_s || (status && !out_status)) return ATACOM_ERR_BAD_PARAM;
-  }
-  if (c->mode == ATACOM_HOST_ZERO_COPY || c->mode == ATACOM_HOST_AUTO) {
-    // zero-copy: one launch on the device aliases of the caller's buffers; loads and stores cross PCIe
-    void* d[7] = {mapped_alias(q), mapped_alias(dq), mapped_alias(s_in), mapped_alias(alpha), mapped_alias(ddq),
-                  mapped_alias(s_out), status ? mapped_alias(status) : nullptr};
-    const bool all = d[0] && d[1] && d[2] && d[3] && d[4] && d[5] && (!status || d[6]);
-    if (!all && c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
-    if (all) {
-    const float *zq = static_cast<const float*>(d[0]), *zdq = static_cast<const float*>(d[1]);
-    const float *zs = static_cast<const float*>(d[2]), *za = static_cast<const float*>(d[3]);
-    float *zddq = static_cast<float*>(d[4]), *zso = static_cast<float*>(d[5]);
-    uint8_t* zst = static_cast<uint8_t*>(d[6]);
-    constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
-    rc = n == 6 ? launch_step<IiwaEnv<6>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0],
-                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window, c->zc_tpb)
-                : launch_step<IiwaEnv<7>, HOST_IO>(zq, zdq, zs, za, zddq, zso, zst, nullptr, B, p, c->streams[0],
-                                                   nullptr, 0, 0, nullptr, nullptr, 0, c->gate, c->zc_window, c->zc_tpb);
-    if (rc != ATACOM_OK) return rc;
-    if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
-    return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
-    }
-  }
-  const void* key[7] = {q, dq, s_in, alpha, ddq, s_out, status};
-  bool hit = c->exec != nullptr && c->key_B == B && c->key_n == n &&
-             memcmp(&c->key_params, p, sizeof(AtacomParams)) == 0;
-  for (int i = 0; i < 7 && hit; ++i) hit = c->key_ptr[i] == key[i];
-  if (!hit) {
-    if (c->exec) {
-      cudaGraphExecDestroy(c->exec);
-      c->exec = nullptr;
-    }
-    // capture: stream 0 is the origin, the others fork from it and join back
-    cudaGraph_t graph = nullptr;
-    const int ns = c->chunks < 4 ? c->chunks : 4;
-    bool ok = cudaStreamBeginCapture(c->streams[0], cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    if (ok) {
-      cudaEventRecord(c->fork, c->streams[0]);
-      for (int i = 1; i < ns; ++i) cudaStreamWaitEvent(c->streams[i], c->fork, 0);
-      const int64_t before = g_launches.load(std::memory_order_relaxed);
-      rc = host_pipeline(c, n, q, dq, s_in, alpha, ddq, s_out, status, B, p, ns, out_ddq, out_s, out_status);
-      c->key_launches = static_cast<int>(g_launches.exchange(before, std::memory_order_relaxed) - before);   // captured, not run
-      for (int i = 1; i < ns; ++i) {
-        cudaEventRecord(c->join[i], c->streams[i]);
-        cudaStreamWaitEvent(c->streams[0], c->join[i], 0);
-      }
-      ok = cudaStreamEndCapture(c->streams[0], &graph) == cudaSuccess && graph != nullptr && rc == ATACOM_OK;
-    }
-    if (ok) ok = cudaGraphInstantiate(&c->exec, graph, 0) == cudaSuccess;
-    if (graph) cudaGraphDestroy(graph);
-    if (!ok) {
-      cudaGetLastError();
-      c->exec = nullptr;
-      return rc != ATACOM_OK ? rc : ATACOM_ERR_CUDA;
-    }
-    for (int i = 0; i < 7; ++i) c->key_ptr[i] = key[i];
-    c->key_B = B;
-    c->key_n = n;
-    c->key_params = *p;
-  }
-  if (cudaGraphLaunch(c->exec, c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
-  g_launches.fetch_add(c->key_launches, std::memory_order_relaxed);   // kernel launches inside the replayed graph
-  if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
-  return cudaGetLastError() == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+  if (n == 6) return step_host<IiwaEnv<6>>(c, 3, q, dq, s_in, alpha, ddq, s_out, status, B, p);
+  if (n == 7) return step_host<IiwaEnv<7>>(c, 3, q, dq, s_in, alpha, ddq, s_out, status, B, p);
+  return ATACOM_ERR_BAD_DIMS;
 }
+
+int atacom_point_reach_step_host(AtacomHostCtx* c, int n_objects, const float* q, const float* dq, const float* obs_p,
+                                 const float* obs_dp, const float* s_in, const float* action, float* w, float* s_out,
+                                 uint8_t* status, int64_t B, const AtacomParams* p) {
+  if (!c || !p || !q || !dq || !obs_p || !obs_dp || !s_in || !action || !w || !s_out) return ATACOM_ERR_NULL_POINTER;
+  if (n_objects < 1 || n_objects > 8) return ATACOM_ERR_BAD_DIMS;
+  if (c->mode == ATACOM_HOST_ZERO_COPY || c->mode == ATACOM_HOST_HYBRID) return ATACOM_ERR_BAD_PARAM;   // staged only
+  const size_t G = static_cast<size_t>(n_objects);
+  HostCall call = {};
+  call.key[0] = 4;
+  call.key[1] = n_objects;
+  call.n_in = 6;
+  call.n_out = 3;
+  call.in[0] = {q, 8};
+  call.in[1] = {dq, 8};
+  call.in[2] = {obs_p, 8 * G};
+  call.in[3] = {obs_dp, 8 * G};
+  call.in[4] = {s_in, 4 * G};
+  call.in[5] = {action, 8};
+  call.out[0] = {w, 8};
+  call.out[1] = {s_out, 4 * G};
+  call.out[2] = {status, 1};
+  call.launch = host_launch_point;
+  return host_call(c, call, B, p);
+}
+
+int atacom_generic_step_host(AtacomHostCtx* c, int n, int F, int G, const float* cc, const float* J, const float* b,
+                             const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
+                             uint8_t* status, int64_t B, const AtacomParams* p) {
+  if (!c || !p) return ATACOM_ERR_NULL_POINTER;
+  if (!atacom_generic_supported(n, F, G)) return ATACOM_ERR_BAD_DIMS;
+  const int na = p->variant == ATACOM_VARIANT_ERROR_CORRECTION ? n : n - F;
+  if (!cc || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out)) || (na > 0 && !alpha)) return ATACOM_ERR_NULL_POINTER;
+  if (c->mode == ATACOM_HOST_ZERO_COPY || c->mode == ATACOM_HOST_HYBRID) return ATACOM_ERR_BAD_PARAM;   // staged only
+  const size_t C = static_cast<size_t>(F + G);
+  HostCall call = {};
+  call.key[0] = 5;
+  call.key[1] = n;
+  call.key[2] = F;
+  call.key[3] = G;
+  call.n_in = 6;
+  call.n_out = 3;
+  call.in[0] = {cc, 4 * C};
+  call.in[1] = {J, 4 * C * static_cast<size_t>(n)};
+  call.in[2] = {b, 4 * C};
+  call.in[3] = {dq, 4 * static_cast<size_t>(n)};
+  call.in[4] = {G > 0 ? s_in : nullptr, 4 * static_cast<size_t>(G)};
+  call.in[5] = {na > 0 ? alpha : nullptr, 4 * static_cast<size_t>(na)};
+  call.out[0] = {ddq, 4 * static_cast<size_t>(n)};
+  call.out[1] = {G > 0 ? s_out : nullptr, 4 * static_cast<size_t>(G)};
+  call.out[2] = {status, 1};
+  call.launch = host_launch_generic;
+  return host_call(c, call, B, p);
+}
+
+int atacom_spin_timeouts(unsigned* out) {
+  if (!out) return ATACOM_ERR_NULL_POINTER;
+  return cudaMemcpyFromSymbol(out, g_spin_timeouts, sizeof(unsigned)) == cudaSuccess ? ATACOM_OK : ATACOM_ERR_CUDA;
+}
+
 
 }  // extern "C"

@@ -41,13 +41,18 @@ class JointSpaceEnv:
     def seed(self, seed):
         torch.manual_seed(int(seed))
 
-    def reset(self, state=None):
+    def reset(self, state=None, mask=None):
+        """mask (bool [B], optional): re-initialise only those environments (per-env episode termination)."""
         if state is not None:
-            self._state = torch.as_tensor(state, dtype=torch.float32, device=self.device).reshape(self.n_envs, -1).clone()
+            new = torch.as_tensor(state, dtype=torch.float32, device=self.device).reshape(self.n_envs, -1).clone()
         else:
-            st = torch.zeros(self.n_envs, 6 + 2 * self.n, device=self.device)
-            st[:, 6:6 + self.n] = self._q_init
-            self._state = st
+            new = torch.zeros(self.n_envs, 6 + 2 * self.n, device=self.device)
+            new[:, 6:6 + self.n] = self._q_init
+        if mask is None or self._state is None:
+            self._state = new
+        else:
+            m = torch.as_tensor(mask, device=self.device).bool()
+            self._state[m] = new[m]
         return self._state
 
     def step(self, action):
@@ -77,7 +82,7 @@ class AirHockeyIiwaAtacom(AtacomEnvWrapper):
     """iiwa_hit_atacom.py:10-63.  n_ctrl_joints = 6 reproduces isolated_joint_7=True (env_single.py:17-18)."""
 
     def __init__(self, task='H', gamma=0.99, horizon=120, timestep=1 / 240., n_intermediate_steps=4, Kc=240.,
-                 n_ctrl_joints=6, base_env=None, n_envs=1, device=None, bias_mode=_lib.BIAS_JDOT_QDOT):
+                 n_ctrl_joints=6, base_env=None, n_envs=1, device=None, bias_mode=_lib.BIAS_OMEGA_X_V):
         if task != 'H':
             raise NotImplementedError                    # iiwa_hit_atacom.py:20-21
         n = n_ctrl_joints
@@ -106,17 +111,13 @@ class AirHockeyIiwaAtacom(AtacomEnvWrapper):
     def acc_to_ctrl_action(self, ddq):
         return ddq
 
-    def _update_constraint_stats(self, q, dq):
-        vel_max = torch.as_tensor(self.vel_max, dtype=dq.dtype, device=dq.device)
-        c_dq_i = (dq.abs() - vel_max).max(1).values
-        self.constr_logs.append(torch.stack([torch.full_like(c_dq_i, float("nan")), c_dq_i], 1))
 
 
 class AirHockeyPlanarAtacom(AtacomEnvWrapper):
     """atacom_air_hockey.py:11-76 (planar 3R arm; URDF constants are parameters)."""
 
     def __init__(self, task='H', gamma=0.99, horizon=120, timestep=1 / 240., n_intermediate_steps=4, Kc=240.,
-                 base_env=None, n_envs=1, device=None, bias_mode=_lib.BIAS_JDOT_QDOT):
+                 base_env=None, n_envs=1, device=None, bias_mode=_lib.BIAS_OMEGA_X_V):
         p = _lib.default_params("planar")
         if base_env is None:
             base_env = JointSpaceEnv(3, (-1.0, 1.6, 0.5), gamma, horizon, timestep, n_intermediate_steps, n_envs, device)
@@ -137,8 +138,3 @@ class AirHockeyPlanarAtacom(AtacomEnvWrapper):
 
     def acc_to_ctrl_action(self, ddq):
         return ddq
-
-    def _update_constraint_stats(self, q, dq):
-        vel_max = torch.as_tensor(self.vel_max, dtype=dq.dtype, device=dq.device)
-        c_dq_i = (dq.abs() - vel_max).max(1).values
-        self.constr_logs.append(torch.stack([torch.full_like(c_dq_i, float("nan")), c_dq_i], 1))

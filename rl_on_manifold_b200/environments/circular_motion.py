@@ -39,7 +39,15 @@ class CircularMotion:
     def seed(self, seed):
         self._gen.manual_seed(int(seed))
 
-    def reset(self, state=None):
+    def reset(self, state=None, mask=None):
+        """mask (bool [B], optional): re-initialise only those environments (per-env episode termination)."""
+        if mask is not None and self._state is not None:
+            old = self._state
+            new = CircularMotion.reset(self, state).clone()
+            m = torch.as_tensor(mask, device=self.device).bool()
+            old[m] = new[m]
+            self._state = old
+            return self._state
         B = self.n_envs
         if state is None:
             if self.random_init:                         # circle_base.py:39-45
@@ -112,7 +120,12 @@ class CircularMotion:
             v = self._stats.cpu().tolist()
             total, n, c_max, c_dq_max = total + v[0], n + int(v[3]), max(c_max, v[1]), max(c_dq_max, v[2])
             self._stats = None
+        if self.shard is not None:                                     # one all-reduce per epoch
+            from ..sharding import reduce_constraint_logs
+            total, n, c_max, c_dq_max = reduce_constraint_logs(total, n, c_max, c_dq_max, self.shard.group)
         return total / max(n, 1), c_max, c_dq_max
+
+    shard = None            # sharding.EnvShard when this env holds one rank's slice of a global batch
 
 
 def _circle_sets():

@@ -40,7 +40,17 @@ class PointGoalReach:
     def seed(self, seed):
         self._gen.manual_seed(int(seed))
 
-    def reset(self, state=None):
+    def reset(self, state=None, mask=None):
+        """mask (bool [B], optional): re-initialise only those environments (per-env episode termination); the
+        obstacles' clock `_time` is shared by the batch and restarts only on a full reset."""
+        if mask is not None and self._state is not None:
+            old, old_c, t = self._state, self._obj_circle_center, self._time
+            new = PointGoalReach.reset(self, state)
+            m = torch.as_tensor(mask, device=self.device).bool()
+            old[m] = new[m]
+            old_c[m] = self._obj_circle_center[m]
+            self._state, self._obj_circle_center, self._time = old, old_c, t
+            return self._state
         self._time = 0.
         B, G = self.n_envs, self.n_objects
         st = torch.zeros(B, self.state_dim)
@@ -120,10 +130,11 @@ class PointReachAtacom(PointGoalReach):
         return (state[:, :2].contiguous(), state[:, 2:4].contiguous(),
                 obj[:, :, :2].reshape(B, -1).contiguous(), obj[:, :, 2:].reshape(B, -1).contiguous())
 
-    def reset(self, state=None):
-        super().reset(state)
+    def reset(self, state=None, mask=None):
+        super().reset(state, mask)
         self.q, self.dq, self.p, self.dp = self._split(self._state)
-        projection.point_reach_slack_init(self.q, self.p, self.params, s=self.s)      # :25
+        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        projection.point_reach_slack_init(self.q, self.p, self.params, s=self.s, mask=m)      # :25
         return self._state
 
     def step(self, action):
@@ -174,4 +185,9 @@ class PointReachAtacom(PointGoalReach):
             v = self._stats.cpu().tolist()
             total, n, c_max = total + v[0], n + int(v[3]), max(c_max, v[1])
             self._stats = None
+        if self.shard is not None:                                     # one all-reduce per epoch
+            from ..sharding import reduce_constraint_logs
+            total, n, c_max, c_dq_max = reduce_constraint_logs(total, n, c_max, c_dq_max, self.shard.group)
         return total / max(n, 1), c_max, c_dq_max
+
+    shard = None            # sharding.EnvShard when this env holds one rank's slice of a global batch

@@ -339,7 +339,7 @@ def point_reach_rollout(state, s, actions, params, *, obstacle_draws=None, obsta
 
 
 class HostContext:
-    """Host-buffer entry point (`atacom_iiwa_step_host`): NumPy / pinned-tensor in, NumPy out,
+    """Host-buffer entry points (`atacom_*_step_host`): NumPy / pinned-tensor in, NumPy out,
     copies inside the call — what a caller of the NumPy reference binds."""
 
     MODES = {"auto": _lib.HOST_AUTO, "staged": _lib.HOST_STAGED, "zero_copy": _lib.HOST_ZERO_COPY,
@@ -355,12 +355,53 @@ class HostContext:
         _lib.check(_lib.lib.atacom_host_ctx_set_mode(self._ctx, self.MODES[mode]))
         self.max_B = max_B
 
+    @staticmethod
+    def _hptr(t):
+        """Host pointer of a (pinned or pageable) CPU tensor or a NumPy array."""
+        if t is None:
+            return None
+        if hasattr(t, "data_ptr"):
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError("host entry points take contiguous CPU tensors / NumPy arrays")
+            return ctypes.c_void_p(t.data_ptr())
+        if not t.flags["C_CONTIGUOUS"]:
+            raise ValueError("host entry points take C-contiguous NumPy arrays")
+        return ctypes.c_void_p(t.ctypes.data)
+
     def iiwa_step(self, n, q, dq, s, alpha, ddq, s_out, params, status=None):
-        B = q.shape[0]
-        ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() if hasattr(t, "data_ptr")
-                                                               else t.ctypes.data)
-        _lib.check(_lib.lib.atacom_iiwa_step_host(self._ctx, n, ptr(q), ptr(dq), ptr(s), ptr(alpha), ptr(ddq),
-                                                  ptr(s_out), ptr(status), B, ctypes.byref(params)))
+        p = self._hptr
+        _lib.check(_lib.lib.atacom_iiwa_step_host(self._ctx, n, p(q), p(dq), p(s), p(alpha), p(ddq), p(s_out),
+                                                  p(status), q.shape[0], ctypes.byref(params)))
+        return ddq, s_out
+
+    def step(self, family, q, dq, s, alpha, ddq, s_out, params, status=None, n_ctrl_joints=6):
+        """`projection.step` on host arrays: family in {"circle", "planar", "iiwa"}."""
+        p = self._hptr
+        args = (p(q), p(dq), p(s), p(alpha), p(ddq), p(s_out), p(status), q.shape[0], ctypes.byref(params))
+        if family == "circle":
+            rc = _lib.lib.atacom_circle_step_host(self._ctx, *args)
+        elif family == "planar":
+            rc = _lib.lib.atacom_planar_step_host(self._ctx, *args)
+        elif family.startswith("iiwa"):
+            rc = _lib.lib.atacom_iiwa_step_host(self._ctx, n_ctrl_joints, *args)
+        else:
+            raise ValueError(family)
+        _lib.check(rc)
+        return ddq, s_out
+
+    def point_reach_step(self, q, dq, obs_p, obs_dp, s, action, w, s_out, params, status=None):
+        """`projection.point_reach_step` on host arrays (PointReachAtacom.step, collision_avoidance_atacom.py:29-47)."""
+        p = self._hptr
+        _lib.check(_lib.lib.atacom_point_reach_step_host(self._ctx, s.shape[1], p(q), p(dq), p(obs_p), p(obs_dp), p(s),
+                                                         p(action), p(w), p(s_out), p(status), q.shape[0],
+                                                         ctypes.byref(params)))
+        return w, s_out
+
+    def generic_step(self, n, F, G, c, J, b, dq, s, alpha, ddq, s_out, params, status=None):
+        """`projection.generic_step` on host arrays (a ConstraintsSet evaluated batched in NumPy)."""
+        p = self._hptr
+        _lib.check(_lib.lib.atacom_generic_step_host(self._ctx, n, F, G, p(c), p(J), p(b), p(dq), p(s), p(alpha),
+                                                     p(ddq), p(s_out), p(status), dq.shape[0], ctypes.byref(params)))
         return ddq, s_out
 
     def close(self):

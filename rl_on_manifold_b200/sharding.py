@@ -17,6 +17,34 @@ def shard_bounds(global_B, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def reduce_constraint_logs(total, count, c_max, c_dq_max, group=None):
+    """Cross-rank merge of one epoch's constraint log (atacom.py:207-216 over the GLOBAL batch): SUM on (sum of
+    c_i, number of samples), MAX on (max c_i, max c_dq_i) — two small all-reduces per epoch, nothing per step.
+    Returns (total, count, c_max, c_dq_max) of the whole job; a no-op without an initialised process group."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return total, count, c_max, c_dq_max
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    sums = torch.tensor([float(total), float(count)], dtype=torch.float64, device=dev)
+    maxs = torch.tensor([float(c_max), float(c_dq_max)], dtype=torch.float64, device=dev)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    s, m = sums.tolist(), maxs.tolist()
+    return s[0], int(round(s[1])), m[0], m[1]
+
+
+def reduce_stats(stats, group=None):
+    """The same for the kernels' device accumulators `stats` [4] = { sum, max c, max c_dq, count }
+    (projection.new_stats; atacom_*_constraint_stats, fused roll-outs): reduced in place across the ranks."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return stats
+    t = stats if (stats.is_cuda == (dist.get_backend(group) == "nccl")) else stats.cpu()
+    sums, maxs = t[[0, 3]].clone(), t[[1, 2]].clone()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    stats[0], stats[3], stats[1], stats[2] = sums[0], sums[1], maxs[0], maxs[1]
+    return stats
+
+
 class EnvShard:
     def __init__(self, global_B, rank=None, world=None, group=None):
         self.group = group

@@ -97,7 +97,7 @@ def oracle_spec(family):
     raise ValueError(family)
 
 
-def oracle_eval(family, q, dq, bias="jdot_qdot"):
+def oracle_eval(family, q, dq, bias="omega_x_v"):
     if family == "circle":
         return oenv.circle_eval(q, dq)
     if family == "planar":
@@ -105,7 +105,7 @@ def oracle_eval(family, q, dq, bias="jdot_qdot"):
     return oenv.iiwa_eval(q, dq, bias)
 
 
-def oracle_batch(family, q, dq, s, alpha, basis="canonical", variant="atacom", bias="jdot_qdot", spec=None):
+def oracle_batch(family, q, dq, s, alpha, basis="canonical", variant="atacom", bias="omega_x_v", spec=None):
     """Run the per-env oracle over a batch (float64 views of the fp32 inputs).  Returns dict of arrays
     plus per-env flags: fired (tolerance branch), rank_def, margin (distance of the closest pivot
     candidate to the tolerance, relative)."""

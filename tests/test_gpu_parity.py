@@ -116,11 +116,11 @@ def test_error_correction_variant(cuda_device, family):
 
 
 @pytest.mark.parametrize("family", ["planar", "iiwa6"])
-def test_bias_mode_omega_cross_v(cuda_device, family):
+def test_bias_mode_jdot_qdot(cuda_device, family):
     q, dq, s, alpha = helpers.synthetic_cpu(family, 256, seed=3)
-    ref = helpers.oracle_batch(family, q, dq, s, alpha, bias="omega_x_v")
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, bias="jdot_qdot")
     p = _params(family)
-    p.bias_mode = _lib.BIAS_OMEGA_X_V
+    p.bias_mode = _lib.BIAS_JDOT_QDOT      # opt-in "corrected" mode: the full dJ/dt dq
     ddq, s_out, _, _ = _run(family, q, dq, s, alpha, p, cuda_device, dbg=False)
     ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
     assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[ok].all()

@@ -97,11 +97,11 @@ def test_error_correction_variant(harness, family):
 
 
 @pytest.mark.parametrize("family", ["planar", "iiwa6", "iiwa7"])
-def test_bias_mode_omega_cross_v(harness, family):
+def test_bias_mode_jdot_qdot(harness, family):
     q, dq, s, alpha = helpers.synthetic_cpu(family, 100, seed=3)
-    ref = helpers.oracle_batch(family, q, dq, s, alpha, bias="omega_x_v")
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, bias="jdot_qdot")
     p = _params(family)
-    p.bias_mode = _lib.BIAS_OMEGA_X_V
+    p.bias_mode = _lib.BIAS_JDOT_QDOT      # opt-in "corrected" mode: the full dJ/dt dq
     ddq, s_out, dbg, st = helpers.harness_step(harness, family, p.flat(), q, dq, s, alpha, np.float64)
     ok = ~ref["rank_def"]
     assert helpers.rel_err(ddq, ref["ddq"])[ok].max() < 1e-6      # params are fp32-rounded constants
