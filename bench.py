@@ -2,19 +2,28 @@
 """Benchmark of the batched ATACOM projection step (BASELINE.json metric: env-steps/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload iiwa|circle|planar|point_reach] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one projection (AtacomEnvWrapper.step_action_function, atacom/atacom.py:123-139) of a
-batch of B = 65 536 IiwaAirHockey-7H environments (n=6, F=1, G=11) per GPU.  Weak scaling: every rank
-owns its own 65 536 environments; at N > 1 each step ends with one NCCL all-gather of the projected
-accelerations ddq.  Rank 0 prints one JSON line.
+One "step" = one projection (AtacomEnvWrapper.step_action_function, atacom/atacom.py:123-139) of one batch of
+environments.  Default workload (the one the metric is quoted on, BASELINE.json configs[3]): B = 65 536
+IiwaAirHockey-7H environments (n=6, F=1, G=11) per GPU (weak scaling) or in total (--scaling strong: 65 536 / N per
+GPU); at N > 1 each step ends with the gather of the projected accelerations ddq, fused into the
+kernel epilogue over NVLink symmetric memory.  The other workloads are BASELINE.json's configs[1], [2], [4].
+Rank 0 prints ONE JSON line.
 
---impl reference times the reference's own per-environment NumPy path (the float64 oracle port of it,
-oracle/atacom_oracle.py — the reference itself is Python and cannot travel to the GPU box) on all host
-cores, on bounded samples of the same workload.
+Timing: the K steps are captured in CUDA graphs over a ring of distinct input batches larger than 2x L2 (every
+step reads cold data); R >= 5 replays of exactly K steps are timed with CUDA events, each bracketed by a barrier and
+a device synchronisation, max over ranks per replay; `value` is computed from the MEDIAN replay (the minimum is
+reported beside it).
+
+--impl reference times the reference's own CPU implementation on all host cores: for the default workload the
+UNMODIFIED reference package (baseline/_ref, staged by baseline/stage_reference.py) driven through
+AtacomEnvWrapper.step_action_function (baseline/reference_driver.py); the oracle port otherwise.
 """
 import argparse
 import json
+import math
 import multiprocessing as mp
 import os
 import statistics
@@ -29,25 +38,40 @@ if ROOT not in sys.path:
 
 METRIC = "atacom_projection_env_steps_per_sec"
 UNIT = "env-steps/s"
-BATCH_PER_GPU = 65536
-N_JOINTS = 6
-DIMS = dict(n=6, F=1, G=11, k=5)
-# algorithmic bytes per env-step, fp32, inputs read once + outputs written once:
-# q6 + dq6 + s11 + alpha5 = 28 floats in, ddq6 + s11 = 17 floats out
-BYTES_IN, BYTES_OUT = 28 * 4, 17 * 4
-BYTES_PER_ENV_STEP = BYTES_IN + BYTES_OUT
 L2_BYTES = 126 * 1024 * 1024
 
+# algorithmic bytes per env-step, fp32, inputs read once + outputs written once
+WORKLOADS = {
+    "iiwa": dict(name="IiwaAirHockey-7H projection (n=6,F=1,G=11)", batch=65536, floats_in=28, floats_out=17,
+                 kernel="atacom_step_kernel<IiwaEnv<6>>", out_dim=6),
+    "circle": dict(name="CircularMotion env A projection (n=2,F=1,G=1)", batch=4096, floats_in=6, floats_out=3,
+                   kernel="atacom_step_kernel<CircleEnv>", out_dim=2),
+    "planar": dict(name="PlanarAirHockey env H projection (n=3,F=0,G=6)", batch=16384, floats_in=15, floats_out=9,
+                   kernel="atacom_step_kernel<PlanarEnv>", out_dim=3),
+    "point_reach": dict(name="CollisionAvoidance env C projection (n=2,G=4 obstacles)", batch=65536, floats_in=26,
+                        floats_out=6, kernel="point_reach_step_kernel<4>", out_dim=2),
+}
+N_JOINTS = 6
 
-def workload_name(n_gpus):
-    return "IiwaAirHockey-7H projection (n=6,F=1,G=11), batch %d per GPU x %d GPU" % (BATCH_PER_GPU, n_gpus)
+
+def workload_label(wl, B, n_gpus, scaling):
+    return "%s, batch %d per GPU x %d GPU (%s scaling)" % (WORKLOADS[wl]["name"], B, n_gpus, scaling)
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def local_batch(args):
+    B = args.batch or WORKLOADS[args.workload]["batch"]
+    if args.scaling == "strong":
+        if B % args.gpus:
+            raise SystemExit("--scaling strong: the global batch %d is not divisible by %d GPUs" % (B, args.gpus))
+        B //= args.gpus
+    return B
 
-def _cpu_worker(args):
-    """Per-environment float64 NumPy path, the way the reference runs it (SVD + rref per call)."""
-    q, dq, s, alpha, reps = args
+
+# ----------------------------------------------------------------------------- CPU arms
+
+def _port_worker(task):
+    """Oracle port (float64 NumPy restatement, oracle/), one environment per call; callbacks' values precomputed."""
+    wl, arrays, reps = task
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(1)
@@ -55,88 +79,152 @@ def _cpu_worker(args):
         limiter = None
     from oracle import atacom_oracle as ao
     from oracle import envs as oenv
-    spec = oenv.iiwa_spec(N_JOINTS)
-    # The reference evaluates its constraint callbacks through pinocchio (C++), which is not available;
-    # the oracle's NumPy kinematics would be ~10x slower than that, so the callbacks' values are
-    # computed beforehand and only the wrapper + linear algebra is timed (this favours the CPU side).
-    evs = [oenv.iiwa_eval(q[i], dq[i]) for i in range(q.shape[0])]
-    t0 = time.perf_counter()
+    m = arrays[0].shape[0]
     acc = 0.0
+    if wl == "point_reach":
+        q, dq, p, dp, s, act = arrays
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for i in range(m):
+                acc += ao.point_reach_step(q[i], dq[i], p[i].reshape(-1, 2), dp[i].reshape(-1, 2), s[i], act[i])["w"][0]
+        return time.perf_counter() - t0, acc
+    q, dq, s, alpha = arrays
+    spec = dict(iiwa=lambda: oenv.iiwa_spec(N_JOINTS), circle=oenv.circle_spec, planar=oenv.planar_spec)[wl]()
+    ev_fn = dict(iiwa=oenv.iiwa_eval, circle=oenv.circle_eval, planar=oenv.planar_eval)[wl]
+    evs = [ev_fn(q[i], dq[i]) for i in range(m)]
+    t0 = time.perf_counter()
     for _ in range(reps):
-        for i in range(q.shape[0]):
-            out = ao.atacom_step(spec, evs[i], dq[i], s[i], alpha[i], basis="svd")
-            acc += out["ddq"][0]
+        for i in range(m):
+            acc += ao.atacom_step(spec, evs[i], dq[i], s[i], alpha[i], basis="svd")["ddq"][0]
     dt = time.perf_counter() - t0
     del limiter
     return dt, acc
 
 
-def _cpu_sample(n_envs, seed):
+def _port_sample(wl, n_envs, seed):
+    """Seeded inputs of a workload as float64 NumPy arrays (slacks from the oracle's reset rule + the mix).
+    Loads the pure input generator by path: no product code in a CPU arm."""
     import numpy as np
+    import torch
+    from baseline import reference_driver as rd
     from oracle import atacom_oracle as ao
     from oracle import envs as oenv
-    from rl_on_manifold_b200 import synthetic
-    import torch
-    q, dq, alpha = synthetic.state_batch("iiwa", n_envs, seed, N_JOINTS)
-    q, dq, alpha = (t.double().numpy() for t in (q, dq, alpha))
-    spec = oenv.iiwa_spec(N_JOINTS)
-    s = np.stack([ao.slack_init(spec, oenv.iiwa_eval(q[i], dq[i]), dq[i]) for i in range(n_envs)])
-    s = synthetic.slack_mix(torch.from_numpy(s.astype(np.float32)), seed).double().numpy()
+    inputs = rd.load_inputs_module()
+    if wl == "point_reach":
+        q, dq, p, dp, act = (t.double().numpy() for t in inputs.point_reach_batch(n_envs, seed, 4))
+        s = np.stack([ao.point_reach_slack_init(q[i], p[i].reshape(-1, 2)) for i in range(n_envs)])
+        return q, dq, p, dp, s.astype(np.float32).astype(np.float64), act
+    q, dq, alpha = (t.double().numpy() for t in inputs.state_batch(wl, n_envs, seed, N_JOINTS))
+    spec = dict(iiwa=lambda: oenv.iiwa_spec(N_JOINTS), circle=oenv.circle_spec, planar=oenv.planar_spec)[wl]()
+    ev_fn = dict(iiwa=oenv.iiwa_eval, circle=oenv.circle_eval, planar=oenv.planar_eval)[wl]
+    s = np.stack([ao.slack_init(spec, ev_fn(q[i], dq[i]), dq[i]) for i in range(n_envs)])
+    s = inputs.slack_mix(torch.from_numpy(s.astype(np.float32)), seed).double().numpy()
     return q, dq, s, alpha
 
 
-def cpu_env_steps_per_sec(pool, cores, sample, reps=1):
-    """Run one bounded sample (`reps` passes over it) split over `cores` processes; returns
-    (env-steps/s, seconds of the slowest worker's timed loop)."""
+PORT_DESC = ("float64 oracle port of atacom.py:123-139 (SciPy SVD + rref per env; constraint callbacks' values "
+             "precomputed), %d processes x 1 thread")
+
+
+def port_env_steps_per_sec(pool, cores, wl, sample, reps=1):
     import numpy as np
-    q, dq, s, alpha = sample
-    idx = np.array_split(np.arange(q.shape[0]), cores)
-    res = pool.map(_cpu_worker, [(q[i], dq[i], s[i], alpha[i], reps) for i in idx])
-    wall = max(r[0] for r in res)
-    return reps * q.shape[0] / wall, wall
+    idx = np.array_split(np.arange(sample[0].shape[0]), cores)
+    t0 = time.perf_counter()
+    pool.map(_port_worker, [(wl, tuple(a[i] for a in sample), reps) for i in idx])
+    wall = time.perf_counter() - t0
+    return reps * sample[0].shape[0] / wall, wall
 
 
-def run_cpu_baseline(envs_per_core=256, reps=24):
+def run_cpu_baseline(wl, budget_s=12.0):
+    """The CPU path beside the GPU line, on a bounded sample (about `budget_s` seconds of all host cores).  Default
+    workload: the reference itself (kind "reference") with the oracle port's number beside it; else the port."""
+    from baseline import reference_driver as rd
     cores = os.cpu_count() or 1
-    sample = _cpu_sample(envs_per_core * cores, 1234)
+    out = None
+    if wl == "iiwa" and rd.reference_present():
+        n_envs = 256 * cores
+        pool = rd.ReferencePool(n_envs, seed=1234, n=N_JOINTS, cores=cores)
+        try:
+            pool.step()                                                   # warm the workers
+            wall1, _ = pool.step()
+            passes = max(1, int(math.ceil(budget_s / max(wall1, 1e-3))))
+            wall, _ = pool.step(passes)
+        finally:
+            pool.close()
+        out = dict(value=passes * n_envs / wall, unit=UNIT, cores=cores, kind="reference",
+                   sample="%d passes over the first %d envs of the seed-1234 %s batch through the unmodified "
+                          "reference's AtacomEnvWrapper.step_action_function (baseline/_ref; leaf callbacks return "
+                          "values precomputed by the oracle's NumPy FK, pinocchio absent), %d processes x 1 thread, "
+                          "%.1f s timed" % (passes, n_envs, WORKLOADS[wl]["name"], cores, wall))
+        budget_s = 5.0
+    n_envs = 128 * cores
+    sample = _port_sample(wl, n_envs, 1234)
     with mp.get_context("fork").Pool(cores) as pool:
-        cpu_env_steps_per_sec(pool, cores, tuple(a[:8 * cores] for a in sample))     # warm the workers
-        value, wall = cpu_env_steps_per_sec(pool, cores, sample, reps)
-    return dict(value=value, unit=UNIT, cores=cores, kind="port",
-                sample="%d passes over the first %d envs of the seed-1234 IiwaAirHockey-7H batch, float64 oracle "
-                       "port of atacom.py:123-139 (SciPy SVD + rref per env; constraint callbacks precomputed, "
-                       "pinocchio absent), %d processes x 1 thread, %.1f s timed"
-                       % (reps, envs_per_core * cores, cores, wall))
+        port_env_steps_per_sec(pool, cores, wl, tuple(a[:8 * cores] for a in sample))     # warm the workers
+        _, wall1 = port_env_steps_per_sec(pool, cores, wl, sample)
+        reps = max(1, int(math.ceil(budget_s / max(wall1, 1e-3))))
+        value, wall = port_env_steps_per_sec(pool, cores, wl, sample, reps)
+    port = dict(value=value, unit=UNIT, cores=cores, kind="port",
+                sample="%d passes over the first %d envs of the seed-1234 %s batch, " % (reps, n_envs, WORKLOADS[wl]["name"])
+                       + PORT_DESC % cores + ", %.1f s timed" % wall)
+    if out is None:
+        return port
+    out["port_value"], out["port_sample"] = port["value"], port["sample"]
+    return out
 
 
 def reference_arm(args):
-    """bench.py --impl reference: the reference's CPU path (oracle port) on all host cores."""
+    """bench.py --impl reference: the reference's CPU path on all host cores, same config as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from baseline import reference_driver as rd
+    wl = args.workload
     cores = os.cpu_count() or 1
-    per_step = 128 * cores                              # distinct envs; 4 passes per step
-    sample = _cpu_sample(per_step, 1234)
-    with mp.get_context("fork").Pool(cores) as pool:
-        for _ in range(max(args.warmup, 1)):
-            cpu_env_steps_per_sec(pool, cores, tuple(a[:16 * cores] for a in sample))
-        walls = []
-        for _ in range(args.steps):
-            walls.append(cpu_env_steps_per_sec(pool, cores, sample, 4)[1])
+    B = local_batch(args)
+    # a step = the full batch when the whole run stays within a few minutes, else a bounded sample of it
+    per_step = B
+    budget = 40
+    if args.steps + args.warmup > budget:
+        per_step = max(64 * cores, B * budget // (args.steps + args.warmup))
+    if os.environ.get("ATACOM_REF_ENVS_PER_STEP"):
+        per_step = int(os.environ["ATACOM_REF_ENVS_PER_STEP"])
+    per_step = min(per_step, B)
+    walls = []
+    if wl == "iiwa" and rd.reference_present():
+        kind = "reference"
+        desc = ("%d envs per step%s through the unmodified reference's AtacomEnvWrapper.step_action_function "
+                "(atacom.py:123-139, staged copy under baseline/_ref; leaf callbacks return values precomputed by the "
+                "oracle's NumPy FK — pinocchio absent — so only the reference's wrapper, constraint stacking, SVD and "
+                "rref are timed), float64, %d processes x 1 thread"
+                % (per_step, "" if per_step == B else " (bounded sample of the %d-env batch)" % B, cores))
+        pool = rd.ReferencePool(per_step, seed=1234, n=N_JOINTS, cores=cores)
+        try:
+            for _ in range(args.warmup):
+                pool.step()
+            for _ in range(args.steps):
+                walls.append(pool.step()[0])
+        finally:
+            pool.close()
+    else:
+        kind = "port"
+        desc = "%d envs per step%s, " % (per_step, "" if per_step == B else " (bounded sample of the %d-env batch)" % B) \
+               + PORT_DESC % cores + ("; the reference tree is not staged on this box" if wl == "iiwa" else "")
+        sample = _port_sample(wl, per_step, 1234)
+        with mp.get_context("fork").Pool(cores) as pool:
+            for _ in range(args.warmup):
+                port_env_steps_per_sec(pool, cores, wl, sample)
+            for _ in range(args.steps):
+                walls.append(port_env_steps_per_sec(pool, cores, wl, sample)[1])
     total = sum(walls)
-    per_step *= 4
     value = per_step * args.steps / total
-    desc = ("%d envs per step (bounded sample of the %d-env batch), float64 oracle port of atacom.py:123-139 "
-            "(SciPy SVD + rref per env; constraint callbacks precomputed, pinocchio absent), "
-            "%d processes x 1 thread" % (per_step, BATCH_PER_GPU, cores))
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=workload_name(args.gpus), sample=desc),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=desc),
-                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
-    emit(line)
+    cfg = dict(workload=workload_label(wl, B, args.gpus, args.scaling), batch_per_gpu=B, global_batch=B * args.gpus,
+               envs_per_step=per_step, sample=desc)
+    emit(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+              ms_per_step=1e3 * statistics.median(walls), higher_is_better=True, scaling=args.scaling, vs_baseline=None,
+              dtype="f64", data="synthetic", impl="reference", config=cfg,
+              cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=desc),
+              e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -196,10 +284,16 @@ def ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run" % (args.gpus, world))
+    wl = args.workload
+    W = WORKLOADS[wl]
+    B = local_batch(args)
+    bytes_in, bytes_out = 4 * W["floats_in"], 4 * W["floats_out"]
+    bytes_env = bytes_in + bytes_out
+    K = args.steps
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_cpu_baseline()               # before CUDA is initialised (fork-safe)
+        cpu_baseline = run_cpu_baseline(wl)             # before CUDA is initialised (fork-safe)
 
     import torch
     import torch.distributed as dist
@@ -213,178 +307,210 @@ def ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
-    n, G, k = DIMS["n"], DIMS["G"], DIMS["k"]
-    params = _lib.default_params("iiwa", N_JOINTS)
-    # a ring of distinct batches whose footprint exceeds L2 twice over: every step's inputs are cold
-    ring = max(2, -(-2 * L2_BYTES // (B * BYTES_PER_ENV_STEP)))
-    sets = []
-    for r in range(ring):
-        q, dq, s, alpha = synthetic.device_batch("iiwa", B, 1234 + rank + 1000 * r, dev, N_JOINTS, params)
-        sets.append(dict(q=q, dq=dq, s=s, alpha=alpha, ddq=torch.empty_like(q), s_out=torch.empty_like(s)))
-    gathered = torch.empty(world * B, n, device=dev) if world > 1 else None
-    fused, fused_note = None, "not attempted"
-    if world > 1 and args.gather == "fused":
+    # ---- inputs: a ring of distinct batches whose footprint exceeds L2 twice over; step (g, i) of graph g uses
+    # slot (g K + i) mod ring, so a slot is only re-read after > 2x L2 of other data went by: every step is cold
+    ring = max(2, -(-2 * L2_BYTES // (B * bytes_env)))
+    n_graphs = max(1, -(-ring // K))
+    n_out = W["out_dim"]
+    fam = wl
+    if wl == "point_reach":
+        params = _lib.default_params("point_reach")
+        q, dq, p, dp, s, act = synthetic.point_reach_device_batch(ring * B, 1234 + rank, dev, 4, params)
+        big = dict(q=q, dq=dq, p=p, dp=dp, s=s, alpha=act)
+    else:
+        params = _lib.default_params("iiwa", N_JOINTS) if wl == "iiwa" else _lib.default_params(wl)
+        q, dq, s, alpha = synthetic.device_batch(fam, ring * B, 1234 + rank, dev, N_JOINTS, params)
+        big = dict(q=q, dq=dq, s=s, alpha=alpha)
+    big["out"] = torch.empty(ring * B, n_out, device=dev)
+    big["s_out"] = torch.empty_like(big["s"])
+    sets = [{k_: v[r * B:(r + 1) * B] for k_, v in big.items()} for r in range(ring)]
+    gathered = torch.empty(world * B, n_out, device=dev) if world > 1 else None
+
+    def kernel_only(i):
+        d = sets[i % ring]
+        if wl == "point_reach":
+            projection.point_reach_step(d["q"], d["dq"], d["p"], d["dp"], d["s"], d["alpha"], params, w=d["out"],
+                                        s_out=d["s_out"])
+        else:
+            projection.step(fam, d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS, ddq=d["out"],
+                            s_out=d["s_out"])
+
+    def step_nccl(i):
+        kernel_only(i)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, sets[i % ring]["out"])
+
+    fused, fused_note = None, None
+    if world > 1 and wl == "iiwa" and args.gather != "nccl":
         try:
             from rl_on_manifold_b200.sharding import SymmetricGather
-            fused = SymmetricGather(B, n)
-            fused_note = "fused peer-store epilogue over NVLink symmetric memory + one device barrier per step"
+            fused = SymmetricGather(B, n_out, deferred=(args.gather == "fused-deferred"))
+            fused_note = fused.describe()
         except Exception as exc:
             fused_note = "fused gather unavailable (%s: %s); NCCL all-gather used" % (type(exc).__name__, exc)
-
-    def step(i):
-        d = sets[i % ring]
-        projection.step("iiwa", d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS,
-                        ddq=d["ddq"], s_out=d["s_out"])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d["ddq"])
 
     def step_fused(i):
         d = sets[i % ring]
         fused.step(d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS, s_out=d["s_out"])
-
-    def kernel_only(i):
-        d = sets[i % ring]
-        projection.step("iiwa", d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS,
-                        ddq=d["ddq"], s_out=d["s_out"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
+    def max_over_ranks(values):
+        if world == 1:
+            return list(values)
+        t = torch.tensor(list(values), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def timed_eager(fn):
+        for i in range(args.warmup):
             fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
-            fn(warmup + i)
+        for i in range(K):
+            fn(args.warmup + i)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks([e0.elapsed_time(e1)])[0]
+
+    def timed_graphs(fn, finish=None, reset=None):
+        """K steps per CUDA graph (n_graphs graphs over disjoint ring slots), R >= 5 timed replays cycling through
+        them; every replay is exactly K steps between barrier + synchronize.  Returns the per-replay ms (max over
+        ranks)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                fn(i)
+            if finish:
+                finish()
+        torch.cuda.current_stream().wait_stream(side)
+        graphs = []
+        for g in range(n_graphs):
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            if reset:
+                reset()                                  # a captured step must not depend on events from outside
+            with torch.cuda.graph(graph):
+                for i in range(K):
+                    fn(g * K + i)
+                if finish:
+                    finish()
+            graphs.append(graph)
+        if reset:
+            reset()
+        for graph in graphs:                             # warm-up replays
+            graph.replay()
+        replays = max(args.replays, n_graphs, 5)
+        ms = []
+        for r in range(replays):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graphs[r % n_graphs].replay()
+            e1.record()
+            barrier()
+            ms.append(e0.elapsed_time(e1))
+        return max_over_ranks(ms)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
 
+    # ---- the step as a user runs it: kernel (+ gather at N > 1)
+    default_step = step_fused if fused is not None else step_nccl
+    default_finish = fused.finish if fused is not None else None
+    gather_mode = "single GPU" if world == 1 else (fused_note if fused is not None else
+                                                   "one NCCL all-gather of the projected action per step")
     launches0 = _lib.launch_count()
-    eager_ms = timed(step, args.steps, args.warmup)
-    launches = _lib.launch_count() - launches0 - args.warmup
-    total_ms, launch_mode = eager_ms, "eager launches from Python (ctypes)"
-    gather_mode = "single GPU" if world == 1 else "one NCCL all-gather of ddq per step"
-    nccl_ms = eager_ms if world > 1 else None
-    if fused is not None:
-        launches1 = _lib.launch_count()
-        fused_ms = timed(step_fused, args.steps, args.warmup)
-        if fused_ms < total_ms:
-            total_ms, gather_mode = fused_ms, fused_note
-            launches = _lib.launch_count() - launches1 - args.warmup
-    kernel_ms = eager_ms if world == 1 else timed(kernel_only, args.steps, args.warmup)
+    eager_ms = timed_eager(default_step)
+    launches_eager = _lib.launch_count() - launches0 - args.warmup
+    if default_finish:
+        default_finish()
+    if args.no_graph:
+        replay_ms, launch_mode = [eager_ms], "eager launches from Python (ctypes)"
+    else:
+        replay_ms = timed_graphs(default_step, default_finish, fused.reset if fused is not None else None)
+        launch_mode = "%d CUDA graph(s) of %d steps, %d timed replays, median" % (n_graphs, K, len(replay_ms))
+        if world == 1 and wl != "point_reach" and os.environ.get("ATACOM_PDL", "1") != "0":
+            launch_mode += "; programmatic dependent launch"
+    total_ms, min_ms = statistics.median(replay_ms), min(replay_ms)
+    launches = K * len(replay_ms) if not args.no_graph else launches_eager
 
-    def timed_graph(fn, steps):
-        """The same K steps captured once in a CUDA graph and replayed: removes the per-launch host cost."""
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(3):
-                fn(i)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for i in range(steps):
-                fn(i)
-        graph.replay()                                   # warm-up replay
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        graph.replay()
-        e1.record()
-        barrier()
-        return e0.elapsed_time(e1)
+    # ---- comparison paths at N > 1 (reported in config, never substituted for the default path)
+    nccl_ms = kernel_ms_list = None
+    if world > 1:
+        kernel_ms_list = [eager_ms] if args.no_graph else timed_graphs(kernel_only)
+        if fused is not None:
+            nccl_ms = statistics.median([timed_eager(step_nccl)] if args.no_graph else timed_graphs(step_nccl))
+    else:
+        kernel_ms_list = replay_ms
+    kernel_ms = statistics.median(kernel_ms_list)
 
-    if not args.no_graph:
-        try:
-            graph_ms = timed_graph(kernel_only, args.steps)
-            if world > 1:
-                t = torch.tensor([graph_ms], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                graph_ms = float(t.item())
-            if graph_ms < kernel_ms:
-                kernel_ms = graph_ms
-            if world == 1 and graph_ms < total_ms:
-                total_ms = graph_ms
-                launch_mode = "CUDA graph of %d launches, one replay" % args.steps
-                if os.environ.get("ATACOM_PDL", "1") != "0":
-                    launch_mode += ", programmatic dependent launch"
-        except Exception as exc:                         # pragma: no cover
-            launch_mode += " (graph capture failed: %s)" % type(exc).__name__
-        if world > 1 and fused is not None:
-            # the fused step (kernel with peer-store epilogue + symmetric-memory barrier) replayed as a graph
-            try:
-                fg_ms = timed_graph(step_fused, args.steps)
-                t = torch.tensor([fg_ms], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                fg_ms = float(t.item())
-                if rank == 0:
-                    print("[bench] fused step: eager %.2f us, CUDA graph %.2f us; NCCL path eager %.2f us"
-                          % (1e3 * fused_ms / args.steps, 1e3 * fg_ms / args.steps, 1e3 * nccl_ms / args.steps),
-                          file=sys.stderr)
-                if fg_ms < total_ms:
-                    total_ms, gather_mode = fg_ms, fused_note
-                    launch_mode = "CUDA graph of %d fused steps, one replay" % args.steps
-            except Exception as exc:                     # pragma: no cover
-                launch_mode += " (fused-step graph capture failed: %s)" % type(exc).__name__
+    # ---- the fused gather delivers what the NCCL all-gather delivers (outside the timed region, every rank)
+    gather_verified = None
+    if world > 1 and fused is not None:
+        d = sets[0]
+        buf, _ = fused.step(d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS, s_out=d["s_out"])
+        fused.finish()
+        torch.cuda.synchronize()
+        got = buf.clone()
+        step_nccl(0)
+        torch.cuda.synchronize()
+        okf = torch.tensor([1.0 if torch.equal(got, gathered) else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        gather_verified = bool(okf.item() == 1.0)
 
-    # End to end through the host-buffer entry point: pinned host arrays in, pinned host arrays out, every
-    # byte of the step's inputs and outputs crosses PCIe inside the timed region.  Two data paths of the same
-    # call are timed: zero-copy (the kernel reads and writes the caller's page-locked buffers directly; what
-    # HostContext picks for pinned buffers) and staged (device buffers + copy engines, replayed as a CUDA graph).
-    # nvidia-smi polling every 100 ms slows driver calls and PCIe traffic measurably (2x on some boxes), so the
-    # sampler runs at 1 s here.
+    # ---- end to end through the host-buffer entry point: pinned host arrays in, pinned host arrays out, every
+    # byte of the step's inputs and outputs crosses PCIe inside the timed region.  Both data paths of the call are
+    # timed and reported; `e2e.value` is the one HostContext picks by default for pinned buffers (mode "auto").
+    # nvidia-smi polling every 100 ms slows driver calls and PCIe traffic measurably, so the sampler runs at 1 s here.
     if rank == 0:
         sampler.pause()
         sampler.start(1000)
-    host = {k_: sets[0][k_].cpu().pin_memory() for k_ in ("q", "dq", "s", "alpha")}
-    ddq_h = torch.empty(B, n).pin_memory()
-    s_h = torch.empty(B, G).pin_memory()
+    keys = ("q", "dq", "p", "dp", "s", "alpha") if wl == "point_reach" else ("q", "dq", "s", "alpha")
+    host = {k_: sets[0][k_].cpu().pin_memory() for k_ in keys}
+    out_h = torch.empty(B, n_out).pin_memory()
+    s_h = torch.empty(B, host["s"].shape[1]).pin_memory()
 
-    def time_e2e(mode, chunks):
-        ctx = projection.HostContext(B, chunks=chunks, mode=mode)
+    def time_e2e(mode):
+        ctx = projection.HostContext(B, chunks=args.chunks, mode=mode)
 
         def e2e_step():
-            ctx.iiwa_step(N_JOINTS, host["q"], host["dq"], host["s"], host["alpha"], ddq_h, s_h, params)
-            return float(ddq_h[0, 0])                                # read the result on the host
+            if wl == "point_reach":
+                ctx.point_reach_step(host["q"], host["dq"], host["p"], host["dp"], host["s"], host["alpha"], out_h, s_h,
+                                     params)
+            else:
+                ctx.step(fam, host["q"], host["dq"], host["s"], host["alpha"], out_h, s_h, params,
+                         n_ctrl_joints=N_JOINTS)
+            return float(out_h[0, 0])                                # read the result on the host
 
         for _ in range(max(3, args.warmup)):
             e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        ms = 1e3 * (time.perf_counter() - t0)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        reps = []
+        for _ in range(5):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                e2e_step()
+            torch.cuda.synchronize()
+            reps.append(1e3 * (time.perf_counter() - t0))
         ctx.close()
-        return ms
+        return statistics.median(max_over_ranks(reps))
 
-    e2e_staged_ms = time_e2e("staged", args.chunks)
-    e2e_ms = time_e2e("auto", args.chunks)
-    e2e_api = "atacom_iiwa_step_host, pinned host buffers, zero-copy (kernel loads/stores cross PCIe via cp.async.bulk)"
-    if e2e_staged_ms < e2e_ms:
-        e2e_ms, e2e_api = e2e_staged_ms, "atacom_iiwa_step_host, pinned host buffers, staged copies (CUDA graph)"
+    e2e_staged_ms = time_e2e("staged")
+    e2e_auto_ms = e2e_staged_ms if wl == "point_reach" else time_e2e("auto")
+    e2e_api = ("atacom_%s_step_host, pinned host buffers, " % wl) + (
+        "staged copies (CUDA graph of H2D, kernel, D2H per chunk)" if wl == "point_reach" else
+        "zero-copy (kernel loads/stores cross PCIe via cp.async.bulk)")
 
     clocks = sampler.stop() if rank == 0 else None
+    timeouts = _lib.spin_timeouts()
 
     if rank == 0:
         peaks = {}
@@ -394,36 +520,43 @@ def ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        k_ms = kernel_ms / args.steps
-        achieved = BYTES_PER_ENV_STEP * B / (k_ms * 1e-3) / 1e9
-        traffic = None
+        k_ms = kernel_ms / K
+        achieved = bytes_env * B / (k_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel: from the committed ncu capture of this workload (written by
+        # profiles/summarize_ncu.py from the .ncu-rep), null when there is none for it
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get("bytes_per_launch")
+            t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            ent = t.get(wl)
+            if ent and int(ent.get("batch", 0)) == B:
+                traffic, traffic_src = ent["bytes_per_launch"], ent.get("source")
         except Exception:
             pass
+        total_envs = world * B * K
         line = dict(
-            metric=METRIC, value=world * B * args.steps / (total_ms * 1e-3), unit=UNIT, n_gpus=world,
-            steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
-            scaling="weak", vs_baseline=None, dtype="f64 (kinematics and projection; fp32 I/O and velocity products)",
-            data="synthetic",
-            config=dict(workload=workload_name(world), batch_per_gpu=B, global_batch=world * B,
+            metric=METRIC, value=total_envs / (total_ms * 1e-3), unit=UNIT, n_gpus=world,
+            steps=K, warmup=args.warmup, ms_per_step=total_ms / K, higher_is_better=True,
+            scaling=args.scaling, vs_baseline=None,
+            dtype="f64 (kinematics and projection; fp32 I/O)", data="synthetic",
+            config=dict(workload=workload_label(wl, B, world, args.scaling), batch_per_gpu=B, global_batch=world * B,
                         parallelism="env-shard x%d; %s" % (world, gather_mode) if world > 1 else "single GPU",
-                        gather=fused_note if world > 1 else None,
-                        nccl_all_gather_ms_per_step=(nccl_ms / args.steps) if nccl_ms else None,
+                        gather_verified=gather_verified,
+                        nccl_all_gather_ms_per_step=(nccl_ms / K) if nccl_ms else None,
                         cold_inputs="ring of %d distinct batches (%.0f MB > 2x L2) rotated every step"
-                                    % (ring, ring * B * BYTES_PER_ENV_STEP / 1e6),
-                        bytes_per_env_step=BYTES_PER_ENV_STEP, launch=launch_mode,
-                        eager_ms_per_step=eager_ms / args.steps),
-            e2e=dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * BYTES_IN,
-                     d2h_bytes_per_step=B * BYTES_OUT, api=e2e_api,
-                     staged_value=world * B * args.steps / (e2e_staged_ms * 1e-3), staged_chunks=args.chunks),
+                                    % (ring, ring * B * bytes_env / 1e6),
+                        bytes_per_env_step=bytes_env, launch=launch_mode, replays=len(replay_ms),
+                        min_ms_per_step=min_ms / K, value_at_min=total_envs / (min_ms * 1e-3),
+                        eager_ms_per_step=eager_ms / K, spin_timeouts=timeouts),
+            e2e=dict(value=world * B * K / (e2e_auto_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * bytes_in,
+                     d2h_bytes_per_step=B * bytes_out, api=e2e_api,
+                     staged_value=world * B * K / (e2e_staged_ms * 1e-3), staged_chunks=args.chunks,
+                     timing="median of 5 repeats of %d calls, wall clock around the calls, max over ranks" % K),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=traffic, peak_source=peak_src, kernel="atacom_step_kernel<IiwaEnv<6>>",
+                          traffic=traffic, traffic_source=traffic_src, peak_source=peak_src, kernel=W["kernel"],
                           kernel_us=k_ms * 1e3, frac_of_8TBs_nominal=achieved / 8000.0,
-                          note="nominal bound; the kernel is FP64-issue and latency bound (~4 k warp-instructions "
-                               "per 32 environments against 5.8 KB of traffic; ncu: FP64 pipe 32 % busy, 0.38 "
-                               "instructions per cycle per scheduler, DRAM 4 %): DESIGN.md section 6"),
+                          note="nominal bound: the kernel is FP64-issue and latency bound, not bandwidth bound "
+                               "(DESIGN.md section 6)"),
             clocks=clocks,
         )
         if cpu_baseline is not None:
@@ -459,11 +592,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--workload", default="iiwa", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help="environments per GPU (weak) / in total (strong); 0 = the workload's")
     ap.add_argument("--chunks", type=int, default=2)
+    ap.add_argument("--replays", type=int, default=7)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--gather", default="fused", choices=["fused", "fused-deferred", "nccl"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

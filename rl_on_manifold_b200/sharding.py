@@ -89,11 +89,22 @@ class SymmetricGather:
     (torch.distributed._symmetric_memory); after the rendezvous every rank holds peer-mapped pointers to all
     of them.  The step kernel stores its shard's rows straight into every rank's buffer (P2P stores over
     NVLink / NVSwitch), so the per-step all-gather costs no extra launch and no extra pass over HBM; one
-    device-side barrier on the kernel's stream then publishes the step.  Buffers alternate between steps so
-    that a rank still reading step i cannot be overwritten by a peer already writing step i + 1.
+    device-side barrier per step then publishes the step.  Buffers rotate between steps so that a rank still
+    reading step t cannot be overwritten by a peer already writing a later step.
+
+    Two schedules:
+      * synchronous (`deferred=False`, 2 buffers): kernel_t, barrier_t on the kernel's stream — the gathered
+        rows of step t are complete before step t + 1 starts; the barrier launch (~5 us) and the NVLink transfer
+        of step t sit between two kernels;
+      * deferred (`deferred=True`, 3 buffers, default of bench.py): barrier_t runs on a side stream behind
+        kernel_t, while kernel_{t+1} already computes on the main stream — the barrier and the transfer of step
+        t are hidden behind the compute of step t + 1.  The consumer of step t (a central learner's replay
+        buffer: nothing in the projection of step t + 1 depends on other ranks' rows) waits on `ready(t)`;
+        kernel_{t+3}, which reuses buffer t mod 3, waits for barrier_{t+1}: by then every rank has passed its
+        own barrier_{t+1} launch, which is stream-ordered behind whatever consumed step t on the side stream.
     """
 
-    def __init__(self, local_B, n, group=None, buffers=2, in_kernel_barrier=False):
+    def __init__(self, local_B, n, group=None, buffers=None, in_kernel_barrier=False, deferred=False):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(group)
@@ -101,6 +112,10 @@ class SymmetricGather:
         if self.world > 8:
             raise ValueError("fused gather supports one NVSwitch domain (<= 8 ranks)")
         self.local_B, self.n = local_B, n
+        self.deferred = bool(deferred) and not in_kernel_barrier
+        buffers = buffers if buffers is not None else (3 if self.deferred else 2)
+        if self.deferred and buffers < 3:
+            raise ValueError("the deferred schedule needs at least 3 buffers")
         name = group.group_name
         dev = torch.device("cuda", torch.cuda.current_device())
         self.bufs, self.handles, self.ptrs = [], [], []
@@ -124,20 +139,71 @@ class SymmetricGather:
             torch.cuda.synchronize()
             self._flag_hdl.barrier()          # every rank's flags are zero before the first step
         self._i = 0
+        self._side = torch.cuda.Stream(device=dev) if self.deferred else None
+        self._bar_done = [None] * buffers     # event: the barrier of the last step that used buffer b has completed
+        self._last = None                     # (buffer index, event) of the newest step
+
+    def describe(self):
+        if self.in_kernel_barrier:
+            return "fused peer-store epilogue over NVLink symmetric memory, cross-rank barrier inside the kernel"
+        if self.deferred:
+            return ("fused peer-store epilogue over NVLink symmetric memory; the barrier of step t runs on a side "
+                    "stream behind kernel t+1 (%d rotating buffers; gathered rows of step t are ready one step later)"
+                    % len(self.bufs))
+        return "fused peer-store epilogue over NVLink symmetric memory + one device barrier per step"
 
     def step(self, q, dq, s, alpha, params, *, n_ctrl_joints=6, s_out=None, status=None):
-        """Project this rank's shard and gather: returns (gathered ddq [world * local_B, n], s_out)."""
+        """Project this rank's shard and gather: returns (gathered ddq [world * local_B, n], s_out).  With the
+        deferred schedule the returned buffer is complete once `ready()` (or `finish()`) has been waited on."""
         from . import projection
-        b = self._i % len(self.bufs)
+        nb = len(self.bufs)
+        b = self._i % nb
+        t = self._i
         self._i += 1
-        if self.in_kernel_barrier:
-            s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
-                                                self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
-                                                status=status, flag_ptrs=self._flag_ptrs,
-                                                local_sync=self._local_sync, rank=self.rank)
-        else:
+        main = torch.cuda.current_stream()
+        with torch.cuda.nvtx.range("atacom_step_gather"):
+            if self.in_kernel_barrier:
+                s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
+                                                    self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
+                                                    status=status, flag_ptrs=self._flag_ptrs,
+                                                    local_sync=self._local_sync, rank=self.rank)
+                return self.bufs[b], s_out
+            if self.deferred:
+                # buffer b was last written at step t - nb; every rank is done with it once barrier_{t-nb+1} ... has
+                # completed here — wait for the newest barrier older than two steps (it completed long ago)
+                prev = self._bar_done[(t - 2) % nb] if t >= 2 else None
+                if prev is not None:
+                    main.wait_event(prev)
             s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
                                                 self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
                                                 status=status)
-            self.handles[b].barrier()
+            if not self.deferred:
+                self.handles[b].barrier()
+                return self.bufs[b], s_out
+            done_k = torch.cuda.Event()
+            done_k.record(main)
+            self._side.wait_event(done_k)
+            with torch.cuda.stream(self._side):
+                self.handles[b].barrier()
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            self._bar_done[b] = ev
+            self._last = (b, ev)
         return self.bufs[b], s_out
+
+    def ready(self, stream=None):
+        """Make `stream` (default: the current one) wait until the newest step's gathered rows are complete."""
+        if self.deferred and self._last is not None:
+            (stream or torch.cuda.current_stream()).wait_event(self._last[1])
+
+    def finish(self):
+        """Join the side stream: after this, on the current stream, every issued step is gathered everywhere."""
+        if self.deferred:
+            torch.cuda.current_stream().wait_stream(self._side)
+
+    def reset(self):
+        """Forget the bookkeeping of earlier steps (call after `finish()`, e.g. before capturing a CUDA graph: a
+        captured step must not wait on an event recorded outside the capture)."""
+        self._i = 0
+        self._bar_done = [None] * len(self.bufs)
+        self._last = None

@@ -1,82 +1,13 @@
 """Seeded synthetic (q, dq, s, alpha) batches of the shapes BASELINE.json names.
 
-Inputs are drawn on the CPU with a seeded torch.Generator (so the NumPy oracle in the tests sees
-bit-identical fp32 values) and moved to the target device.  The slack variables start from the
-reference's own reset rule (atacom.py:145-149), evaluated by the slack-init kernel, and are then
-pushed into an interior / boundary mix: 85 % of the environments keep every slack >= 0.3,
+The draws themselves live in `_inputs.py` (pure torch, importable without the native library).  The slack
+variables start from the reference's own reset rule (atacom.py:145-149), evaluated by the slack-init kernel,
+and are then pushed into an interior / boundary mix: 85 % of the environments keep every slack >= 0.3,
 15 % get one slack drawn from U(0, 0.02) (an active constraint).
 """
-import math
-
-import torch
-
 from . import _lib, projection
-
-# joint angles that put the striker tip at (0.65, 0, 0.1505) in the robot frame, pointing down
-# (the pose env_single.py:39-44 solves for by CLIK), found once with the oracle's FK
-IIWA_HOME = (0.0, 0.2596, 0.0, -1.2247, 0.0, 1.4384, 0.0)
-IIWA_Q_MAX = (2.9670597283903604, 2.0943951023931953, 2.9670597283903604, 2.0943951023931953,
-              2.9670597283903604, 2.0943951023931953, 3.0543261909900763)
-
-
-def _u(gen, shape, lo, hi):
-    return torch.rand(shape, generator=gen, dtype=torch.float32) * (hi - lo) + lo
-
-
-def state_batch(family, B, seed, n_ctrl_joints=6, params=None):
-    """(q, dq, alpha) on the CPU, fp32, for one env family."""
-    gen = torch.Generator().manual_seed(int(seed))
-    if family == "circle":
-        th = _u(gen, (B,), -math.pi / 6, 7 * math.pi / 6)
-        rad = 1.0 + _u(gen, (B,), -1e-3, 1e-3)
-        q = torch.stack([torch.cos(th), torch.sin(th)], 1) * rad[:, None]
-        v = _u(gen, (B,), -1.0, 1.0)
-        dq = torch.stack([-torch.sin(th), torch.cos(th)], 1) * v[:, None] + _u(gen, (B, 2), -0.01, 0.01)
-        alpha = _u(gen, (B, 1), -10.0, 10.0)
-    elif family == "planar":
-        p = params or _lib.default_params("planar")
-        qmax = torch.tensor(list(p.env[5:8]))
-        vmax = torch.tensor(list(p.vel_max[:3]))
-        q = _u(gen, (B, 3), -0.8, 0.8) * qmax
-        dq = _u(gen, (B, 3), -0.5, 0.5) * vmax
-        alpha = _u(gen, (B, 3), -10.0, 10.0)
-    elif family == "iiwa":
-        n = n_ctrl_joints
-        p = params or _lib.default_params("iiwa", n)
-        vmax = torch.tensor(list(p.vel_max[:n]))
-        qmax = torch.tensor(IIWA_Q_MAX[:n])
-        q = torch.tensor(IIWA_HOME[:n]) + _u(gen, (B, n), -0.35, 0.35)
-        q = torch.minimum(torch.maximum(q, -0.95 * qmax), 0.95 * qmax)
-        dq = _u(gen, (B, n), -0.5, 0.5) * vmax
-        alpha = _u(gen, (B, n - 1), -10.0, 10.0)
-    else:
-        raise ValueError(family)
-    return q.contiguous(), dq.contiguous(), alpha.contiguous()
-
-
-def slack_mix(s, seed, interior=0.85, s_floor=0.3, s_active=0.02):
-    """Apply the interior / boundary mix to slacks `s` [B, G] (any device); deterministic in seed."""
-    B, G = s.shape
-    gen = torch.Generator().manual_seed(int(seed) + 7919)
-    boundary = torch.rand(B, generator=gen) >= interior
-    which = torch.randint(0, G, (B,), generator=gen)
-    small = torch.rand(B, generator=gen, dtype=torch.float32) * s_active
-    boundary, which, small = boundary.to(s.device), which.to(s.device), small.to(s.device)
-    out = torch.clamp(s, min=s_floor)
-    rows = torch.nonzero(boundary, as_tuple=True)[0]
-    out[rows, which[rows]] = small[rows]
-    return out.contiguous()
-
-
-def point_reach_batch(B, seed, n_objects=4):
-    """(q, dq, p, dp, action) on the CPU for env C."""
-    gen = torch.Generator().manual_seed(int(seed))
-    q = _u(gen, (B, 2), 1.0, 9.0)
-    dq = _u(gen, (B, 2), -1.0, 1.0)
-    p = _u(gen, (B, 2 * n_objects), 2.0, 8.0)
-    dp = _u(gen, (B, 2 * n_objects), -1.0, 1.0)
-    action = _u(gen, (B, 2), -1.0, 1.0)
-    return q, dq, p, dp, action
+from ._inputs import (IIWA_HOME, IIWA_Q_MAX, IIWA_VEL_MAX, PLANAR_Q_MAX, PLANAR_VEL_MAX, point_reach_batch,  # noqa: F401
+                      slack_mix, state_batch)
 
 
 def device_batch(family, B, seed, device, n_ctrl_joints=6, params=None):
@@ -88,3 +19,13 @@ def device_batch(family, B, seed, device, n_ctrl_joints=6, params=None):
     s = projection.slack_init(family, q, dq, params, n_ctrl_joints=n_ctrl_joints)
     s = slack_mix(s, seed)
     return q, dq, s, alpha
+
+
+def point_reach_device_batch(B, seed, device, n_objects=4, params=None):
+    """(q, dq, p, dp, s, action) on `device` for env C, slacks from PointReachAtacom.reset's rule
+    (collision_avoidance_atacom.py:25) through the slack-init kernel."""
+    if params is None:
+        params = _lib.default_params("point_reach")
+    q, dq, p, dp, action = (t.to(device) for t in point_reach_batch(B, seed, n_objects))
+    s = projection.point_reach_slack_init(q, p, params)
+    return q, dq, p, dp, s, action

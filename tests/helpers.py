@@ -12,6 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS_DIR = os.path.join(ROOT, "tests", "host_harness")
 CSRC = os.path.join(ROOT, "rl_on_manifold_b200", "csrc")
 
+# the null basis the product's default mode reproduces (see oracle/nullspace.py)
+REFERENCE_BASIS = "canonical"
+
 ENV_ID = {"circle": 0, "planar": 1, "iiwa6": 2, "iiwa7": 3}
 DIMS = {"circle": (2, 1, 1), "planar": (3, 0, 6), "iiwa6": (6, 1, 11), "iiwa7": (7, 1, 12)}
 
@@ -129,6 +132,41 @@ def oracle_batch(family, q, dq, s, alpha, basis="canonical", variant="atacom", b
         sv = np.linalg.svd(o["Jc"], compute_uv=False)
         out["cond"][i] = sv[0] / max(sv[-1], 1e-300)
     return out
+
+
+def oracle_point_reach_batch(q, dq, p, dp, s, action):
+    """Env C oracle over a batch (collision_avoidance_atacom.py:29-47).  `pmin`: the smallest pivot candidate of the
+    rref (the reference's tolerance there is ~1e-15; the kernels decide with 2.4e-6, so candidates in between are
+    outside the parity domain)."""
+    B, G = s.shape
+    out = dict(w=np.zeros((B, 2 + G)), s_new=np.zeros((B, G)), rank_def=np.zeros(B, bool), pmin=np.full(B, np.inf))
+    q, dq, p, dp, s, action = (np.asarray(a, dtype=np.float64) for a in (q, dq, p, dp, s, action))
+    for i in range(B):
+        try:
+            o = ao.point_reach_step(q[i], dq[i], p[i].reshape(G, 2), dp[i].reshape(G, 2), s[i], action[i])
+        except ValueError:
+            out["rank_def"][i] = True
+            continue
+        out["w"][i], out["s_new"][i] = o["w"], o["s_new"]
+        out["rank_def"][i] = o["rank"] < G
+        cand = [pv for (_, _, pv) in o["trace"]["pivots"] + o["trace"]["dropped"]]
+        out["pmin"][i] = min(cand) if cand else np.inf
+    return out
+
+
+def oracle_batch_mp(family, *arrays, basis="canonical", variant="atacom", bias="omega_x_v", tmpdir=None):
+    """`oracle_batch` (or `oracle_point_reach_batch` for family "point_reach") fanned out over all host cores in a
+    separate interpreter (tests/oracle_mp.py): what makes parity at BASELINE.json's full batch sizes affordable."""
+    import sys
+    import tempfile
+    d = tmpdir or tempfile.mkdtemp(prefix="oracle_mp_")
+    src, dst = os.path.join(str(d), "in_%s.npz" % family), os.path.join(str(d), "out_%s.npz" % family)
+    names = ("q", "dq", "p", "dp", "s", "action") if family == "point_reach" else ("q", "dq", "s", "alpha")
+    np.savez(src, family=family, basis=basis, variant=variant, bias=bias,
+             **{k: np.ascontiguousarray(a) for k, a in zip(names, arrays)})
+    subprocess.check_call([sys.executable, "-W", "ignore", "-m", "tests.oracle_mp", src, dst], cwd=ROOT)
+    z = np.load(dst)
+    return {k: z[k] for k in z.files}
 
 
 def rel_err(x, ref, scale=None):

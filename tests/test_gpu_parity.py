@@ -310,6 +310,64 @@ def test_host_buffer_entry_point(cuda_device, mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("family", ["circle", "planar", "iiwa7"])
+@pytest.mark.parametrize("mode", ["staged", "zero_copy", "hybrid", "auto"])
+def test_host_buffer_entry_points_of_the_other_step_families(cuda_device, family, mode):
+    """atacom_{circle,planar,iiwa}_step_host: bit-identical to the device-resident call on every data path."""
+    fam, nj = _fam(family)
+    p = _params(family)
+    n, F, G = helpers.DIMS[family]
+    B = 3001
+    q, dq, s, alpha = synthetic.device_batch(fam, B, 31, cuda_device, nj, p)
+    st = torch.zeros(B, dtype=torch.uint8, device=cuda_device)
+    ddq, s_out = projection.step(fam, q, dq, s, alpha, p, n_ctrl_joints=nj, status=st)
+    ctx = projection.HostContext(B, chunks=3, mode=mode)
+    h = [t.cpu().pin_memory() for t in (q, dq, s, alpha)]
+    ddq_h, s_h = torch.empty(B, n).pin_memory(), torch.empty(B, G).pin_memory()
+    st_h = torch.zeros(B, dtype=torch.uint8).pin_memory()
+    for rep in range(3):
+        ddq_h.zero_()
+        ctx.step(fam, *h, ddq_h, s_h, p, status=st_h, n_ctrl_joints=nj)
+        assert torch.equal(ddq_h, ddq.cpu()) and torch.equal(s_h, s_out.cpu()) and torch.equal(st_h, st.cpu())
+    ctx.close()
+
+
+def test_host_buffer_entry_points_point_reach_and_generic(cuda_device, golden):
+    """atacom_point_reach_step_host / atacom_generic_step_host (NumPy in, NumPy out, staged data path) against
+    the device-resident calls; the other data paths are refused for these two families."""
+    dev = cuda_device
+    B, G = 2500, 4
+    p = _lib.default_params("point_reach")
+    q, dq, P, DP, s, act = synthetic.point_reach_device_batch(B, 8, dev, G, p)
+    w, s_out = projection.point_reach_step(q, dq, P, DP, s, act, p)
+    ctx = projection.HostContext(B, chunks=2, mode="auto")
+    hn = [t.cpu().numpy() for t in (q, dq, P, DP, s, act)]
+    w_h, s_h = np.zeros((B, 2), np.float32), np.zeros((B, G), np.float32)
+    for rep in range(2):
+        ctx.point_reach_step(*hn, w_h, s_h, p)
+        assert np.array_equal(w_h, w.cpu().numpy()) and np.array_equal(s_h, s_out.cpu().numpy())
+    # generic ConstraintsSet of the iiwa shape, from the reference-recorded cases
+    tag = "g6111"
+    spec = generic_spec(golden[tag + "_meta"])
+    n, F, Gg = spec.n, spec.F, spec.G
+    gp = _lib.AtacomParams()
+    gp.K_f[:F] = list(spec.K_f); gp.K_g[:Gg] = list(spec.K_g); gp.K_c[:F + Gg] = list(spec.K_c)
+    gp.K_q[:n] = list(spec.K_q); gp.vel_max[:n] = list(spec.vel_max); gp.acc_max[:n] = list(spec.acc_max)
+    gp.dt, gp.rref_tol, gp.clip_acc = spec.dt, 0.05, 1
+    arr = {k: np.ascontiguousarray(golden["%s_%s" % (tag, k)], dtype=np.float32) for k in ("c", "J", "b", "dq", "s", "alpha")}
+    t = {k: torch.from_numpy(v).to(dev) for k, v in arr.items()}
+    ddq, so = projection.generic_step(n, F, Gg, t["c"], t["J"], t["b"], t["dq"], t["s"], t["alpha"], gp)
+    Bg = arr["c"].shape[0]
+    ddq_h, so_h = np.zeros((Bg, n), np.float32), np.zeros((Bg, Gg), np.float32)
+    ctx.generic_step(n, F, Gg, arr["c"], arr["J"], arr["b"], arr["dq"], arr["s"], arr["alpha"], ddq_h, so_h, gp)
+    assert np.array_equal(ddq_h, ddq.cpu().numpy()) and np.array_equal(so_h, so.cpu().numpy())
+    ctx.close()
+    ctx = projection.HostContext(B, chunks=2, mode="zero_copy")
+    with pytest.raises(_lib.AtacomError):
+        ctx.point_reach_step(*hn, w_h, s_h, p)
+    ctx.close()
+
+
 @pytest.mark.parametrize("window", ["0", "3", "192"])
 @pytest.mark.parametrize("n", [6, 7])
 def test_zero_copy_ordered_admission(cuda_device, monkeypatch, window, n):

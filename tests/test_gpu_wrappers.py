@@ -259,3 +259,98 @@ def test_batched_core_circle_experiment_loop(cuda_device):
     assert c_max < 2e-2 and c_dq_max < 0.5 and 0 < Jm < Rm          # ATACOM keeps the agent on the manifold
     core.learn(n_steps=30, n_steps_per_fit=10)
     assert agent.n_fits == 3
+
+
+@pytest.mark.parametrize("cls,n", [(AirHockeyIiwaAtacom, 6), (AirHockeyPlanarAtacom, 3)])
+def test_air_hockey_constraint_log_is_finite_and_matches_oracle(cuda_device, cls, n):
+    """get_constraints_logs() of the air-hockey wrappers (atacom.py:201-216 with origin_constr=True): finite, and
+    equal to max(|f|, g) of the oracle's constraint functions along the roll-out."""
+    B = 64
+    env = cls(n_envs=B, device=cuda_device)
+    env.reset()
+    gen = torch.Generator().manual_seed(0)
+    want_c, want_dq = [], []
+    fam = "iiwa6" if n == 6 else "planar"
+    for _ in range(5):
+        a = (torch.rand(B, env.info.action_space.low.shape[0], generator=gen) * 2 - 1).to(cuda_device)
+        env.step(a)
+        qn, dqn = env.q.double().cpu().numpy(), env.dq.double().cpu().numpy()
+        for i in range(B):
+            ev = helpers.oracle_eval(fam, qn[i], dqn[i])
+            want_c.append(max(np.abs(ev.c_f).max() if ev.c_f.size else -np.inf, ev.c_g.max()))
+            want_dq.append((np.abs(dqn[i]) - env.vel_max).max())
+    c_avg, c_max, c_dq_max = env.get_constraints_logs()
+    assert np.isfinite([c_avg, c_max, c_dq_max]).all()
+    assert abs(c_avg - np.mean(want_c)) < 1e-5 and abs(c_max - np.max(want_c)) < 1e-5
+    assert abs(c_dq_max - np.max(want_dq)) < 1e-5
+
+
+def test_masked_reset_reinitialises_only_the_selected_environments(cuda_device):
+    """Per-environment episode termination: reset(mask=...) re-initialises the state and — through
+    the slack-init kernels' mask — the slacks of the selected environments only."""
+    B = 96
+    mask = torch.arange(B, device=cuda_device) % 3 == 0
+    for env in (CircleEnvAtacom(n_envs=B, random_init=True, device=cuda_device),
+                AirHockeyIiwaAtacom(n_envs=B, device=cuda_device),
+                PointReachAtacom(n_objects=4, random_walk=True, n_envs=B, device=cuda_device)):
+        env.seed(1)
+        env.reset()
+        gen = torch.Generator().manual_seed(2)
+        adim = env.info.action_space.low.shape[0]
+        for _ in range(3):
+            env.step((torch.rand(B, adim, generator=gen) * 2 - 1).to(cuda_device))
+        base = env.env if hasattr(env, "env") else env
+        st0, s0 = base._state.clone(), env.s.clone()
+        env.reset(mask=mask)
+        st1, s1 = base._state, env.s
+        assert torch.equal(st1[~mask], st0[~mask]) and torch.equal(s1[~mask], s0[~mask])
+        assert not torch.equal(st1[mask], st0[mask])
+        # the re-initialised slacks are what a full reset computes for those states
+        fresh = type(env).__new__(type(env))
+        if isinstance(env, PointReachAtacom):
+            want = __import__("rl_on_manifold_b200").projection.point_reach_slack_init(*[env._split(st1)[i] for i in (0, 2)],
+                                                                                       env.params)
+        else:
+            from rl_on_manifold_b200 import projection
+            want = projection.slack_init(env._family, env._get_q(st1).contiguous(), env._get_dq(st1).contiguous(),
+                                         env.params, n_ctrl_joints=env._n_ctrl_joints)
+        assert torch.equal(s1[mask], want[mask])
+        del fresh
+
+
+def test_bare_viability_constraint_and_missing_callbacks(cuda_device):
+    """The reference accepts a bare ViabilityConstraint for f / g (atacom.py:18-19); a constraint without callbacks
+    outside a built-in family raises a clear error instead of a TypeError deep inside."""
+    g = ViabilityConstraint(3, 3, fun=lambda q: q - 0.9, J=lambda q: torch.eye(3, device=q.device).expand(q.shape[0], 3, 3),
+                            b=lambda q, dq: torch.zeros_like(q), K=0.5)
+    f = ViabilityConstraint(3, 1, fun=lambda q: (q ** 2).sum(1, keepdim=True) - 1, J=lambda q: 2 * q[:, None, :],
+                            b=lambda q, dq: 2 * (dq ** 2).sum(1, keepdim=True), K=0.2)
+
+    class _Base:
+        def __init__(self, B, dev):
+            self.device, self.B = dev, B
+            self._info = MDPInfo(Box(-np.ones(6) * np.inf, np.ones(6) * np.inf), Box(-np.ones(3), np.ones(3)), 0.99, 10)
+            self.step_action_function = None
+
+        info = property(lambda self: self._info)
+
+        def reset(self, state=None):
+            self.state = torch.zeros(self.B, 6, device=self.device)
+            self.state[:, 0] = 1.0
+            return self.state
+
+        def _create_observation(self, s):
+            return s
+
+    class _W(AtacomEnvWrapper):
+        def _get_q(self, st): return st[:, :3]
+        def _get_dq(self, st): return st[:, 3:]
+        def acc_to_ctrl_action(self, ddq): return ddq
+
+    w = _W(_Base(8, cuda_device), 3, vel_max=1.5, acc_max=10., f=f, g=g, Kc=50., Kq=13.)
+    assert isinstance(w.f, ConstraintsSet) and w.dims == {'q': 3, 'f': 1, 'g': 3, 'null': 2, 'c': 4}
+    w.reset()
+    out = w.step_action_function(w.state, torch.zeros(8, 2, device=cuda_device))
+    assert out.shape == (8, 3) and torch.isfinite(out).all()
+    with pytest.raises(ValueError, match="callbacks"):
+        ViabilityConstraint(3, 1, K=1.0).fun(torch.zeros(2, 3), torch.zeros(2, 3))

@@ -152,7 +152,7 @@ def test_iiwa_kinematics_finite_differences(n):
     for _ in range(5):
         q = rng.uniform(-0.8, 0.8, n) * oenv.IIWA_Q_MAX[:n]
         dq = rng.uniform(-0.5, 0.5, n) * oenv.IIWA_VEL_MAX[:n]
-        ev = oenv.iiwa_eval(q, dq)
+        ev = oenv.iiwa_eval(q, dq, bias="jdot_qdot")      # the full dJ/dt dq is what finite differences see
         cfun = lambda x: np.concatenate([oenv.iiwa_eval(x, dq).c_f, oenv.iiwa_eval(x, dq).c_g])
         h = 1e-6
         Jfd = np.stack([(cfun(q + h * e) - cfun(q - h * e)) / (2 * h) for e in np.eye(n)], 1)
@@ -160,6 +160,24 @@ def test_iiwa_kinematics_finite_differences(n):
         h = 1e-4
         bfd = (cfun(q + h * dq) - 2 * cfun(q) + cfun(q - h * dq)) / h ** 2
         assert np.abs(np.concatenate([ev.b_f, ev.b_g]) - bfd).max() < 1e-5
+        # default mode (what the reference executes: classical acceleration with data.a = 0): omega x v of each
+        # frame, checked against finite-difference velocities of the oracle's own FK
+        ev2 = oenv.iiwa_eval(q, dq)
+        qf, dqf = np.zeros(7), np.zeros(7)
+        qf[:n], dqf[:n] = q, dq
+        fr = oenv.chain_fk(oenv.IIWA_ORIGINS, qf)
+
+        def frame_point(x, joint, off):
+            f = oenv.chain_fk(oenv.IIWA_ORIGINS, x)
+            return f[joint - 1][1] + f[joint - 1][0] @ np.asarray(off, float)
+
+        want = []
+        for joint, off in ((7, oenv.IIWA_TIP), (4, (0, 0, 0)), (7, (0, 0, 0))):
+            v = (frame_point(qf + 1e-6 * dqf, joint, off) - frame_point(qf - 1e-6 * dqf, joint, off)) / 2e-6
+            w = sum(fr[i][0][:, 2] * dqf[i] for i in range(joint))
+            want.append(np.cross(w, v))
+        b = np.array([want[0][2], -want[0][0], -want[0][1], want[0][1], -want[1][2], -want[2][2]])
+        assert np.abs(np.concatenate([ev2.b_f, ev2.b_g[:5]]) - b).max() < 1e-7
 
 
 def test_iiwa_fk_facts():
@@ -180,7 +198,7 @@ def test_iiwa_fk_facts():
 def test_planar_kinematics_finite_differences():
     rng = np.random.default_rng(2)
     q, dq = rng.uniform(-0.8, 0.8, 3), rng.uniform(-1, 1, 3)
-    ev = oenv.planar_eval(q, dq)
+    ev = oenv.planar_eval(q, dq, bias="jdot_qdot")
     cfun = lambda x: oenv.planar_eval(x, dq).c_g
     h = 1e-6
     Jfd = np.stack([(cfun(q + h * e) - cfun(q - h * e)) / (2 * h) for e in np.eye(3)], 1)
