@@ -54,11 +54,25 @@ enum {
   ATACOM_ST_COLUMN_DROPPED = 2, /* the tolerance branch of rref fired (null_space_coordinate.py:60) */
   ATACOM_ST_SLACK_PIVOT = 4,    /* a slack column became a tangent coordinate                       */
   ATACOM_ST_NONFINITE = 8,
-  ATACOM_ST_DENSE_PATH = 16     /* generic / point-reach kernels: the structured fast path deferred to the dense
+  ATACOM_ST_DENSE_PATH = 16,    /* generic / point-reach kernels: the structured fast path deferred to the dense
                                    Householder path (the step kernels of the four families never set it)       */
+  ATACOM_ST_LAPACK_PATH = 32    /* inside the tolerance band of rref: projected with the reference's LAPACK null
+                                   basis (ATACOM_BASIS_LAPACK) instead of the basis-free fast path            */
 };
 
 enum { ATACOM_VARIANT_ATACOM = 0, ATACOM_VARIANT_ERROR_CORRECTION = 1 };
+/* Null basis handed to rref(tol) (atacom.py:127-128).  Where the tolerance branch of rref does not fire the result
+ * does not depend on it.  Where it fires (an active constraint: 15-25 % of the synthetic benchmark batches) it does:
+ *   LAPACK     (default, 0): the reference's own basis — SciPy svd / LAPACK gesdd returns, for a full-row-rank Jc,
+ *              the trailing columns of the product of the right Householder reflectors of the bidiagonalisation
+ *              (dgebd2; dgelq2 when N >= 11 C / 6): a deterministic function of Jc, reproduced here
+ *              (csrc/atacom_lapack.cuh), so the output equals the reference's on both strata.  The step kernels
+ *              run the basis-free fast path everywhere and redo the environments inside the tolerance band
+ *              (flagged ATACOM_ST_LAPACK_PATH) with this basis in a second, compacted launch;
+ *   CANONICAL  (1): Gram-Schmidt of the projected unit vectors in column order — a function of null(Jc) alone;
+ *              one launch, ~40 % faster, equal to the reference's output only where the tolerance branch stays
+ *              silent. */
+enum { ATACOM_BASIS_LAPACK = 0, ATACOM_BASIS_CANONICAL = 1 };
 /* b(q, dq) of the Cartesian rows.  OMEGA_X_V (default of the *_default_params): what the reference executes —
  * pinocchio's classical frame acceleration after a FIRST-order forwardKinematics, data.a = 0, i.e. omega x v
  * (iiwa_hit_atacom.py:87-89,122-128; atacom_air_hockey.py:94-96).  JDOT_QDOT: the full dJ/dt dq the paper
@@ -79,7 +93,7 @@ typedef struct AtacomParams {
   int32_t variant;             /* ATACOM_VARIANT_*                                                    */
   int32_t bias_mode;           /* ATACOM_BIAS_* for the Cartesian rows of planar / iiwa               */
   int32_t clip_acc;            /* 1: apply acc_truncation (atacom.py:117-121)                         */
-  int32_t reserved;
+  int32_t basis_mode;          /* ATACOM_BASIS_*: which null basis the tolerance-RREF sees (0 = the reference's) */
   double env[ATACOM_ENV_PARAMS]; /* geometry constants, double because K_c amplifies their rounding:
                                     planar: l1 l2 l3 base_x base_y qmax[3] half_len half_wid;
                                     iiwa: base_x half_len half_wid height z4_min z7_min qmax[7];

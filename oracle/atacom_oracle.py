@@ -123,6 +123,12 @@ def null_coordinates(Jc, k, tol, basis="svd", pinv_Q=None, trace=None):
         V = np.zeros((k, Jc.shape[1]))
         kk = min(k, Q.shape[1])
         V[:kk] = Q[:, :kk].T                      # Nc[:, :k] silently truncates (atacom.py:128)
+    elif basis == "lapack":
+        if Q.shape[1] != k:                       # rank-deficient Jc: LAPACK's extra null vectors come out of its
+            V = np.zeros((k, Jc.shape[1]))        # SVD iteration and are not restated; flagged by the callers
+            V[:min(k, Q.shape[1])] = Q[:, :min(k, Q.shape[1])].T
+        else:
+            V = ns.lapack_null_basis(Jc).T
     elif basis == "canonical":
         V = ns.canonical_null_basis(Jc, k, 0.0 if tol is None else tol, pinv=pinv)
     else:

@@ -147,6 +147,10 @@ def iiwa_eval(q, dq, bias="omega_x_v"):
     l4 = point_kinematics(fr, dq, 4, (0, 0, 0), n)
     l7 = point_kinematics(fr, dq, 7, (0, 0, 0), n)
     p, J, b = tip[0], tip[1], tip[sel]
+    if n == 7:
+        # the tip lies on the axis of joint 7 (env_base.py:147-151): its Jacobian column is exactly zero, where
+        # z_7 x (tip - o_7) leaves rounding noise of either sign
+        J[:, 6] = 0.0
     xw = p[0] + IIWA_BASE_X
     half_l = TABLE_LENGTH / 2 - MALLET_RADIUS
     half_w = TABLE_WIDTH / 2 - MALLET_RADIUS

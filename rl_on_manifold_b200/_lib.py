@@ -16,6 +16,8 @@ OK = 0
 ST_RANK_DEFICIENT, ST_COLUMN_DROPPED, ST_SLACK_PIVOT, ST_NONFINITE, ST_DENSE_PATH = 1, 2, 4, 8, 16
 VARIANT_ATACOM, VARIANT_ERROR_CORRECTION = 0, 1
 BIAS_JDOT_QDOT, BIAS_OMEGA_X_V = 0, 1
+BASIS_LAPACK, BASIS_CANONICAL = 0, 1
+ST_LAPACK_PATH = 32
 HOST_AUTO, HOST_STAGED, HOST_ZERO_COPY, HOST_HYBRID = 0, 1, 2, 3
 
 
@@ -33,7 +35,7 @@ class AtacomParams(ctypes.Structure):
         ("variant", ctypes.c_int32),
         ("bias_mode", ctypes.c_int32),
         ("clip_acc", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("basis_mode", ctypes.c_int32),
         ("env", ctypes.c_double * ENV_PARAMS),
     ]
 

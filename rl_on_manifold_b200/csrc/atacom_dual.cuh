@@ -41,6 +41,7 @@
 #pragma once
 
 #include "atacom_core.cuh"
+#include "atacom_lapack.cuh"
 
 namespace atacom {
 
@@ -482,9 +483,16 @@ struct Dual {
   // inequality), alpha: k.  w_mn (type W), w_null (type R): N each.
   // defer_general: do not run the general routine here but return ST_DENSE_PATH as a request, with sigma and gamma
   // in w_null[0 .. 2n) — the caller then runs it with the whole warp (null_part_general_warp) and overwrites w_null.
+  // band_defer: leave every environment whose result may depend on the null BASIS to the LAPACK-basis routine
+  // (atacom_lapack.cuh) and return ST_LAPACK_PATH for it, w_null unfinished.  The reference's rref can only drop
+  // column j (r pivots found so far) if the canonical pivot p_j — the norm of what is left of P e_j, computed here —
+  // is at most sqrt(k - r) tol: its candidate is the largest of k - r entries y_i = <w_i, P e_j> of rows w_i that
+  // are an elimination-transformed basis of the remaining null space with Gram matrix >= I, so max |y_i| >=
+  // p_j / sqrt(k - r).  Outside that band no column is dropped by either procedure, the pivots are the first k
+  // columns, and the result is the basis-free closed form computed here.
   template <bool defer_general = false, class YS, class LS, typename W>
   static ATACOM_HD uint8_t project(YS& Y, LS& Ls, const R* dg, const R* s, const R* r, const R* alpha, R tol,
-                                   bool want_null, W* w_mn, R* w_null) {
+                                   bool want_null, W* w_mn, R* w_null, bool band_defer = false) {
     uint8_t status = 0;
 
     // ---- (1) diagonal rows -> coordinates t_j
@@ -655,10 +663,14 @@ struct Dual {
     R vinv[n], bcol[n];
     bool take[n];
     int npiv = 0;
+    bool band = false;
     ATACOM_UNROLL
     for (int c = 0; c < n; ++c) {
       const R d = Gx[c][c];
       const bool tested = npiv < k;
+      // (a numerically zero pivot — a column that is structurally dependent, e.g. the last joint of iiwa-7 — is dropped
+      // by every basis alike and what is zeroed there is rounding noise: not a reason to defer)
+      band = band || (tested && !(d > tol * tol * R(k - npiv)) && d > R(1e-14));
       const bool tk = tested && (d > tol * tol) && (d > R(DUAL_TINY));
       const R inv = tk ? dual_rsqrt(d) : R(0);
       take[c] = tk;
@@ -722,6 +734,7 @@ struct Dual {
     }
     ATACOM_UNROLL
     for (int i = 0; i < GD; ++i) w_null[n + i] = -s[i] * yv[F + i];
+    if (band_defer && (band || npiv < k) && !(status & ST_RANK_DEFICIENT)) return status | ST_LAPACK_PATH;
     if (npiv == k) return status;
 
     // ---- (7) slack columns become tangent-space coordinates

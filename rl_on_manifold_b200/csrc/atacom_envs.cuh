@@ -34,12 +34,13 @@ struct ParamsT {
   int32_t variant;
   int32_t bias_mode;
   int32_t clip_acc;
-  int32_t reserved;
+  int32_t basis_mode;
   double env[24];
 };
 
 enum { VARIANT_ATACOM = 0, VARIANT_EC = 1 };
 enum { BIAS_JDOT_QDOT = 0, BIAS_OMEGA_X_V = 1 };
+enum { BASIS_LAPACK = 0, BASIS_CANONICAL = 1 };
 
 // The environment functors hand their results to a SINK, one value at a time and as early as it is
 // known: put_c(i, c_i(q)), put_Jdq(i, (J dq)_i), put_J(i, j, J_ij), put_b(i, b_i(q, dq)), i over
@@ -277,7 +278,10 @@ struct IiwaEnv {
     HP v4z = HP(0), v7z = HP(0);
     ATACOM_UNROLL
     for (int j = 0; j < NJ; ++j) {
-      const Vec3<HP> ct = cross(zax[j], tip - org[j]);
+      // the tip lies on the axis of joint 7: its Jacobian column is exactly zero (env_base.py:147-151; "isolated
+      // joint 7"), not the rounding noise of the cross product — the sign of such noise would decide the sign of a
+      // Householder reflector of the LAPACK basis
+      const Vec3<HP> ct = (j == 6) ? Vec3<HP>{HP(0), HP(0), HP(0)} : cross(zax[j], tip - org[j]);
       vt = vt + dqh[j] * ct;
       HP c4z = HP(0), c7z = HP(0);
       if (j < 3) c4z = zax[j].x * (org[3].y - org[j].y) - zax[j].y * (org[3].x - org[j].x);
@@ -488,7 +492,7 @@ inline ParamsT<To> widen_params(const ParamsT<From>& P) {
   Q.variant = P.variant;
   Q.bias_mode = P.bias_mode;
   Q.clip_acc = P.clip_acc;
-  Q.reserved = P.reserved;
+  Q.basis_mode = P.basis_mode;
   for (int i = 0; i < 24; ++i) Q.env[i] = P.env[i];
   return Q;
 }
@@ -519,6 +523,52 @@ struct DualSink {
     else if (j == i - m) dg[j] = Kd.K[i] * v;
   }
 };
+
+// Assembly shared by the dual and the LAPACK-basis paths: ddq_ds = w_mn + w_null (variant E: alpha in place of the
+// null part), slack integration in HP (atacom.py:135), acceleration truncation (atacom.py:117-121).
+template <class D, typename T, typename HP>
+ATACOM_HD uint8_t finish_step(const ParamsT<T>& P, const DualConsts<HP>& Kd, const HP* w_mn, HP* w_null, const HP* sh,
+                              const T* alpha, const T* dq, T* ddq, HP* s_new, T* w_dbg, uint8_t st) {
+  constexpr int n = D::n, G = D::G, N = D::N;
+  const bool ec = P.variant == VARIANT_EC;
+  if (ec) {
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) w_null[j] = cvt<HP>(alpha[j]);    // error_correction_wrapper.py:127
+  }
+  bool finite = true;
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) {
+    const HP wz = cvt<HP>(w_mn[n + i]) + w_null[n + i];
+    s_new[i] = sh[i] + wz * Kd.dt;                                // atacom.py:135
+    finite = finite && (s_new[i] - s_new[i] == HP(0));
+  }
+  ATACOM_UNROLL
+  for (int j = 0; j < n; ++j) {
+    T a = cvt<T>(cvt<HP>(w_mn[j]) + w_null[j]);
+    finite = finite && (a - a == T(0));
+    if (P.clip_acc) {                                             // atacom.py:117-121
+      const T am = P.acc_max[j];
+      T up = -P.K_q[j] * (dq[j] - P.vel_max[j]);
+      up = up < am ? up : am;
+      up = up > -am ? up : -am;
+      T lo = -P.K_q[j] * (dq[j] + P.vel_max[j]);
+      lo = lo > -am ? lo : -am;
+      lo = lo < am ? lo : am;
+      a = a > lo ? a : lo;
+      a = a < up ? a : up;
+    }
+    ddq[j] = a;
+  }
+  if (w_dbg) {
+    ATACOM_UNROLL
+    for (int i = 0; i < N; ++i) {
+      w_dbg[i] = cvt<T>(w_mn[i]);
+      w_dbg[N + i] = cvt<T>(w_null[i]);
+    }
+  }
+  if (!finite) st |= ST_NONFINITE;
+  return st;
+}
 
 // The whole step around the dual projection (atacom_dual.cuh): everything between the fp32 inputs and
 // the fp32 outputs is carried in HP.
@@ -551,7 +601,8 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   // past the end of the batch recompute the last environment); a scratch slot is shared by the warps that map to
   // it under the lock stored behind it.
   constexpr bool COOP = is_shared_store<YS>::value && N >= 2 * n;
-  uint8_t st = Dual<HP, D, NDIAG>::template project<COOP>(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null);
+  const bool band_defer = P.basis_mode == BASIS_LAPACK && k > 1;     // (k = 1: the null basis is unique up to its sign)
+  uint8_t st = Dual<HP, D, NDIAG>::template project<COOP>(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null, band_defer);
   if constexpr (COOP) {
     using DU = Dual<HP, D, NDIAG>;
     unsigned pend = __ballot_sync(0xffffffffu, (st & ST_DENSE_PATH) != 0);
@@ -593,46 +644,11 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
     }
   }
 #else
-  uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null);
+  const bool band_defer = P.basis_mode == BASIS_LAPACK && k > 1;
+  uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null, band_defer);
 #endif
-  if (st & ST_DENSE_PATH) return st;
-  if (ec) {
-    ATACOM_UNROLL
-    for (int j = 0; j < n; ++j) w_null[j] = cvt<HP>(alpha[j]);    // error_correction_wrapper.py:127
-  }
-  bool finite = true;
-  ATACOM_UNROLL
-  for (int i = 0; i < G; ++i) {
-    const HP wz = cvt<HP>(w_mn[n + i]) + w_null[n + i];
-    s_new[i] = sh[i] + wz * Kd.dt;                                // atacom.py:135
-    finite = finite && (s_new[i] - s_new[i] == HP(0));
-  }
-  ATACOM_UNROLL
-  for (int j = 0; j < n; ++j) {
-    T a = cvt<T>(cvt<HP>(w_mn[j]) + w_null[j]);
-    finite = finite && (a - a == T(0));
-    if (P.clip_acc) {                                             // atacom.py:117-121
-      const T am = P.acc_max[j];
-      T up = -P.K_q[j] * (dq[j] - P.vel_max[j]);
-      up = up < am ? up : am;
-      up = up > -am ? up : -am;
-      T lo = -P.K_q[j] * (dq[j] + P.vel_max[j]);
-      lo = lo > -am ? lo : -am;
-      lo = lo < am ? lo : am;
-      a = a > lo ? a : lo;
-      a = a < up ? a : up;
-    }
-    ddq[j] = a;
-  }
-  if (w_dbg) {
-    ATACOM_UNROLL
-    for (int i = 0; i < N; ++i) {
-      w_dbg[i] = cvt<T>(w_mn[i]);
-      w_dbg[N + i] = cvt<T>(w_null[i]);
-    }
-  }
-  if (!finite) st |= ST_NONFINITE;
-  return st;
+  if (st & (ST_DENSE_PATH | ST_LAPACK_PATH)) return st;     // (only after the warp-wide ballot above)
+  return finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, s_new, w_dbg, st);
 }
 
 template <class Env, typename T, typename HP, class YS, class LS, class Fetch>
@@ -652,7 +668,7 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
   sink.add_slack_terms(sh);
   const uint8_t st = dual_tail<Env, T, HP>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg, coop, coop_slots,
                                            coop_stride);
-  if (st & ST_DENSE_PATH) return st;
+  if (st & (ST_DENSE_PATH | ST_LAPACK_PATH)) return st;
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
   return st;
@@ -669,6 +685,49 @@ ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
     for (int j = 0; j < D::n; ++j) a_row[j] = alpha[j];
   };
   return step_dual_lazy<Env, T, HP>(P, Kd, Y, Ls, q, dq, fetch, ddq, s_out, w_dbg);
+}
+
+// The whole step on the LAPACK-basis routine (atacom_lapack.cuh): what the step kernels run for the environments
+// the dual path flagged (Dual::project, band_defer), and the generic kernel for every environment.  S: a store of
+// Lapack<HP, D>::SIZE entries (a column of a shared-memory array on the device).
+template <class D, typename T, typename HP, class ST>
+ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST& S,
+                                       const RawConstraints<T, HP, D, HP>& R, const T* dq, const T* s, const T* alpha,
+                                       T* ddq, T* s_out, T* w_dbg) {
+  using LP = Lapack<HP, D>;
+  constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
+  const bool ec = P.variant == VARIANT_EC;
+  ATACOM_ROLLED
+  for (int e = 0; e < LP::SIZE; ++e) S.set(e, HP(0));
+  HP r[at_least_1<C>::value], sh[at_least_1<G>::value], sn[at_least_1<G>::value];
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
+  ATACOM_UNROLL
+  for (int i = 0; i < C; ++i) {
+    ATACOM_UNROLL
+    for (int j = 0; j < n; ++j) S.set(LP::a(i, j), Kd.K[i] * R.J[i][j]);                 // constraints.py:39-40
+    if (i >= F) S.set(LP::a(i, n + (i >= F ? i - F : 0)), sh[i >= F ? i - F : 0]);       // atacom.py:151-165
+    HP ri = Kd.K_c[i] * R.c[i] + Kd.wJ[i] * R.Jdq[i] + Kd.wb[i] * cvt<HP>(R.b[i]);       // see DualConsts
+    if (i >= F) ri += HP(0.5) * Kd.K_c[i] * sh[i >= F ? i - F : 0] * sh[i >= F ? i - F : 0];
+    r[i] = ri;
+  }
+  HP ah[at_least_1<k>::value], w_mn[N], w_null[N];
+  ATACOM_UNROLL
+  for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
+  uint8_t st = LP::project(S, r, ah, Kd.tol, !ec, w_mn, w_null) | ST_LAPACK_PATH;
+  st = finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, sn, w_dbg, st);
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
+  return st;
+}
+
+template <class Env, typename T, typename HP, class ST>
+ATACOM_HD uint8_t step_lapack(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST& S, const T* q, const T* dq, const T* s,
+                              const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+  using D = typename Env::D;
+  RawConstraints<T, HP, D, HP> R;
+  Env::template eval<T, HP>(P, q, dq, R);
+  return step_lapack_from_raw<D, T, HP>(P, Kd, S, R, dq, s, alpha, ddq, s_out, w_dbg);
 }
 
 // atacom.py:145-149

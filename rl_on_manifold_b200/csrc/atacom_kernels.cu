@@ -142,6 +142,11 @@ struct StepArgs {
   // ticket order, so the first blocks compute and store while the last ones are still waiting for PCIe
   int32_t gate_window;
   uint32_t* gate;
+  // ATACOM_BASIS_LAPACK: the environments the dual path leaves to the LAPACK-basis routine (Dual::project,
+  // band_defer).  Block b appends their indices to fix_list[b * blockDim.x ...] and stores how many in fix_count[b];
+  // the fix-up kernel (same grid) then redoes exactly those.  Null: nothing is deferred (canonical basis).
+  int32_t* fix_list;
+  int32_t* fix_count;
 };
 
 // ------------------------------------------------------------------ row access
@@ -203,6 +208,7 @@ struct StepScratch {
   // iiwa-6, two for iiwa-7; the 448-thread blocks take the 228 KB carve-out either way.
   static constexpr size_t SMEM_MAX = 227 * 1024;
   static constexpr size_t TICKET_OFFSET = 0;
+  static constexpr size_t FIXN_OFFSET = 4;       // number of environments this block left to the fix-up kernel
   static constexpr size_t COOP_OFFSET = 16;
   static constexpr size_t COOP_SLOT_BYTES = (sizeof(double) * DU::COOP_DOUBLES + 16 + 15) / 16 * 16;
   static constexpr size_t COOP_SPARE = SMEM_MAX - 128 - COOP_OFFSET - sizeof(uint64_t) * MAX_WARPS - WARP_BYTES * MAX_WARPS;
@@ -298,12 +304,15 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   // programmatic dependent launch (no-ops otherwise): let the next kernel's blocks queue up behind this one's,
   // and do not touch global memory before the previous kernel has completed
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (threadIdx.x == 0) SC::coop_init(atacom_smem);
+  if (threadIdx.x == 0) {
+    SC::coop_init(atacom_smem);
+    *reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::FIXN_OFFSET) = 0u;
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) {
     if (gated) *tk = atomicAdd(a.gate + 2, 1u);
   }
-  if (SC::SHARED || gated) __syncthreads();     // the only block barrier of the kernel, before any work (measured free)
+  if (SC::SHARED || gated || a.fix_list != nullptr) __syncthreads();     // before any work (measured free)
   if (gated) bid = *tk;
   const int64_t e_raw = static_cast<int64_t>(bid) * blockDim.x + threadIdx.x;
   const bool valid = e_raw < a.B;
@@ -434,8 +443,20 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
   if (IO == 1 && a.gate != nullptr) bid2 = *reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::TICKET_OFFSET);
   const int64_t e2 = static_cast<int64_t>(bid2) * blockDim.x + tid2;
   const int64_t wenv2 = e2 - lane2;
-  if (e2 < a.B && a.status) a.status[e2] = st;
+  // left to the fix-up kernel (which writes ddq, s_out and status of these environments): queue the index and
+  // leave the outputs alone — s_out may alias s_in, which that kernel still has to read
+  const bool fix = (st & ST_LAPACK_PATH) != 0;
+  if (fix && e2 < a.B) {
+    const unsigned pos = atomicAdd(reinterpret_cast<unsigned*>(atacom_smem + SC::FIXN_OFFSET), 1u);
+    a.fix_list[static_cast<int64_t>(bid2) * blockDim.x + pos] = static_cast<int32_t>(e2);
+  }
+  if (e2 < a.B && a.status && !fix) a.status[e2] = st;
   if ((IO == 1 || IO == 2) && ATACOM_X_BULK_STORE && a.aligned16 && (wenv2 + 32 <= a.B)) {
+    if (fix) {      // the slab store below covers this row too: hand the slack row on unchanged, a placeholder for ddq
+      if (G > 0) row_load<G1>(a.s_in, e2, so);
+#pragma unroll
+      for (int j = 0; j < n; ++j) ddq[j] = 0.f;
+    }
     float* oq = reinterpret_cast<float*>(SC::region(atacom_smem, static_cast<int>(tid2 >> 5)));
     float* os = oq + 32 * n;
     __syncwarp();     // every lane is done with its scratch
@@ -453,10 +474,14 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
       if (a.local_sync != nullptr) bulk_commit_wait_all();   // the step is published below: writes must have landed
       else bulk_commit_wait_read();
     }
-  } else if (e2 < a.B) {
+  } else if (e2 < a.B && !fix) {
     if (a.ddq) row_store<n>(a.ddq, e2, ddq);
     if (G > 0) row_store<G1>(a.s_out, e2, so);
     for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e2, ddq);
+  }
+  if (a.fix_list != nullptr) {
+    __syncthreads();                                   // every thread of the block has queued its environment
+    if (tid2 == 0) a.fix_count[bid2] = static_cast<int32_t>(*reinterpret_cast<volatile uint32_t*>(atacom_smem + SC::FIXN_OFFSET));
   }
   // Ordered admission: the last warp of the launch (every ticket taken, every gate passed) zeroes the counters.
   if (IO == 1 && a.gate != nullptr && lane2 == 0) {
@@ -610,6 +635,75 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_substeps_kernel(const __
   }
 }
 
+// ------------------------------------------------------------------ fix-up: the LAPACK-basis routine on the deferred
+// environments (ATACOM_BASIS_LAPACK).  Block b works through segment b of the list the step kernel wrote — ~21 % of
+// the batch at the benchmark's mix of active constraints, compacted per block — one thread per environment, the
+// C x N working array of atacom_lapack.cuh as a column of a [cell][thread] shared-memory array.
+struct FixArgs {
+  const float* q;
+  const float* dq;
+  const float* s_in;
+  const float* alpha;
+  float* ddq;
+  float* s_out;
+  uint8_t* status;
+  float* w_dbg;
+  const int32_t* fix_list;
+  const int32_t* fix_count;
+  int32_t seg_stride;       // block size of the step kernel = length of a segment
+  float* peer[ATACOM_MAX_PEERS];
+  int64_t gather_row0;
+  int32_t n_peers;
+};
+
+template <class Env>
+struct FixCfg {
+  using LP = Lapack<double, typename Env::D>;
+  static constexpr size_t SMEM_MAX = 227 * 1024;
+  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE));
+  static constexpr int TPB = FIT >= 128 ? 128 : (FIT / 32) * 32;       // iiwa-6: 128 (204 KB), iiwa-7: 96
+  static_assert(TPB >= 32, "the LAPACK working array of one warp does not fit into shared memory");
+  static constexpr size_t BYTES = sizeof(double) * LP::SIZE * TPB;
+};
+
+template <class Env>
+__global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __grid_constant__ FixArgs a,
+                                                                      const __grid_constant__ ParamsT<float> P,
+                                                                      const __grid_constant__ DualConsts<double> Kd) {
+  using D = typename Env::D;
+  constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
+  constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
+  constexpr int FTPB = FixCfg<Env>::TPB;
+  extern __shared__ __align__(128) unsigned char atacom_smem[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the step kernel has completed: list, counts and its outputs are visible
+  const int cnt = a.fix_count[blockIdx.x];
+  const int32_t* seg = a.fix_list + static_cast<int64_t>(blockIdx.x) * a.seg_stride;
+  SharedStore<double, FTPB> S{reinterpret_cast<double*>(atacom_smem) + threadIdx.x};
+  const bool ec = P.variant == VARIANT_EC;
+  for (int t = threadIdx.x; t < cnt; t += FTPB) {
+    const int64_t e = seg[t];
+    float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
+    row_load<n>(a.q, e, q);
+    row_load<n>(a.dq, e, dq);
+    if (G > 0) row_load<G1>(a.s_in, e, s);
+    if (ec) {
+      row_load<n>(a.alpha, e, al);
+    } else {
+      float ak[K1];
+      if (k > 0) row_load<K1>(a.alpha, e, ak);
+#pragma unroll
+      for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
+    }
+    float* dbg = a.w_dbg ? a.w_dbg + e * (2 * N) : nullptr;
+    const uint8_t st = step_lapack<Env, float, double>(P, Kd, S, q, dq, s, al, ddq, so, dbg);
+    if (a.status) a.status[e] = st;
+    if (a.ddq) row_store<n>(a.ddq, e, ddq);
+    if (G > 0) row_store<G1>(a.s_out, e, so);
+    for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
+  }
+}
+
 template <class Env>
 __global__ void __launch_bounds__(TPB) atacom_slack_init_kernel(const float* __restrict__ q,
                                                                 const float* __restrict__ dq, float* s,
@@ -674,6 +768,56 @@ __global__ void __launch_bounds__(TPB) atacom_generic_kernel(const float* __rest
   for (int i = 0; i < G; ++i) s[i] = a.s_in[e * G + i];
   double dbg[2 * N];
   const uint8_t st = step_from_raw<double, double, D, 0>(P, R, dq, s, al, ddq, so, a.w_dbg ? dbg : nullptr);
+  if (a.status) a.status[e] = st;
+#pragma unroll
+  for (int j = 0; j < n; ++j) a.ddq[e * n + j] = static_cast<float>(ddq[j]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) a.s_out[e * G + i] = static_cast<float>(so[i]);
+  if (a.w_dbg) {
+#pragma unroll
+    for (int i = 0; i < 2 * N; ++i) a.w_dbg[e * (2 * N) + i] = static_cast<float>(dbg[i]);
+  }
+}
+
+// The same with the reference's LAPACK null basis (ATACOM_BASIS_LAPACK, the default): every environment goes
+// through atacom_lapack.cuh, the working array in local memory.
+template <int n_, int F_, int G_>
+__global__ void __launch_bounds__(TPB) atacom_generic_lapack_kernel(const float* __restrict__ c,
+                                                                    const float* __restrict__ J,
+                                                                    const float* __restrict__ b, StepArgs a,
+                                                                    const __grid_constant__ ParamsT<double> P,
+                                                                    const __grid_constant__ DualConsts<double> Kd) {
+  using D = Dims<n_, F_, G_>;
+  constexpr int n = D::n, G = D::G, k = D::k, C = D::C, N = D::N;
+  constexpr int G1 = at_least_1<G>::value;
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TPB + threadIdx.x;
+  if (e >= a.B) return;
+  const bool ec = P.variant == VARIANT_EC;
+  const int na = ec ? n : k;
+  double dq[n], s[G1], al[n], ddq[n], so[G1];
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    dq[j] = a.dq[e * n + j];
+    al[j] = j < na ? static_cast<double>(a.alpha[e * na + j]) : 0.0;
+  }
+  RawConstraints<double, double, D> R;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    R.c[i] = c[e * C + i];
+    R.b[i] = b[e * C + i];
+    double jdq = 0.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      R.J[i][j] = J[(e * C + i) * n + j];
+      jdq += R.J[i][j] * dq[j];
+    }
+    R.Jdq[i] = jdq;
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) s[i] = a.s_in[e * G + i];
+  double dbg[2 * N];
+  ArrayStore<double, Lapack<double, D>::SIZE> S;
+  const uint8_t st = step_lapack_from_raw<D, double, double>(P, Kd, S, R, dq, s, al, ddq, so, a.w_dbg ? dbg : nullptr);
   if (a.status) a.status[e] = st;
 #pragma unroll
   for (int j = 0; j < n; ++j) a.ddq[e * n + j] = static_cast<float>(ddq[j]);
@@ -1083,6 +1227,19 @@ bool configure_step_kernel() {
   return state.load(std::memory_order_acquire) == 1;
 }
 
+template <class Env>
+bool configure_fix_kernel() {
+  static std::atomic<int> states[MAX_DEVICES];
+  std::atomic<int>& state = states[current_device()];
+  if (state.load(std::memory_order_acquire) == 0) {
+    state.store((FixCfg<Env>::BYTES <= 48 * 1024 ||
+                 cudaFuncSetAttribute(atacom_fix_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(FixCfg<Env>::BYTES)) == cudaSuccess) ? 1 : -1,
+                std::memory_order_release);
+  }
+  return state.load(std::memory_order_acquire) == 1;
+}
+
 template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : ATACOM_STEP_DEVICE_IO)>
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
@@ -1097,7 +1254,8 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   if (!q || !dq || (!ddq && n_peers == 0) || (D::G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   const bool needs_alpha = p->variant == ATACOM_VARIANT_ERROR_CORRECTION || D::k > 0;
   if (needs_alpha && !alpha) return ATACOM_ERR_NULL_POINTER;
-  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0, {}, nullptr, rank, 0, nullptr};
+  StepArgs a{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, gather_row0, n_peers, 0, {}, nullptr, rank, 0, nullptr,
+             nullptr, nullptr};
   if (IO == 1 && gate != nullptr && gate_window > 0) {
     a.gate = gate;
     a.gate_window = gate_window;
@@ -1122,6 +1280,48 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   const size_t smem = StepScratch<Env>::bytes(tpb);
   if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
+  NvtxRange range("atacom_step");
+  // ATACOM_BASIS_LAPACK (default): the step kernel leaves the environments inside the tolerance band of rref to the
+  // fix-up kernel.  The per-block lists live in stream-ordered scratch memory (capturable in a CUDA graph).
+  const bool two_pass = p->basis_mode == ATACOM_BASIS_LAPACK && p->variant == ATACOM_VARIANT_ATACOM && D::k > 1;
+  if (p->basis_mode != ATACOM_BASIS_LAPACK && p->basis_mode != ATACOM_BASIS_CANONICAL) return ATACOM_ERR_BAD_PARAM;
+  if (two_pass && local_sync) return ATACOM_ERR_BAD_PARAM;   // the in-kernel barrier would publish the step before the fix-up
+  int32_t* scratch = nullptr;
+  if (two_pass) {
+    if (!configure_fix_kernel<Env>()) return ATACOM_ERR_CUDA;
+    const size_t bytes = sizeof(int32_t) * (static_cast<size_t>(grid) * tpb + grid);
+    if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+      cudaGetLastError();
+      return ATACOM_ERR_CUDA;
+    }
+    a.fix_list = scratch;
+    a.fix_count = scratch + static_cast<size_t>(grid) * tpb;
+  }
+  auto fix_up = [&]() -> int {      // second launch + release of the scratch, after the step kernel is in the stream
+    if (!two_pass) return ATACOM_OK;
+    FixArgs f{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, a.fix_list, a.fix_count, tpb, {}, gather_row0, n_peers};
+    for (int w = 0; w < n_peers; ++w) f.peer[w] = peers[w];
+    const ParamsT<float> Pk = as_params(p);
+    const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(static_cast<unsigned>(FixCfg<Env>::TPB));
+    cfg.dynamicSmemBytes = FixCfg<Env>::BYTES;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = step_pdl_enabled() ? 1 : 0;
+    const bool ok = cudaLaunchKernelEx(&cfg, atacom_fix_kernel<Env>, f, Pk, Kd) == cudaSuccess;
+    cudaFreeAsync(scratch, static_cast<cudaStream_t>(stream));
+    if (!ok) {
+      cudaGetLastError();
+      return ATACOM_ERR_CUDA;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ATACOM_OK;
+  };
   if (step_pdl_enabled() && IO != 1 && n_peers == 0) {   // (fused gather: measured neutral to slightly slower, left out)
     // Programmatic dependent launch: the blocks of this launch may start — one by one, as the blocks of the
     // previous kernel in the stream leave their SMs — and set up while that kernel drains; they touch global
@@ -1140,15 +1340,21 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
     if (cudaLaunchKernelEx(&cfg, atacom_step_kernel<Env, IO>, a, Pk, Kd) != cudaSuccess) {
       cudaGetLastError();
+      if (scratch) cudaFreeAsync(scratch, static_cast<cudaStream_t>(stream));
       return ATACOM_ERR_CUDA;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return ATACOM_OK;
+    return fix_up();
   }
   atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
       a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return check_launch();
+  rc = check_launch();
+  if (rc != ATACOM_OK) {
+    if (scratch) cudaFreeAsync(scratch, static_cast<cudaStream_t>(stream));
+    return rc;
+  }
+  return fix_up();
 }
 
 template <class Env>
@@ -1400,6 +1606,16 @@ int atacom_iiwa_step_substeps(int n, int K, const float* q, const float* dq, con
   if ((n != 6 && n != 7) || K < 1 || K > 64) return ATACOM_ERR_BAD_DIMS;
   if (B == 0) return ATACOM_OK;
   if (!q || !dq || !s_in || !alpha || !ddq || !s_out) return ATACOM_ERR_NULL_POINTER;
+  if (p->basis_mode == ATACOM_BASIS_LAPACK && p->variant == ATACOM_VARIANT_ATACOM) {
+    // every sub-step may leave environments to the fix-up kernel, and the next sub-step needs their slacks: K
+    // two-pass steps back to back (the fused single launch is the canonical-basis mode's)
+    for (int kk = 0; kk < K; ++kk) {
+      rc = atacom_iiwa_step(n, q, dq, kk == 0 ? s_in : s_out, alpha, ddq + static_cast<int64_t>(kk) * B * n, s_out,
+                            status, nullptr, B, p, stream);      // (status: the last sub-step's)
+      if (rc != ATACOM_OK) return rc;
+    }
+    return ATACOM_OK;
+  }
   SubstepArgs a{q, dq, s_in, alpha, ddq, s_out, status, workspace, B, K};
   const int tpb = step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
@@ -1562,9 +1778,21 @@ int atacom_generic_step(int n, int F, int G, const float* c, const float* J, con
   if (!c || !J || !b || !dq || !ddq || (G > 0 && (!s_in || !s_out))) return ATACOM_ERR_NULL_POINTER;
   if ((p->variant == ATACOM_VARIANT_ERROR_CORRECTION || n - F > 0) && !alpha) return ATACOM_ERR_NULL_POINTER;
   if (B == 0) return ATACOM_OK;
-  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0, 0, {}, nullptr, 0};
+  StepArgs a{nullptr, dq, s_in, alpha, ddq, s_out, status, w_dbg, B, {}, 0, 0, 0, {}, nullptr, 0, 0, nullptr, nullptr,
+             nullptr};
   const ParamsT<double> Pd = widen_params<double>(as_params(p));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->basis_mode != ATACOM_BASIS_LAPACK && p->basis_mode != ATACOM_BASIS_CANONICAL) return ATACOM_ERR_BAD_PARAM;
+  if (p->basis_mode == ATACOM_BASIS_LAPACK) {      // the reference's own null basis, every environment
+    const DualConsts<double> Kd = make_dual_consts<double, double>(Pd, F, G);
+#define X(n_, F_, G_)                                                                             \
+  if (n == n_ && F == F_ && G == G_)                                                              \
+    atacom_generic_lapack_kernel<n_, F_, G_><<<blocks_for(B), TPB, 0, st>>>(c, J, b, a, Pd, Kd);
+    ATACOM_GENERIC_SHAPES(X)
+#undef X
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch();
+  }
 #define X(n_, F_, G_)                                                                             \
   if (n == n_ && F == F_ && G == G_)                                                              \
     atacom_generic_kernel<n_, F_, G_><<<blocks_for(B), TPB, 0, st>>>(c, J, b, a, Pd);
@@ -1806,7 +2034,7 @@ static int step_host(AtacomHostCtx* c, int family_id, const float* q, const floa
   // every kernel instantiation the call may use opts in to its shared memory now, not while capturing
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
   if (!configure_step_kernel<Env, ATACOM_STEP_DEVICE_IO>() || !configure_step_kernel<Env, HOST_IO>() ||
-      !configure_step_kernel<Env, 2>())
+      !configure_step_kernel<Env, 2>() || !configure_fix_kernel<Env>())
     return ATACOM_ERR_CUDA;
   step_block_size(1);
   HostCall call = {};

@@ -13,7 +13,19 @@ HARNESS_DIR = os.path.join(ROOT, "tests", "host_harness")
 CSRC = os.path.join(ROOT, "rl_on_manifold_b200", "csrc")
 
 # the null basis the product's default mode reproduces (see oracle/nullspace.py)
-REFERENCE_BASIS = "canonical"
+REFERENCE_BASIS = "svd"          # SciPy's own SVD null basis: what atacom.py:127 hands to rref
+
+# the two null-basis modes of the kernels and the oracle basis each one reproduces
+ORACLE_BASIS = {"lapack": "svd", "canonical": "canonical"}
+
+
+def with_basis(params, mode):
+    """Copy of `params` in the given basis mode ("lapack": the reference's own null basis, the default;
+    "canonical": the basis-free fast path alone)."""
+    p = params.copy()
+    p.basis_mode = {"lapack": 0, "canonical": 1}[mode]
+    return p
+
 
 ENV_ID = {"circle": 0, "planar": 1, "iiwa6": 2, "iiwa7": 3}
 DIMS = {"circle": (2, 1, 1), "planar": (3, 0, 6), "iiwa6": (6, 1, 11), "iiwa7": (7, 1, 12)}
@@ -58,6 +70,18 @@ def harness_dense(lib, n, F, G, Af, Ag, s, r, alpha, tol, dtype=np.float32):
     wmn, wn, st = np.zeros((B, N), dtype), np.zeros((B, N), dtype), np.zeros(B, np.uint8)
     ct = ctypes.c_float if dtype == np.float32 else ctypes.c_double
     rc = fn(n, F, G, ctypes.c_int64(B), *[_p(a) for a in arrs], ct(tol), _p(wmn), _p(wn), _p(st))
+    assert rc == 0, "shape not compiled into the harness"
+    return wmn, wn, st
+
+
+def harness_lapack(lib, n, F, G, Af, Ag, s, r, alpha, tol):
+    """The LAPACK-basis routine (atacom_lapack.cuh) built for the host in double."""
+    B = s.shape[0] if G else alpha.shape[0]
+    N = n + G
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Af, Ag, s, r, alpha)]
+    wmn, wn, st = np.zeros((B, N)), np.zeros((B, N)), np.zeros(B, np.uint8)
+    rc = lib.harness_lapack_f64(n, F, G, ctypes.c_int64(B), *[_p(a) for a in arrs], ctypes.c_double(tol), _p(wmn), _p(wn),
+                                _p(st))
     assert rc == 0, "shape not compiled into the harness"
     return wmn, wn, st
 
@@ -108,7 +132,7 @@ def oracle_eval(family, q, dq, bias="omega_x_v"):
     return oenv.iiwa_eval(q, dq, bias)
 
 
-def oracle_batch(family, q, dq, s, alpha, basis="canonical", variant="atacom", bias="omega_x_v", spec=None):
+def oracle_batch(family, q, dq, s, alpha, basis="svd", variant="atacom", bias="omega_x_v", spec=None):
     """Run the per-env oracle over a batch (float64 views of the fp32 inputs).  Returns dict of arrays
     plus per-env flags: fired (tolerance branch), rank_def, margin (distance of the closest pivot
     candidate to the tolerance, relative)."""
@@ -154,7 +178,7 @@ def oracle_point_reach_batch(q, dq, p, dp, s, action):
     return out
 
 
-def oracle_batch_mp(family, *arrays, basis="canonical", variant="atacom", bias="omega_x_v", tmpdir=None):
+def oracle_batch_mp(family, *arrays, basis="svd", variant="atacom", bias="omega_x_v", tmpdir=None):
     """`oracle_batch` (or `oracle_point_reach_batch` for family "point_reach") fanned out over all host cores in a
     separate interpreter (tests/oracle_mp.py): what makes parity at BASELINE.json's full batch sizes affordable."""
     import sys

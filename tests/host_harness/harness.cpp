@@ -6,6 +6,7 @@
 #include <cstdint>
 #include "../../rl_on_manifold_b200/csrc/atacom_envs.cuh"
 #include "../../rl_on_manifold_b200/csrc/atacom_structured.cuh"
+#include "../../rl_on_manifold_b200/csrc/atacom_lapack.cuh"
 
 using namespace atacom;
 
@@ -16,6 +17,24 @@ static void run_dense(int64_t B, const T* Af, const T* Ag, const T* s, const T* 
   for (int64_t b = 0; b < B; ++b) {
     status[b] = project_dense<T, D>(Af + b * F * n, Ag + b * G * n, s + b * G, r + b * D::C,
                                     alpha + b * D::k, tol, true, w_mn + b * D::N, w_null + b * D::N);
+  }
+}
+
+// the LAPACK-basis routine (atacom_lapack.cuh) on the same interface: Jc assembled from A_f, A_g, s
+template <typename T, int n, int F, int G>
+static void run_lapack(int64_t B, const T* Af, const T* Ag, const T* s, const T* r, const T* alpha, T tol,
+                       T* w_mn, T* w_null, uint8_t* status) {
+  using D = Dims<n, F, G>;
+  using LP = Lapack<T, D>;
+  for (int64_t b = 0; b < B; ++b) {
+    ArrayStore<T, LP::SIZE> S;
+    for (int i = 0; i < LP::SIZE; ++i) S.set(i, T(0));
+    for (int i = 0; i < D::C; ++i)
+      for (int j = 0; j < n; ++j) S.set(LP::a(i, j), i < F ? Af[(b * F + i) * n + j] : Ag[(b * G + i - F) * n + j]);
+    for (int i = 0; i < G; ++i) S.set(LP::a(F + i, n + i), s[b * G + i]);
+    T rr[D::C > 0 ? D::C : 1];
+    for (int i = 0; i < D::C; ++i) rr[i] = r[b * D::C + i];
+    status[b] = LP::project(S, rr, alpha + b * D::k, tol, true, w_mn + b * D::N, w_null + b * D::N);
   }
 }
 
@@ -41,6 +60,11 @@ int harness_dense_f64(int n, int F, int G, int64_t B, const double* Af, const do
                       uint8_t* status) {
   DISPATCH(double, run_dense)
 }
+int harness_lapack_f64(int n, int F, int G, int64_t B, const double* Af, const double* Ag, const double* s,
+                       const double* r, const double* alpha, double tol, double* w_mn, double* w_null,
+                       uint8_t* status) {
+  DISPATCH(double, run_lapack)
+}
 }
 
 // ---- full step: env functor + viability terms + projection + slack integration + clipping
@@ -60,7 +84,7 @@ static ParamsT<T> unpack(const double* f) {
   P.variant = (int32_t)*p++;
   P.bias_mode = (int32_t)*p++;
   P.clip_acc = (int32_t)*p++;
-  P.reserved = (int32_t)*p++;
+  P.basis_mode = (int32_t)*p++;
   for (int i = 0; i < 24; ++i) P.env[i] = *p++;
   return P;
 }
@@ -99,6 +123,11 @@ static void run_step(int64_t B, const double* params, const T* q, const T* dq, c
       LocalStore<double, DU::L_SIZE> Ls;
       uint8_t st = step_dual<Env, T, double>(P, Kd, Ys, Ls, q + b * D::n, dq + b * D::n, s + b * D::G, al,
                                              ddq + b * D::n, s_out + b * D::G, w_dbg + b * 2 * D::N);
+      if (st & ST_LAPACK_PATH) {   // what the fix-up kernel does for the environments the dual path flagged
+        ArrayStore<double, Lapack<double, D>::SIZE> S;
+        st = step_lapack<Env, T, double>(P, Kd, S, q + b * D::n, dq + b * D::n, s + b * D::G, al, ddq + b * D::n,
+                                         s_out + b * D::G, w_dbg + b * 2 * D::N);
+      }
       status[b] = st;
     }
   }

@@ -38,6 +38,17 @@ def _worker(rank, world, port, B, out):
     # cross-rank barrier inside the kernel / as a separate launch on the kernel's stream / deferred to a side stream
     for kw in (dict(in_kernel_barrier=True), dict(), dict(deferred=True)):
         fg = SymmetricGather(B, 6, **kw)
+        if kw.get("in_kernel_barrier"):
+            # the barrier inside the step kernel would publish a step before the fix-up launch of the default
+            # (LAPACK-basis) mode has written its rows: this variant exists for the canonical mode only
+            pk = params.copy()
+            pk.basis_mode = _lib.BASIS_CANONICAL
+            want_ddq, want_s = projection.step("iiwa", q, dq, s, alpha, pk)
+            for it in range(5):
+                gathered, s_f = fg.step(sq, sdq, ss, sal, pk)
+                ok = ok and torch.equal(gathered, want_ddq) and torch.equal(s_f, want_s[shard.lo:shard.hi])
+            torch.cuda.synchronize()
+            continue
         for it in range(7):                                                   # exercises every buffer twice
             gathered, s_f = fg.step(sq, sdq, ss, sal, params)
             # no host synchronisation between launch and check: waiting on the step's own completion (the stream

@@ -37,10 +37,13 @@ def _run(family, q, dq, s, alpha, params, dev, dbg=True):
 
 
 @pytest.mark.parametrize("family,B", [("circle", 4096), ("planar", 2048), ("iiwa6", 2048), ("iiwa7", 512)])
-def test_step_vs_oracle(cuda_device, family, B):
+@pytest.mark.parametrize("mode", ["lapack", "canonical"])
+def test_step_vs_oracle(cuda_device, family, B, mode):
+    """Mode "lapack" (the default): against the oracle on SciPy's own SVD null basis — the reference's computation,
+    atacom.py:127-128 — on both strata; mode "canonical": the fast path alone against the canonical basis."""
     q, dq, s, alpha = helpers.synthetic_cpu(family, B, seed=1234)
-    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
-    ddq, s_out, dbg, st = _run(family, q, dq, s, alpha, _params(family), cuda_device)
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis=helpers.ORACLE_BASIS[mode])
+    ddq, s_out, dbg, st = _run(family, q, dq, s, alpha, helpers.with_basis(_params(family), mode), cuda_device)
     N = ref["w"].shape[1]
     ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
     assert ok.mean() > 0.9
@@ -61,7 +64,8 @@ def test_step_vs_oracle(cuda_device, family, B):
 
 @pytest.mark.parametrize("family", ["planar", "iiwa6", "iiwa7"])
 @pytest.mark.parametrize("active", [2, 3, 4])
-def test_several_active_constraints(cuda_device, family, active):
+@pytest.mark.parametrize("mode", ["lapack", "canonical"])
+def test_several_active_constraints(cuda_device, family, active, mode):
     """Two, three or four constraints exactly active at once (s_i = 0: that many slack pivots).  Two stay on the
     thread's own closed form; three or more take the general null-space routine, which the iiwa kernels run
     warp-cooperatively (Dual::null_part_general_warp: every lane of the warp works on one environment at a time,
@@ -75,8 +79,8 @@ def test_several_active_constraints(cuda_device, family, active):
     rng = np.random.default_rng(8)
     for i in range(B):
         s[i, rng.choice(G, active, replace=False)] = 0.0
-    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
-    ddq, s_out, dbg, st = _run(family, q, dq, s, alpha, _params(family), cuda_device)
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis=helpers.ORACLE_BASIS[mode])
+    ddq, s_out, dbg, st = _run(family, q, dq, s, alpha, helpers.with_basis(_params(family), mode), cuda_device)
     N = n + G
     ok = ~ref["rank_def"] & (ref["margin"] > 1e-3)
     assert ok.sum() > 0.3 * B
@@ -95,7 +99,7 @@ def test_stratum_one_equals_reference_svd_basis(cuda_device, family):
     q, dq, s, alpha = helpers.synthetic_cpu(family, 512, seed=99)
     ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="svd")
     can = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
-    ddq, s_out, _, _ = _run(family, q, dq, s, alpha, _params(family), cuda_device, dbg=False)
+    ddq, s_out, _, _ = _run(family, q, dq, s, alpha, helpers.with_basis(_params(family), "canonical"), cuda_device, dbg=False)
     stratum1 = ~ref["fired"] & ~can["fired"] & ~ref["rank_def"]
     assert stratum1.mean() > 0.5
     assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[stratum1].all()
@@ -173,7 +177,12 @@ def test_circle_single_projection_golden(cuda_device, golden):
 
 
 @pytest.mark.parametrize("tag", GENERIC)
-def test_generic_constraint_set_golden(cuda_device, golden, tag):
+@pytest.mark.parametrize("mode", ["lapack", "canonical"])
+def test_generic_constraint_set_golden(cuda_device, golden, tag, mode):
+    """AtacomEnvWrapper.step_action_function recorded from the reference itself on synthetic ConstraintsSets.  In the
+    default mode EVERY recorded case must be reproduced — also those in which the reference's rref fired its
+    tolerance branch (a quarter of them have a slack <= 0.02) — because the kernel uses the reference's own LAPACK
+    null basis; the canonical mode is held to the cases where the branch stayed silent."""
     spec = generic_spec(golden[tag + "_meta"])
     n, F, G = spec.n, spec.F, spec.G
     assert projection.generic_supported(n, F, G)
@@ -181,6 +190,7 @@ def test_generic_constraint_set_golden(cuda_device, golden, tag):
     p.K_f[:F] = list(spec.K_f); p.K_g[:G] = list(spec.K_g); p.K_c[:F + G] = list(spec.K_c)
     p.K_q[:n] = list(spec.K_q); p.vel_max[:n] = list(spec.vel_max); p.acc_max[:n] = list(spec.acc_max)
     p.dt, p.rref_tol, p.clip_acc = spec.dt, 0.05, 1
+    p = helpers.with_basis(p, mode)
     dev = cuda_device
     t = {k: torch.from_numpy(np.ascontiguousarray(golden["%s_%s" % (tag, k)], dtype=np.float32)).to(dev)
          for k in ("c", "J", "b", "dq", "s", "alpha")}
@@ -201,6 +211,19 @@ def test_generic_constraint_set_golden(cuda_device, golden, tag):
         tr = [ao.atacom_step(spec, ev, g["dq"], g["s"], g["alpha"], basis=bs)["trace"] for bs in ("svd", "canonical")]
         fired.append(any(pv > 1e-9 for t_ in tr for (_, _, pv) in t_["dropped"]))
     keep = ~np.array(fired)
+    if mode == "lapack":
+        # the inputs were rounded to fp32 on the way in: a recorded case whose pivot candidate sits within 1e-4 of the
+        # tolerance may decide differently; everything else must match, fired or not
+        near = []
+        for i in range(B):
+            g = {k: golden["%s_%s" % (tag, k)][i] for k in ("c", "J", "b", "dq", "s", "alpha")}
+            ev = ao.ConstraintEval(c_f=g["c"][:F], J_f=g["J"][:F], b_f=g["b"][:F], c_g=g["c"][F:], J_g=g["J"][F:], b_g=g["b"][F:])
+            tr = ao.atacom_step(spec, ev, g["dq"], g["s"], g["alpha"], basis="svd")["trace"]
+            cand = [pv for (_, _, pv) in tr.get("pivots", []) + tr.get("dropped", [])] if tr else []
+            near.append(any(abs(pv - 0.05) < 5e-6 for pv in cand))
+        keep = ~np.array(near)
+        print("\n[%s] %d recorded cases, tolerance branch fired in %d, all compared but %d" % (tag, B, sum(fired), (~keep).sum()))
+        assert keep.sum() >= B - 1
     assert helpers.rel_err(w_dbg[:, N:].cpu().numpy()[keep], golden[tag + "_act_b"][keep]).max() < 5e-6
     assert helpers.rel_err(ddq.cpu().numpy()[keep], golden[tag + "_ddq"][keep]).max() < 5e-6
 
@@ -451,7 +474,7 @@ def test_fused_substeps_equal_repeated_steps(cuda_device, nj):
         ev = helpers.oracle_eval(fam, qn[i], dqn[i])
         si = sn[i].copy()
         for kk in range(K):
-            o = ao.atacom_step(spec, ev, dqn[i], si, an[i], basis="canonical")
+            o = ao.atacom_step(spec, ev, dqn[i], si, an[i], basis="svd")
             tr = o["trace"]
             cand = [pv for (_, _, pv) in tr["pivots"] + tr["dropped"]]
             if o["rank"] < spec.C or min(abs(pv - spec.tol) / spec.tol for pv in cand) < 1e-3:

@@ -199,7 +199,7 @@ def test_generic_constraints_set_through_wrapper(cuda_device):
         ev = ao.ConstraintEval(c_f=np.array([(qn[i] ** 2).sum() - 1]), J_f=2 * qn[i][None], b_f=np.array([2 * (dqn[i] ** 2).sum()]),
                                c_g=qn[i] - 0.9, J_g=np.eye(3), b_g=np.zeros(3))
         np.testing.assert_allclose(s0[i], ao.slack_init(spec, ev, dqn[i]), atol=1e-6)
-        o = ao.atacom_step(spec, ev, dqn[i], s0[i], ao.scale_action(spec, action[i].double().numpy()), basis="canonical")
+        o = ao.atacom_step(spec, ev, dqn[i], s0[i], ao.scale_action(spec, action[i].double().numpy()), basis="svd")
         if any(p > 1e-9 and abs(p - 0.05) < 5e-4 for (_, _, p) in o["trace"]["dropped"] + o["trace"]["pivots"]):
             continue
         worst = max(worst, np.abs(ddq[i] - o["ddq"]).max() / max(1.0, np.abs(o["w"]).max()))

@@ -43,10 +43,15 @@ def test_default_params_match_reference_constructor_values(family):
 
 @pytest.mark.parametrize("family,B", [("circle", 400), ("planar", 400), ("iiwa6", 500), ("iiwa7", 200)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_full_step_vs_oracle(harness, family, B, dtype):
+@pytest.mark.parametrize("mode", ["lapack", "canonical"])
+def test_full_step_vs_oracle(harness, family, B, dtype, mode):
+    """The step as the kernels run it (host build of the same source).  Mode "lapack" (default): the dual fast path
+    + the LAPACK-basis routine for the flagged environments, against the oracle on SciPy's SVD null basis — the
+    reference's own computation — on BOTH strata; mode "canonical": the fast path alone against the canonical basis."""
     q, dq, s, alpha = helpers.synthetic_cpu(family, B, seed=1234)
-    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
-    pf = _params(family).flat() if dtype == np.float32 else helpers.exact_params_flat(family, _params(family))
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis=helpers.ORACLE_BASIS[mode])
+    pm = helpers.with_basis(_params(family), mode)
+    pf = pm.flat() if dtype == np.float32 else helpers.exact_params_flat(family, pm)
     ddq, s_out, dbg, st = helpers.harness_step(harness, family, pf, q, dq, s, alpha, dtype)
     N = ref["w"].shape[1]
     ok = ~ref["rank_def"]
@@ -65,6 +70,15 @@ def test_full_step_vs_oracle(harness, family, B, dtype):
     dropped = (st & _lib.ST_COLUMN_DROPPED) != 0
     assert (dropped[ok] >= ref["fired"][ok]).all()
     assert ((st & _lib.ST_NONFINITE) == 0).all()
+    if mode == "lapack":
+        # every environment in which the reference's rref fires was handed to the LAPACK-basis routine (the band
+        # criterion of Dual::project is a superset), and the band stays a minority
+        redone = (st & _lib.ST_LAPACK_PATH) != 0
+        assert (redone[ok] >= ref["fired"][ok]).all() or family == "circle"
+        assert redone.mean() < 0.45
+        print("\n[%s %s] fired %.3f, redone with the LAPACK basis %.3f" % (family, dtype.__name__, ref["fired"].mean(), redone.mean()))
+    else:
+        assert ((st & _lib.ST_LAPACK_PATH) == 0).all()
 
 
 @pytest.mark.parametrize("family", ["circle", "planar", "iiwa6"])
@@ -74,7 +88,8 @@ def test_stratum_one_equals_reference_svd_basis(harness, family):
     q, dq, s, alpha = helpers.synthetic_cpu(family, 300, seed=99)
     ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="svd")
     can = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
-    ddq, s_out, dbg, st = helpers.harness_step(harness, family, _params(family).flat(), q, dq, s, alpha, np.float32)
+    pc = helpers.with_basis(_params(family), "canonical")
+    ddq, s_out, dbg, st = helpers.harness_step(harness, family, pc.flat(), q, dq, s, alpha, np.float32)
     stratum1 = ~ref["fired"] & ~can["fired"] & ~ref["rank_def"]
     assert stratum1.sum() > 0.5 * len(stratum1)
     assert (helpers.rel_err(ddq, ref["ddq"], ref["w"]) < 2e-6)[stratum1].all()
@@ -190,7 +205,8 @@ def test_point_reach_vs_oracle_and_golden(harness, golden):
 
 @pytest.mark.parametrize("family", ["circle", "planar", "iiwa6", "iiwa7"])
 @pytest.mark.parametrize("case", ["one_zero", "one_tiny", "two_zero", "two_small", "three_zero", "all_large"])
-def test_dual_projection_edge_cases(harness, family, case):
+@pytest.mark.parametrize("mode", ["lapack", "canonical"])
+def test_dual_projection_edge_cases(harness, family, case, mode):
     """The dual path (atacom_dual.cuh) of the step kernels at the corners of its domain: an exactly active
     constraint (s_i = 0, what reset produces for a violated constraint, atacom.py:145-149), a nearly active one
     (s_i = 1e-7), two of them at once (two slack pivots: the dual path defers, the general path answers),
@@ -206,9 +222,14 @@ def test_dual_projection_edge_cases(harness, family, case):
             k_ = 2 if case.startswith("two") and G >= 2 else (3 if case.startswith("three") and G >= 3 else 1)
             idx = rng.choice(G, k_, replace=False)
             s[i, idx] = {"one_zero": 0.0, "one_tiny": 1e-7, "two_zero": 0.0, "two_small": 0.01, "three_zero": 0.0}[case]
+            if case == "two_small" and len(idx) > 1:
+                # two slacks of exactly the same small value are a degenerate input for the reference itself: its
+                # LAPACK null basis then hinges on a breakdown of the bidiagonalisation, i.e. on rounding noise
+                # (SciPy's own result moves by 1e-2 under a 1e-16 relative perturbation of Jc)
+                s[i, idx[1]] = 0.0123
     q, dq, alpha = (a.astype(np.float64) for a in (q, dq, alpha))
-    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis="canonical")
-    pf = helpers.exact_params_flat(family, _params(family))
+    ref = helpers.oracle_batch(family, q, dq, s, alpha, basis=helpers.ORACLE_BASIS[mode])
+    pf = helpers.exact_params_flat(family, helpers.with_basis(_params(family), mode))
     ddq, s_out, dbg, st = helpers.harness_step(harness, family, pf, q, dq, s, alpha, np.float64)
     N = n + G
     ok = ~ref["rank_def"] & (ref["margin"] > 1e-6)

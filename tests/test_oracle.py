@@ -8,6 +8,7 @@ from oracle import atacom_oracle as ao
 from oracle import envs as oenv
 from oracle import nullspace as ns
 from oracle import ref_loader
+from tests import helpers
 
 
 def test_rref_matches_reference_golden(golden):
@@ -235,3 +236,37 @@ def test_oracle_against_live_reference():
         state, _ = oenv.circle_base_step(state, o["ddq"] / spec.acc_max)
         np.testing.assert_allclose(state, ref_state, atol=1e-12)
         np.testing.assert_allclose(s, env.s, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(2, 3), (6, 9), (12, 17), (13, 19), (4, 6), (5, 7), (3, 5), (2, 4), (1, 3), (5, 8)])
+def test_lapack_null_basis_is_scipy_svd_null_basis(shape):
+    """The reference's null basis (SciPy svd -> LAPACK gesdd, null_space_coordinate.py:9-18) is NOT arbitrary: for
+    a full-row-rank matrix it is the trailing columns of the product of the right Householder reflectors of the
+    bidiagonalisation (or, for N >= 11 M / 6, of the LQ factorisation).  The restatement reproduces SciPy's
+    vectors, signs included."""
+    m, n = shape
+    rng = np.random.default_rng(m * 100 + n)
+    for t in range(60):
+        A = rng.normal(size=(m, n))
+        if t % 3 == 0 and m > 1:                      # the block structure of Jc: [[A_f, 0], [A_g, diag(s)]]
+            nq = n - (m - 1)
+            A[0, nq:] = 0.0
+            A[1:, nq:] = np.diag(np.abs(rng.normal(size=m - 1)) * (0.01 if t % 2 else 1.0))
+        _, Q, rank = ns.svd_pinv_null(A)
+        assert rank == m
+        np.testing.assert_allclose(ns.lapack_null_basis(A), Q, atol=1e-11)
+
+
+@pytest.mark.parametrize("family", ["planar", "iiwa6", "iiwa7"])
+def test_lapack_basis_reproduces_the_reference_on_both_strata(family):
+    """tol_rref of the restated LAPACK basis == tol_rref of SciPy's SVD basis (what atacom.py:127-128 computes),
+    on the synthetic benchmark batch including every environment where the tolerance branch fires."""
+    B = 400
+    q, dq, s, alpha = helpers.synthetic_cpu(family, B, seed=77)
+    svd = helpers.oracle_batch(family, q, dq, s, alpha, basis="svd")
+    lap = helpers.oracle_batch(family, q, dq, s, alpha, basis="lapack")
+    ok = ~svd["rank_def"] & (svd["margin"] > 1e-6)
+    assert svd["fired"][ok].sum() > 20
+    assert helpers.rel_err(lap["w_null"], svd["w_null"])[ok].max() < 1e-9
+    assert helpers.rel_err(lap["ddq"], svd["ddq"], svd["w"])[ok].max() < 1e-9
+    assert (lap["fired"] == svd["fired"])[ok].all()
