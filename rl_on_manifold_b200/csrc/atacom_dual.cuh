@@ -106,6 +106,15 @@ struct SharedStore {
   ATACOM_HD R get_dyn(int i) const { return *static_cast<const volatile R*>(base + i * STRIDE); }
 };
 
+// The same column of a [SIZE][STRIDE] shared-memory array with plain accesses: for code that WANTS the compiler to
+// schedule its loads early and keep values in registers (the LAPACK-basis routine: rows and reflector vectors).
+template <typename R, int STRIDE>
+struct PlainSharedStore {
+  R* base;
+  ATACOM_HD R get(int i) const { return base[i * STRIDE]; }
+  ATACOM_HD void set(int i, R x) { base[i * STRIDE] = x; }
+};
+
 template <class S> struct is_shared_store { static constexpr bool value = false; };
 template <typename R, int STRIDE> struct is_shared_store<SharedStore<R, STRIDE>> { static constexpr bool value = true; };
 template <typename R, int STRIDE>

@@ -697,8 +697,6 @@ ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>
   using LP = Lapack<HP, D>;
   constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
   const bool ec = P.variant == VARIANT_EC;
-  ATACOM_ROLLED
-  for (int e = 0; e < LP::SIZE; ++e) S.set(e, HP(0));
   HP r[at_least_1<C>::value], sh[at_least_1<G>::value], sn[at_least_1<G>::value];
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
@@ -706,7 +704,8 @@ ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>
   for (int i = 0; i < C; ++i) {
     ATACOM_UNROLL
     for (int j = 0; j < n; ++j) S.set(LP::a(i, j), Kd.K[i] * R.J[i][j]);                 // constraints.py:39-40
-    if (i >= F) S.set(LP::a(i, n + (i >= F ? i - F : 0)), sh[i >= F ? i - F : 0]);       // atacom.py:151-165
+    ATACOM_UNROLL
+    for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
     HP ri = Kd.K_c[i] * R.c[i] + Kd.wJ[i] * R.Jdq[i] + Kd.wb[i] * cvt<HP>(R.b[i]);       // see DualConsts
     if (i >= F) ri += HP(0.5) * Kd.K_c[i] * sh[i >= F ? i - F : 0] * sh[i >= F ? i - F : 0];
     r[i] = ri;

@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
   asm volatile("griddepcontrol.wait;" ::: "memory");      // the step kernel has completed: list, counts and its outputs are visible
   const int cnt = a.fix_count[blockIdx.x];
   const int32_t* seg = a.fix_list + static_cast<int64_t>(blockIdx.x) * a.seg_stride;
-  SharedStore<double, FTPB> S{reinterpret_cast<double*>(atacom_smem) + threadIdx.x};
+  PlainSharedStore<double, FTPB> S{reinterpret_cast<double*>(atacom_smem) + threadIdx.x};
   const bool ec = P.variant == VARIANT_EC;
   for (int t = threadIdx.x; t < cnt; t += FTPB) {
     const int64_t e = seg[t];

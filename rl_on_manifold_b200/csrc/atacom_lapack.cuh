@@ -71,91 +71,133 @@ struct Lapack {
 
   // S: on entry Jc (C x N, row-major, S.get(i * N + j)); destroyed.  r: C (right-hand side psi + K_c c; destroyed),
   // alpha: k.  w_mn = -Jc^+ r, w_null = Nc alpha (N each).  Returns status bits.
+  //
+  // Memory traffic is what bounds this routine on the device (one thread per environment, the array in shared
+  // memory): the current reflector vector lives in registers, a row / column of the trailing matrix is loaded
+  // once, updated and stored once per reflector (inner loops unrolled over the static bound with predicates, the
+  // outer ones rolled), and the null basis Z is formed entirely in registers.
   template <class ST>
   static ATACOM_HD uint8_t project(ST& S, R* r, const R* alpha, R tol, bool want_null, R* w_mn, R* w_null) {
     uint8_t status = 0;
     R taup[C1];
     R amax = R(0);
-    ATACOM_ROLLED
-    for (int e = 0; e < C * N; ++e) {
-      const R v = num<R>::abs(S.get(e));
-      amax = v > amax ? v : amax;
-    }
-    const R rank_floor = R(64) * num<R>::eps() * amax;
 
     // ---- reflectors (dgebd2 / dgelq2), left reflectors applied to the right-hand side as they are formed
     ATACOM_ROLLED
     for (int i = 0; i < C; ++i) {
-      R xn2 = R(0);
-      ATACOM_ROLLED
-      for (int j = i + 1; j < N; ++j) {
-        const R x = S.get(a(i, j));
-        xn2 += x * x;
+      R v[N];                                      // row i from the diagonal on, then the reflector vector
+      R xn2 = R(0), x0 = R(0);
+      ATACOM_UNROLL
+      for (int j = 0; j < N; ++j) {
+        v[j] = R(0);
+        if (j >= i) {
+          const R x = S.get(a(i, j));
+          const R ax = num<R>::abs(x);
+          amax = ax > amax ? ax : amax;
+          if (j == i) x0 = x;
+          else {
+            v[j] = x;
+            xn2 += x * x;
+          }
+        }
       }
       R beta, tau, sc;
-      larfg(S.get(a(i, i)), xn2, &beta, &tau, &sc);
+      larfg(x0, xn2, &beta, &tau, &sc);
       S.set(a(i, i), beta);
       taup[i] = tau;
       if (tau != R(0)) {
+        ATACOM_UNROLL
+        for (int j = 0; j < N; ++j) {
+          v[j] *= sc;
+          if (j > i) S.set(a(i, j), v[j]);
+        }
         ATACOM_ROLLED
-        for (int j = i + 1; j < N; ++j) S.set(a(i, j), S.get(a(i, j)) * sc);
-        ATACOM_ROLLED
-        for (int l = i + 1; l < C; ++l) {          // rows below: A <- A G_i
-          R w = S.get(a(l, i));
-          ATACOM_ROLLED
-          for (int j = i + 1; j < N; ++j) w += S.get(a(l, j)) * S.get(a(i, j));
-          w *= tau;
-          S.set(a(l, i), S.get(a(l, i)) - w);
-          ATACOM_ROLLED
-          for (int j = i + 1; j < N; ++j) S.set(a(l, j), S.get(a(l, j)) - w * S.get(a(i, j)));
+        for (int l = i + 1; l < C; ++l) {          // rows below: A <- A G_i, one load and one store per entry
+          R row[N];
+          R w0 = R(0), w1 = R(0), w2 = R(0), w3 = R(0);
+          ATACOM_UNROLL
+          for (int j = 0; j < N; ++j) {
+            row[j] = R(0);
+            if (j >= i) {
+              row[j] = S.get(a(l, j));
+              const R pr = (j == i) ? row[j] : row[j] * v[j];
+              if ((j & 3) == 0) w0 += pr;
+              else if ((j & 3) == 1) w1 += pr;
+              else if ((j & 3) == 2) w2 += pr;
+              else w3 += pr;
+            }
+          }
+          const R w = ((w0 + w1) + (w2 + w3)) * tau;
+          ATACOM_UNROLL
+          for (int j = 0; j < N; ++j) {
+            if (j == i) S.set(a(l, j), row[j] - w);
+            else if (j > i) S.set(a(l, j), row[j] - w * v[j]);
+          }
         }
       }
       if (!LQ_PATH && i + 1 < C) {
-        R un2 = R(0);
-        ATACOM_ROLLED
-        for (int l = i + 2; l < C; ++l) {
-          const R x = S.get(a(l, i));
-          un2 += x * x;
+        R u[C1];                                   // column i below the diagonal, then the reflector vector
+        R un2 = R(0), c0 = R(0);
+        ATACOM_UNROLL
+        for (int l = 0; l < C; ++l) {
+          u[l] = R(0);
+          if (l >= i + 1) {
+            const R x = S.get(a(l, i));
+            if (l == i + 1) c0 = x;
+            else {
+              u[l] = x;
+              un2 += x * x;
+            }
+          }
         }
         R betaq, tauq, scq;
-        larfg(S.get(a(i + 1, i)), un2, &betaq, &tauq, &scq);
-        S.set(a(i + 1, i), betaq);
+        larfg(c0, un2, &betaq, &tauq, &scq);
+        S.set(a(i + 1, i), betaq);                 // (u itself is not needed again: it is applied to r right here)
         if (tauq != R(0)) {
-          ATACOM_ROLLED
-          for (int l = i + 2; l < C; ++l) S.set(a(l, i), S.get(a(l, i)) * scq);
+          ATACOM_UNROLL
+          for (int l = 0; l < C; ++l) u[l] = (l == i + 1) ? R(1) : u[l] * scq;
           ATACOM_ROLLED
           for (int j = i + 1; j < N; ++j) {        // columns to the right: A <- H_i A
-            R w = S.get(a(i + 1, j));
-            ATACOM_ROLLED
-            for (int l = i + 2; l < C; ++l) w += S.get(a(l, i)) * S.get(a(l, j));
-            w *= tauq;
-            S.set(a(i + 1, j), S.get(a(i + 1, j)) - w);
-            ATACOM_ROLLED
-            for (int l = i + 2; l < C; ++l) S.set(a(l, j), S.get(a(l, j)) - w * S.get(a(l, i)));
+            R col[C1];
+            R w0 = R(0), w1 = R(0);
+            ATACOM_UNROLL
+            for (int l = 0; l < C; ++l) {
+              col[l] = R(0);
+              if (l >= i + 1) {
+                col[l] = S.get(a(l, j));
+                if (l & 1) w1 += col[l] * u[l];
+                else w0 += col[l] * u[l];
+              }
+            }
+            const R w = (w0 + w1) * tauq;
+            ATACOM_UNROLL
+            for (int l = 0; l < C; ++l) {
+              if (l >= i + 1) S.set(a(l, j), col[l] - w * u[l]);
+            }
           }
-          R w = r[i + 1];                          // and the right-hand side: r <- H_i r
-          ATACOM_ROLLED
-          for (int l = i + 2; l < C; ++l) w += S.get(a(l, i)) * r[l];
+          R w = R(0);                              // and the right-hand side: r <- H_i r   (u is zero above row i + 1)
+          ATACOM_UNROLL
+          for (int l = 0; l < C; ++l) w += u[l] * r[l];
           w *= tauq;
-          r[i + 1] -= w;
-          ATACOM_ROLLED
-          for (int l = i + 2; l < C; ++l) r[l] -= w * S.get(a(l, i));
+          ATACOM_UNROLL
+          for (int l = 0; l < C; ++l) r[l] -= w * u[l];
         }
       }
     }
+    const R rank_floor = R(64) * num<R>::eps() * amax;     // (amax: the largest entry met while walking the rows)
 
     // ---- minimum-norm part: Jc = U B P^T (B lower bidiagonal) or L Q;  x = P [y; 0],  B y = -U^T r  /  L y = -r
     R t[N];
-    ATACOM_ROLLED
+    ATACOM_UNROLL
     for (int i = 0; i < N; ++i) t[i] = R(0);
-    ATACOM_ROLLED
+    ATACOM_UNROLL
     for (int i = 0; i < C; ++i) {
       R acc = -r[i];
       if (LQ_PATH) {
-        ATACOM_ROLLED
+        ATACOM_UNROLL
         for (int j = 0; j < i; ++j) acc -= S.get(a(i, j)) * t[j];
       } else if (i > 0) {
-        acc -= S.get(a(i, i - 1)) * t[i - 1];
+        acc -= S.get(a(i, i > 0 ? i - 1 : 0)) * t[i > 0 ? i - 1 : 0];
       }
       const R d = S.get(a(i, i));
       if (num<R>::abs(d) > rank_floor) {
@@ -165,16 +207,17 @@ struct Lapack {
         t[i] = R(0);
       }
     }
-    ATACOM_ROLLED
+    R tau_s[C1];                                   // (static copies: the loops below are unrolled)
+    ATACOM_UNROLL
+    for (int i = 0; i < C; ++i) tau_s[i] = taup[i];
+    ATACOM_UNROLL
     for (int i = C - 1; i >= 0; --i) {
-      const R tau = taup[i];
-      if (tau == R(0)) continue;
       R w = t[i];
-      ATACOM_ROLLED
+      ATACOM_UNROLL
       for (int j = i + 1; j < N; ++j) w += S.get(a(i, j)) * t[j];
-      w *= tau;
+      w *= tau_s[i];
       t[i] -= w;
-      ATACOM_ROLLED
+      ATACOM_UNROLL
       for (int j = i + 1; j < N; ++j) t[j] -= w * S.get(a(i, j));
     }
     ATACOM_UNROLL
@@ -184,69 +227,99 @@ struct Lapack {
     }
     if (!want_null || k == 0) return status;
 
-    // ---- Z = G_0 ... G_{C-1} [0; I]: the null basis as gesdd returns it (columns of Z = rows C.. of VT)
-    ATACOM_ROLLED
-    for (int j = C; j < N; ++j) {
-      ATACOM_ROLLED
-      for (int c = 0; c < k; ++c) S.set(zcell(j, c), (j - C == c) ? R(1) : R(0));
-    }
-    ATACOM_ROLLED
-    for (int i = C - 1; i >= 0; --i) {
-      const R tau = taup[i];
-      R zi[K1];                                    // row i of Z: zero before reflector i, created by it
+    // ---- Z = G_0 ... G_{C-1} [0; I]: the null basis as gesdd returns it (columns of Z = rows C.. of VT), formed in
+    // registers (every index static); it goes to its cells of the array only when the last reflector has been read
+    {
+      R Z[N][K1];
       ATACOM_UNROLL
-      for (int c = 0; c < k; ++c) {
-        R w = R(0);
-        ATACOM_ROLLED
-        for (int j = i + 1; j < N; ++j) w += S.get(a(i, j)) * S.get(zcell(j, c));
-        zi[c] = w * tau;
-      }
-      ATACOM_ROLLED
-      for (int j = i + 1; j < N; ++j) {
-        const R v = S.get(a(i, j));
+      for (int j = 0; j < N; ++j) {
         ATACOM_UNROLL
-        for (int c = 0; c < k; ++c) S.set(zcell(j, c), S.get(zcell(j, c)) - zi[c] * v);
+        for (int c = 0; c < k; ++c) Z[j][c] = (j - C == c) ? R(1) : R(0);
       }
       ATACOM_UNROLL
-      for (int c = 0; c < k; ++c) S.set(zcell(i, c), -zi[c]);   // (v_i is dead from here on: its cells may be reused)
+      for (int i = C - 1; i >= 0; --i) {
+        R vi[N];
+        ATACOM_UNROLL
+        for (int j = i + 1; j < N; ++j) vi[j] = S.get(a(i, j));
+        ATACOM_UNROLL
+        for (int c = 0; c < k; ++c) {
+          R w = R(0);                              // (row i of Z is zero before reflector i)
+          ATACOM_UNROLL
+          for (int j = (i + 1 > C ? i + 1 : C); j < N; ++j) w += vi[j] * Z[j][c];      // rows < C above i are zero too
+          ATACOM_UNROLL
+          for (int j = i + 1; j < C; ++j) w += vi[j] * Z[j][c];
+          w *= tau_s[i];
+          Z[i][c] = -w;
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) Z[j][c] -= w * vi[j];
+        }
+      }
+      ATACOM_UNROLL
+      for (int j = 0; j < N; ++j) {
+        ATACOM_UNROLL
+        for (int c = 0; c < k; ++c) S.set(zcell(j, c), Z[j][c]);
+      }
     }
 
     // ---- the reference's rref on V = Z^T (k x N), null_space_coordinate.py:40-79 as written: walk the columns; the
     // pivot candidate is the first largest |.| among the rows not used yet; <= tol: zero those entries and move on;
     // else swap (columns j.. only), scale the pivot row, eliminate the column from every other row.
     int rr = 0;
+    ATACOM_ROLLED
     for (int j = 0; j < N && rr < k; ++j) {
+      R colj[K1];
       int kk = rr;
       R p = R(-1);
-      ATACOM_ROLLED
-      for (int i = rr; i < k; ++i) {
-        const R v = num<R>::abs(S.get(zcell(j, i)));
-        if (v > p) {
-          p = v;
+      ATACOM_UNROLL
+      for (int i = 0; i < k; ++i) {
+        colj[i] = S.get(zcell(j, i));
+        const R av = num<R>::abs(colj[i]);
+        if (i >= rr && av > p) {
+          p = av;
           kk = i;
         }
       }
       if (!(p > tol)) {
         status |= ST_COLUMN_DROPPED;
-        ATACOM_ROLLED
-        for (int i = rr; i < k; ++i) S.set(zcell(j, i), R(0));
+        ATACOM_UNROLL
+        for (int i = 0; i < k; ++i) {
+          if (i >= rr) S.set(zcell(j, i), R(0));
+        }
         continue;
       }
       if (j >= n) status |= ST_SLACK_PIVOT;
-      const R inv = R(1) / S.get(zcell(j, kk));
-      ATACOM_ROLLED
-      for (int jj = j; jj < N; ++jj) {
-        const R lead = S.get(zcell(jj, kk)) * inv;             // pivot row, scaled
-        if (kk != rr) S.set(zcell(jj, kk), S.get(zcell(jj, rr)));   // swap rows rr <-> kk on columns j..
-        S.set(zcell(jj, rr), lead);
-      }
-      ATACOM_ROLLED
+      R piv = R(0), other = R(0);                  // entries of column j in rows kk (the pivot) and rr
+      ATACOM_UNROLL
       for (int i = 0; i < k; ++i) {
-        if (i == rr) continue;
-        const R f = S.get(zcell(j, i));
-        if (f == R(0)) continue;
-        ATACOM_ROLLED
-        for (int jj = j; jj < N; ++jj) S.set(zcell(jj, i), S.get(zcell(jj, i)) - f * S.get(zcell(jj, rr)));
+        piv = (i == kk) ? colj[i] : piv;
+        other = (i == rr) ? colj[i] : other;
+      }
+      const R inv = R(1) / piv;
+      // multipliers of the elimination: row i loses f_i times the scaled pivot row; after the swap row kk holds what
+      // was row rr
+      R f[K1];
+      ATACOM_UNROLL
+      for (int i = 0; i < k; ++i) f[i] = (i == rr) ? R(0) : ((i == kk) ? other : colj[i]);
+      ATACOM_UNROLL
+      for (int jj = 0; jj < N; ++jj) {
+        if (jj >= j) {
+          R e[K1];
+          ATACOM_UNROLL
+          for (int i = 0; i < k; ++i) e[i] = S.get(zcell(jj, i));
+          R ek = R(0), er = R(0);
+          ATACOM_UNROLL
+          for (int i = 0; i < k; ++i) {
+            ek = (i == kk) ? e[i] : ek;
+            er = (i == rr) ? e[i] : er;
+          }
+          const R lead = ek * inv;
+          ATACOM_UNROLL
+          for (int i = 0; i < k; ++i) {
+            const R cur = (i == kk) ? er : e[i];                 // swap rr <-> kk (a no-op when kk == rr)
+            const R out = (i == rr) ? lead : cur - f[i] * lead;
+            S.set(zcell(jj, i), out);
+          }
+        }
       }
       ++rr;
     }

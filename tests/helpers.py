@@ -159,11 +159,11 @@ def oracle_batch(family, q, dq, s, alpha, basis="svd", variant="atacom", bias="o
 
 
 def oracle_point_reach_batch(q, dq, p, dp, s, action):
-    """Env C oracle over a batch (collision_avoidance_atacom.py:29-47).  `pmin`: the smallest pivot candidate of the
-    rref (the reference's tolerance there is ~1e-15; the kernels decide with 2.4e-6, so candidates in between are
-    outside the parity domain)."""
+    """Env C oracle over a batch (collision_avoidance_atacom.py:29-47).  `ambiguous`: some pivot candidate of the rref
+    lies between the reference's tolerance (~1e-15) and the kernels' (2.4e-6 in fp32 terms): decided differently,
+    outside the parity domain."""
     B, G = s.shape
-    out = dict(w=np.zeros((B, 2 + G)), s_new=np.zeros((B, G)), rank_def=np.zeros(B, bool), pmin=np.full(B, np.inf))
+    out = dict(w=np.zeros((B, 2 + G)), s_new=np.zeros((B, G)), rank_def=np.zeros(B, bool), ambiguous=np.zeros(B, bool))
     q, dq, p, dp, s, action = (np.asarray(a, dtype=np.float64) for a in (q, dq, p, dp, s, action))
     for i in range(B):
         try:
@@ -174,7 +174,7 @@ def oracle_point_reach_batch(q, dq, p, dp, s, action):
         out["w"][i], out["s_new"][i] = o["w"], o["s_new"]
         out["rank_def"][i] = o["rank"] < G
         cand = [pv for (_, _, pv) in o["trace"]["pivots"] + o["trace"]["dropped"]]
-        out["pmin"][i] = min(cand) if cand else np.inf
+        out["ambiguous"][i] = any(1e-12 < pv < 1e-4 for pv in cand)
     return out
 
 

@@ -270,3 +270,50 @@ def test_lapack_basis_reproduces_the_reference_on_both_strata(family):
     assert helpers.rel_err(lap["w_null"], svd["w_null"])[ok].max() < 1e-9
     assert helpers.rel_err(lap["ddq"], svd["ddq"], svd["w"])[ok].max() < 1e-9
     assert (lap["fired"] == svd["fired"])[ok].all()
+
+
+def test_canonical_mode_stratum_two_acceptance():
+    """SURVEY.md §7.3-1 for the opt-in CANONICAL basis mode (the default mode needs no such test: it reproduces the
+    reference's own LAPACK basis).  Where the reference's rref fires its tolerance branch, the canonical member of the
+    output family is compared with the reference's (SciPy SVD basis): same pivot columns in the large majority,
+    constraint residual |Jc Nc| comparable, and the distance to the reference within the reference's own spread
+    under 16 random rotations of its null basis.  Stratum sizes are printed."""
+    family, B = "iiwa6", 500
+    q, dq, s, alpha = helpers.synthetic_cpu(family, B, 4242)
+    spec = helpers.oracle_spec(family)
+    rng = np.random.default_rng(0)
+    rows = []
+    n_ok = 0
+    for i in range(B):
+        ev = helpers.oracle_eval(family, q[i].astype(float), dq[i].astype(float))
+        A_f, A_g, _, _, _ = ao.viability_terms(spec, ev, dq[i].astype(float))
+        Jc = ao.stack_Jc(spec, A_f, A_g, s[i].astype(float))
+        pinv, Q, rank = ns.svd_pinv_null(Jc)
+        if rank < spec.C:
+            continue
+        n_ok += 1
+        tr_s, tr_c = {}, {}
+        Nc_s = ao.null_coordinates(Jc, spec.k, spec.tol, "svd", (pinv, Q), tr_s)
+        Nc_c = ao.null_coordinates(Jc, spec.k, spec.tol, "canonical", (pinv, Q), tr_c)
+        fired = [any(p > 1e-9 for (_, _, p) in t["dropped"]) for t in (tr_s, tr_c)]
+        if not any(fired):
+            np.testing.assert_allclose(Nc_c, Nc_s, atol=1e-9 * max(1.0, np.abs(Nc_s).max()))     # stratum I: basis-free
+            continue
+        a = alpha[i].astype(float)
+        spread = 0.0
+        for _ in range(16):
+            M = np.linalg.qr(rng.normal(size=(spec.k, spec.k)))[0]
+            spread = max(spread, np.abs(ns.tol_rref((Q[:, :spec.k] @ M).T, tol=spec.tol).T @ a - Nc_s @ a).max())
+        rows.append(dict(same=[c for (_, c, _) in tr_s["pivots"]] == [c for (_, c, _) in tr_c["pivots"]],
+                         res_s=np.abs(Jc @ Nc_s).max(), res_c=np.abs(Jc @ Nc_c).max(),
+                         d=np.abs(Nc_c @ a - Nc_s @ a).max(), spread=spread))
+    same = np.array([r["same"] for r in rows])
+    d, spread = np.array([r["d"] for r in rows]), np.array([r["spread"] for r in rows])
+    res_c, res_s = np.array([r["res_c"] for r in rows]), np.array([r["res_s"] for r in rows])
+    print("\n[%s] %d environments, stratum II %d (%.1f %%): same pivot columns %.1f %%, |ours - ref| <= spread %.1f %%, "
+          "median |Jc Nc| ours %.3g ref %.3g" % (family, n_ok, len(rows), 100.0 * len(rows) / n_ok, 100 * same.mean(),
+                                                 100 * (d <= spread + 1e-9).mean(), np.median(res_c), np.median(res_s)))
+    assert 0.1 < len(rows) / n_ok < 0.35
+    assert same.mean() > 0.85
+    assert (d <= spread + 1e-9).mean() > 0.93
+    assert np.median(res_c) < 1.25 * np.median(res_s)
