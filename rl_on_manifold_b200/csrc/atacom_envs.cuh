@@ -690,10 +690,12 @@ ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
 // The whole step on the LAPACK-basis routine (atacom_lapack.cuh): what the step kernels run for the environments
 // the dual path flagged (Dual::project, band_defer), and the generic kernel for every environment.  S: a store of
 // Lapack<HP, D>::SIZE entries (a column of a shared-memory array on the device).
-template <class D, typename T, typename HP, class ST>
+// LPE lanes of a warp may share one environment (`Grp`, see Lapack::project): every lane evaluates the constraints,
+// the rows of Jc are written round robin, the outputs are valid in lane 0 of the group.
+template <class D, typename T, typename HP, int LPE = 1, class ST, class GRP = SoloGroup>
 ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST& S,
                                        const RawConstraints<T, HP, D, HP>& R, const T* dq, const T* s, const T* alpha,
-                                       T* ddq, T* s_out, T* w_dbg) {
+                                       T* ddq, T* s_out, T* w_dbg, const GRP& Grp = GRP()) {
   using LP = Lapack<HP, D>;
   constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
   const bool ec = P.variant == VARIANT_EC;
@@ -702,10 +704,12 @@ ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   ATACOM_UNROLL
   for (int i = 0; i < C; ++i) {
-    ATACOM_UNROLL
-    for (int j = 0; j < n; ++j) S.set(LP::a(i, j), Kd.K[i] * R.J[i][j]);                 // constraints.py:39-40
-    ATACOM_UNROLL
-    for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
+    if (LPE == 1 || (i % LPE) == Grp.sub()) {
+      ATACOM_UNROLL
+      for (int j = 0; j < n; ++j) S.set(LP::a(i, j), Kd.K[i] * R.J[i][j]);               // constraints.py:39-40
+      ATACOM_UNROLL
+      for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
+    }
     HP ri = Kd.K_c[i] * R.c[i] + Kd.wJ[i] * R.Jdq[i] + Kd.wb[i] * cvt<HP>(R.b[i]);       // see DualConsts
     if (i >= F) ri += HP(0.5) * Kd.K_c[i] * sh[i >= F ? i - F : 0] * sh[i >= F ? i - F : 0];
     r[i] = ri;
@@ -713,20 +717,20 @@ ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>
   HP ah[at_least_1<k>::value], w_mn[N], w_null[N];
   ATACOM_UNROLL
   for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
-  uint8_t st = LP::project(S, r, ah, Kd.tol, !ec, w_mn, w_null) | ST_LAPACK_PATH;
+  uint8_t st = LP::template project<LPE>(S, r, ah, Kd.tol, !ec, w_mn, w_null, Grp) | ST_LAPACK_PATH;
   st = finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, sn, w_dbg, st);
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
   return st;
 }
 
-template <class Env, typename T, typename HP, class ST>
+template <class Env, typename T, typename HP, int LPE = 1, class ST, class GRP = SoloGroup>
 ATACOM_HD uint8_t step_lapack(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST& S, const T* q, const T* dq, const T* s,
-                              const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+                              const T* alpha, T* ddq, T* s_out, T* w_dbg, const GRP& Grp = GRP()) {
   using D = typename Env::D;
   RawConstraints<T, HP, D, HP> R;
   Env::template eval<T, HP>(P, q, dq, R);
-  return step_lapack_from_raw<D, T, HP>(P, Kd, S, R, dq, s, alpha, ddq, s_out, w_dbg);
+  return step_lapack_from_raw<D, T, HP, LPE>(P, Kd, S, R, dq, s, alpha, ddq, s_out, w_dbg, Grp);
 }
 
 // atacom.py:145-149

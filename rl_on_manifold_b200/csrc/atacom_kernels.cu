@@ -656,14 +656,29 @@ struct FixArgs {
   int32_t n_peers;
 };
 
+constexpr int FIX_LPE = 4;      // lanes of a warp per deferred environment
+
+// The lanes of a warp that share one environment in the fix-up kernel (Lapack::project, GRP).
+struct WarpLanes {
+  int s;
+  unsigned mask;      // the lanes of the warp that take part in this round
+  __device__ __forceinline__ int sub() const { return s; }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
 template <class Env>
 struct FixCfg {
   using LP = Lapack<double, typename Env::D>;
   static constexpr size_t SMEM_MAX = 227 * 1024;
-  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE));
-  static constexpr int TPB = FIT >= 128 ? 128 : (FIT / 32) * 32;       // iiwa-6: 128 (204 KB), iiwa-7: 96
-  static_assert(TPB >= 32, "the LAPACK working array of one warp does not fit into shared memory");
-  static constexpr size_t BYTES = sizeof(double) * LP::SIZE * TPB;
+  // environments per block: a multiple of 8 (a warp holds 8 groups of 4 lanes); the [cell][environment] array is
+  // padded to a stride = 4 mod 16, so that the 16 threads of a half-warp — 4 environments x 4 lanes, the lanes on
+  // cells 17 (rows) or 1 (columns) apart — hit 16 different pairs of banks
+  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE)) - 4;
+  static constexpr int ENVS = FIT >= 128 ? 128 : (FIT / 16) * 16;      // iiwa-6: 128, iiwa-7: 112
+  static constexpr int STRIDE = ENVS + 4;
+  static constexpr int TPB = ENVS * FIX_LPE;
+  static_assert(ENVS >= 16, "the LAPACK working arrays do not fit into shared memory");
+  static constexpr size_t BYTES = sizeof(double) * LP::SIZE * STRIDE;
 };
 
 template <class Env>
@@ -671,18 +686,22 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
                                                                       const __grid_constant__ ParamsT<float> P,
                                                                       const __grid_constant__ DualConsts<double> Kd) {
   using D = typename Env::D;
+  using CFG = FixCfg<Env>;
   constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
   constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
-  constexpr int FTPB = FixCfg<Env>::TPB;
   extern __shared__ __align__(128) unsigned char atacom_smem[];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");      // the step kernel has completed: list, counts and its outputs are visible
   const int cnt = a.fix_count[blockIdx.x];
   const int32_t* seg = a.fix_list + static_cast<int64_t>(blockIdx.x) * a.seg_stride;
-  PlainSharedStore<double, FTPB> S{reinterpret_cast<double*>(atacom_smem) + threadIdx.x};
+  const int slot = threadIdx.x / FIX_LPE, sub = threadIdx.x % FIX_LPE;
+  PlainSharedStore<double, CFG::STRIDE> S{reinterpret_cast<double*>(atacom_smem) + slot};
   const bool ec = P.variant == VARIANT_EC;
-  for (int t = threadIdx.x; t < cnt; t += FTPB) {
-    const int64_t e = seg[t];
+  for (int t0 = 0; t0 < cnt; t0 += CFG::ENVS) {
+    const bool active = t0 + slot < cnt;
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!active) continue;
+    const int64_t e = seg[t0 + slot];
     float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
     row_load<n>(a.q, e, q);
     row_load<n>(a.dq, e, dq);
@@ -695,12 +714,16 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
 #pragma unroll
       for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
     }
-    float* dbg = a.w_dbg ? a.w_dbg + e * (2 * N) : nullptr;
-    const uint8_t st = step_lapack<Env, float, double>(P, Kd, S, q, dq, s, al, ddq, so, dbg);
-    if (a.status) a.status[e] = st;
-    if (a.ddq) row_store<n>(a.ddq, e, ddq);
-    if (G > 0) row_store<G1>(a.s_out, e, so);
-    for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
+    float* dbg = (a.w_dbg && sub == 0) ? a.w_dbg + e * (2 * N) : nullptr;
+    const WarpLanes grp{sub, mask};
+    const uint8_t st = step_lapack<Env, float, double, FIX_LPE>(P, Kd, S, q, dq, s, al, ddq, so, dbg, grp);
+    if (sub == 0) {
+      if (a.status) a.status[e] = st;
+      if (a.ddq) row_store<n>(a.ddq, e, ddq);
+      if (G > 0) row_store<G1>(a.s_out, e, so);
+      for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
+    }
+    __syncwarp(mask);      // the next round reuses the group's array
   }
 }
 

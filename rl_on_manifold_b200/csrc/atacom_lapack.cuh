@@ -37,6 +37,13 @@ struct ArrayStore {
   ATACOM_HD void set(int i, R x) { v[i] = x; }
 };
 
+// The lanes working on one environment: the host build and the generic kernels use one (SoloGroup); the fix-up kernel
+// of the step families uses LPE lanes of a warp (WarpLanes, atacom_kernels.cu).
+struct SoloGroup {
+  ATACOM_HD int sub() const { return 0; }
+  ATACOM_HD void sync() const {}
+};
+
 template <typename R, class D>
 struct Lapack {
   static constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
@@ -70,120 +77,112 @@ struct Lapack {
   }
 
   // S: on entry Jc (C x N, row-major, S.get(i * N + j)); destroyed.  r: C (right-hand side psi + K_c c; destroyed),
-  // alpha: k.  w_mn = -Jc^+ r, w_null = Nc alpha (N each).  Returns status bits.
+  // alpha: k.  w_mn = -Jc^+ r, w_null = Nc alpha (N each; valid in lane 0 of the group).  Returns status bits.
   //
-  // Memory traffic is what bounds this routine on the device (one thread per environment, the array in shared
-  // memory): the current reflector vector lives in registers, a row / column of the trailing matrix is loaded
-  // once, updated and stored once per reflector (inner loops unrolled over the static bound with predicates, the
-  // outer ones rolled), and the null basis Z is formed entirely in registers.
-  template <class ST>
-  static ATACOM_HD uint8_t project(ST& S, R* r, const R* alpha, R tol, bool want_null, R* w_mn, R* w_null) {
+  // LPE lanes of one warp work on one environment (LPE = 1: one thread, the host build).  The rows the right
+  // reflector G_i updates are independent of each other, and so are the columns the left reflector H_i updates: the
+  // lanes of a group take them round robin (lane `sub` of LPE), every lane forms the reflector itself from the row /
+  // column it needs, and a __syncwarp separates the phases (`G.sync()`, over the lanes of the warp that take part).
+  // The null basis Z is formed column-wise in registers, one or two columns per lane, and the elimination steps of the
+  // rref are shared column-wise as well.  What bounds the routine on the device is shared-memory traffic — every
+  // trailing entry is loaded and stored once per reflector — and with LPE = 4 there are enough warps to keep it busy.
+  template <int LPE = 1, class ST, class GRP = SoloGroup>
+  static ATACOM_HD uint8_t project(ST& S, R* r, const R* alpha, R tol, bool want_null, R* w_mn, R* w_null,
+                                   const GRP& Grp = GRP()) {
+    const int sub = Grp.sub();
     uint8_t status = 0;
-    R taup[C1];
+    R tau_s[C1];
     R amax = R(0);
 
-    // ---- reflectors (dgebd2 / dgelq2), left reflectors applied to the right-hand side as they are formed
-    ATACOM_ROLLED
+    // ---- reflectors (dgebd2 / dgelq2), left reflectors applied to the right-hand side as they are formed.
+    // The loop over i is unrolled: every range below is static, nothing is predicated.
+    ATACOM_UNROLL
     for (int i = 0; i < C; ++i) {
-      R v[N];                                      // row i from the diagonal on, then the reflector vector
-      R xn2 = R(0), x0 = R(0);
+      Grp.sync();                                  // row i is final: the previous reflectors have been applied to it
+      R v[N];                                      // row i right of the diagonal, then the reflector vector
+      R xn2 = R(0);
+      const R x0 = S.get(a(i, i));
+      amax = num<R>::abs(x0) > amax ? num<R>::abs(x0) : amax;
       ATACOM_UNROLL
-      for (int j = 0; j < N; ++j) {
-        v[j] = R(0);
-        if (j >= i) {
-          const R x = S.get(a(i, j));
-          const R ax = num<R>::abs(x);
-          amax = ax > amax ? ax : amax;
-          if (j == i) x0 = x;
-          else {
-            v[j] = x;
-            xn2 += x * x;
-          }
-        }
+      for (int j = i + 1; j < N; ++j) {
+        v[j] = S.get(a(i, j));
+        const R ax = num<R>::abs(v[j]);
+        amax = ax > amax ? ax : amax;
+        xn2 += v[j] * v[j];
       }
       R beta, tau, sc;
       larfg(x0, xn2, &beta, &tau, &sc);
-      S.set(a(i, i), beta);
-      taup[i] = tau;
-      if (tau != R(0)) {
-        ATACOM_UNROLL
-        for (int j = 0; j < N; ++j) {
-          v[j] *= sc;
-          if (j > i) S.set(a(i, j), v[j]);
+      tau_s[i] = tau;
+      ATACOM_UNROLL
+      for (int j = i + 1; j < N; ++j) v[j] *= sc;
+      if (sub == 0) {
+        S.set(a(i, i), beta);
+        if (tau != R(0)) {
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) S.set(a(i, j), v[j]);
         }
+      }
+      if (tau != R(0)) {
         ATACOM_ROLLED
-        for (int l = i + 1; l < C; ++l) {          // rows below: A <- A G_i, one load and one store per entry
+        for (int l = i + 1 + sub; l < C; l += LPE) {      // rows below: A <- A G_i, one load and one store per entry
           R row[N];
-          R w0 = R(0), w1 = R(0), w2 = R(0), w3 = R(0);
           ATACOM_UNROLL
-          for (int j = 0; j < N; ++j) {
-            row[j] = R(0);
-            if (j >= i) {
-              row[j] = S.get(a(l, j));
-              const R pr = (j == i) ? row[j] : row[j] * v[j];
-              if ((j & 3) == 0) w0 += pr;
-              else if ((j & 3) == 1) w1 += pr;
-              else if ((j & 3) == 2) w2 += pr;
-              else w3 += pr;
-            }
-          }
-          const R w = ((w0 + w1) + (w2 + w3)) * tau;
+          for (int j = i; j < N; ++j) row[j] = S.get(a(l, j));
+          R w0 = row[i], w1 = R(0);
           ATACOM_UNROLL
-          for (int j = 0; j < N; ++j) {
-            if (j == i) S.set(a(l, j), row[j] - w);
-            else if (j > i) S.set(a(l, j), row[j] - w * v[j]);
+          for (int j = i + 1; j < N; ++j) {
+            if ((j - i) & 1) w1 += row[j] * v[j];
+            else w0 += row[j] * v[j];
           }
+          const R w = (w0 + w1) * tau;
+          S.set(a(l, i), row[i] - w);
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) S.set(a(l, j), row[j] - w * v[j]);
         }
       }
       if (!LQ_PATH && i + 1 < C) {
-        R u[C1];                                   // column i below the diagonal, then the reflector vector
-        R un2 = R(0), c0 = R(0);
+        Grp.sync();                                // column i is final
+        R u[C1];                                   // column i below the subdiagonal, then the reflector vector
+        R un2 = R(0);
+        const R c0 = S.get(a(i + 1 < C ? i + 1 : 0, i));
         ATACOM_UNROLL
-        for (int l = 0; l < C; ++l) {
-          u[l] = R(0);
-          if (l >= i + 1) {
-            const R x = S.get(a(l, i));
-            if (l == i + 1) c0 = x;
-            else {
-              u[l] = x;
-              un2 += x * x;
-            }
-          }
+        for (int l = i + 2; l < C; ++l) {
+          u[l] = S.get(a(l, i));
+          un2 += u[l] * u[l];
         }
         R betaq, tauq, scq;
         larfg(c0, un2, &betaq, &tauq, &scq);
-        S.set(a(i + 1, i), betaq);                 // (u itself is not needed again: it is applied to r right here)
+        if (sub == 0) S.set(a(i + 1 < C ? i + 1 : 0, i), betaq);     // (u itself is not needed again: it is applied to r here)
         if (tauq != R(0)) {
           ATACOM_UNROLL
-          for (int l = 0; l < C; ++l) u[l] = (l == i + 1) ? R(1) : u[l] * scq;
+          for (int l = i + 2; l < C; ++l) u[l] *= scq;
           ATACOM_ROLLED
-          for (int j = i + 1; j < N; ++j) {        // columns to the right: A <- H_i A
+          for (int j = i + 1 + sub; j < N; j += LPE) {    // columns to the right: A <- H_i A
             R col[C1];
-            R w0 = R(0), w1 = R(0);
             ATACOM_UNROLL
-            for (int l = 0; l < C; ++l) {
-              col[l] = R(0);
-              if (l >= i + 1) {
-                col[l] = S.get(a(l, j));
-                if (l & 1) w1 += col[l] * u[l];
-                else w0 += col[l] * u[l];
-              }
+            for (int l = i + 1; l < C; ++l) col[l] = S.get(a(l, j));
+            R w0 = col[i + 1 < C ? i + 1 : 0], w1 = R(0);
+            ATACOM_UNROLL
+            for (int l = i + 2; l < C; ++l) {
+              if ((l - i) & 1) w1 += col[l] * u[l];
+              else w0 += col[l] * u[l];
             }
             const R w = (w0 + w1) * tauq;
+            S.set(a(i + 1 < C ? i + 1 : 0, j), col[i + 1 < C ? i + 1 : 0] - w);
             ATACOM_UNROLL
-            for (int l = 0; l < C; ++l) {
-              if (l >= i + 1) S.set(a(l, j), col[l] - w * u[l]);
-            }
+            for (int l = i + 2; l < C; ++l) S.set(a(l, j), col[l] - w * u[l]);
           }
-          R w = R(0);                              // and the right-hand side: r <- H_i r   (u is zero above row i + 1)
+          R w = r[i + 1 < C ? i + 1 : 0];          // and the right-hand side (every lane keeps its own copy)
           ATACOM_UNROLL
-          for (int l = 0; l < C; ++l) w += u[l] * r[l];
+          for (int l = i + 2; l < C; ++l) w += u[l] * r[l];
           w *= tauq;
+          r[i + 1 < C ? i + 1 : 0] -= w;
           ATACOM_UNROLL
-          for (int l = 0; l < C; ++l) r[l] -= w * u[l];
+          for (int l = i + 2; l < C; ++l) r[l] -= w * u[l];
         }
       }
     }
+    Grp.sync();
     const R rank_floor = R(64) * num<R>::eps() * amax;     // (amax: the largest entry met while walking the rows)
 
     // ---- minimum-norm part: Jc = U B P^T (B lower bidiagonal) or L Q;  x = P [y; 0],  B y = -U^T r  /  L y = -r
@@ -207,63 +206,62 @@ struct Lapack {
         t[i] = R(0);
       }
     }
-    R tau_s[C1];                                   // (static copies: the loops below are unrolled)
+    // Z = G_0 ... G_{C-1} [0; I]: the null basis as gesdd returns it (columns of Z = rows C.. of VT).  The reflectors
+    // are applied to the minimum-norm vector and to this lane's columns of Z in one sweep (every index static).
+    constexpr int CPL = (k + LPE - 1) / LPE;       // columns of Z per lane
+    R Z[CPL > 0 ? CPL : 1][N];
     ATACOM_UNROLL
-    for (int i = 0; i < C; ++i) tau_s[i] = taup[i];
+    for (int cc = 0; cc < CPL; ++cc) {
+      ATACOM_UNROLL
+      for (int j = 0; j < N; ++j) Z[cc][j] = (j - C == sub + cc * LPE) ? R(1) : R(0);
+    }
+    const bool null_part = want_null && k > 0;
     ATACOM_UNROLL
     for (int i = C - 1; i >= 0; --i) {
+      R vi[N];
+      ATACOM_UNROLL
+      for (int j = i + 1; j < N; ++j) vi[j] = S.get(a(i, j));
       R w = t[i];
       ATACOM_UNROLL
-      for (int j = i + 1; j < N; ++j) w += S.get(a(i, j)) * t[j];
+      for (int j = i + 1; j < N; ++j) w += vi[j] * t[j];
       w *= tau_s[i];
       t[i] -= w;
       ATACOM_UNROLL
-      for (int j = i + 1; j < N; ++j) t[j] -= w * S.get(a(i, j));
+      for (int j = i + 1; j < N; ++j) t[j] -= w * vi[j];
+      if (null_part) {
+        ATACOM_UNROLL
+        for (int cc = 0; cc < CPL; ++cc) {
+          R wz = R(0);                             // (row i of Z is zero before reflector i)
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) wz += vi[j] * Z[cc][j];
+          wz *= tau_s[i];
+          Z[cc][i] = -wz;
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) Z[cc][j] -= wz * vi[j];
+        }
+      }
     }
     ATACOM_UNROLL
     for (int i = 0; i < N; ++i) {
       w_mn[i] = t[i];
       w_null[i] = R(0);
     }
-    if (!want_null || k == 0) return status;
-
-    // ---- Z = G_0 ... G_{C-1} [0; I]: the null basis as gesdd returns it (columns of Z = rows C.. of VT), formed in
-    // registers (every index static); it goes to its cells of the array only when the last reflector has been read
-    {
-      R Z[N][K1];
-      ATACOM_UNROLL
-      for (int j = 0; j < N; ++j) {
+    if (!null_part) return status;
+    Grp.sync();                                    // every lane has read the last reflector: its cells may be reused
+    ATACOM_UNROLL
+    for (int cc = 0; cc < CPL; ++cc) {
+      const int c = sub + cc * LPE;
+      if (c < k) {
         ATACOM_UNROLL
-        for (int c = 0; c < k; ++c) Z[j][c] = (j - C == c) ? R(1) : R(0);
-      }
-      ATACOM_UNROLL
-      for (int i = C - 1; i >= 0; --i) {
-        R vi[N];
-        ATACOM_UNROLL
-        for (int j = i + 1; j < N; ++j) vi[j] = S.get(a(i, j));
-        ATACOM_UNROLL
-        for (int c = 0; c < k; ++c) {
-          R w = R(0);                              // (row i of Z is zero before reflector i)
-          ATACOM_UNROLL
-          for (int j = (i + 1 > C ? i + 1 : C); j < N; ++j) w += vi[j] * Z[j][c];      // rows < C above i are zero too
-          ATACOM_UNROLL
-          for (int j = i + 1; j < C; ++j) w += vi[j] * Z[j][c];
-          w *= tau_s[i];
-          Z[i][c] = -w;
-          ATACOM_UNROLL
-          for (int j = i + 1; j < N; ++j) Z[j][c] -= w * vi[j];
-        }
-      }
-      ATACOM_UNROLL
-      for (int j = 0; j < N; ++j) {
-        ATACOM_UNROLL
-        for (int c = 0; c < k; ++c) S.set(zcell(j, c), Z[j][c]);
+        for (int j = 0; j < N; ++j) S.set(zcell(j, c), Z[cc][j]);
       }
     }
+    Grp.sync();
 
     // ---- the reference's rref on V = Z^T (k x N), null_space_coordinate.py:40-79 as written: walk the columns; the
     // pivot candidate is the first largest |.| among the rows not used yet; <= tol: zero those entries and move on;
-    // else swap (columns j.. only), scale the pivot row, eliminate the column from every other row.
+    // else swap (columns j.. only), scale the pivot row, eliminate the column from every other row.  Every lane takes
+    // the same decisions; the columns an elimination step touches are shared out round robin.
     int rr = 0;
     ATACOM_ROLLED
     for (int j = 0; j < N && rr < k; ++j) {
@@ -281,9 +279,12 @@ struct Lapack {
       }
       if (!(p > tol)) {
         status |= ST_COLUMN_DROPPED;
-        ATACOM_UNROLL
-        for (int i = 0; i < k; ++i) {
-          if (i >= rr) S.set(zcell(j, i), R(0));
+        Grp.sync();                                // everyone has read column j
+        if (sub == 0) {
+          ATACOM_UNROLL
+          for (int i = 0; i < k; ++i) {
+            if (i >= rr) S.set(zcell(j, i), R(0));
+          }
         }
         continue;
       }
@@ -300,29 +301,30 @@ struct Lapack {
       R f[K1];
       ATACOM_UNROLL
       for (int i = 0; i < k; ++i) f[i] = (i == rr) ? R(0) : ((i == kk) ? other : colj[i]);
-      ATACOM_UNROLL
-      for (int jj = 0; jj < N; ++jj) {
-        if (jj >= j) {
-          R e[K1];
-          ATACOM_UNROLL
-          for (int i = 0; i < k; ++i) e[i] = S.get(zcell(jj, i));
-          R ek = R(0), er = R(0);
-          ATACOM_UNROLL
-          for (int i = 0; i < k; ++i) {
-            ek = (i == kk) ? e[i] : ek;
-            er = (i == rr) ? e[i] : er;
-          }
-          const R lead = ek * inv;
-          ATACOM_UNROLL
-          for (int i = 0; i < k; ++i) {
-            const R cur = (i == kk) ? er : e[i];                 // swap rr <-> kk (a no-op when kk == rr)
-            const R out = (i == rr) ? lead : cur - f[i] * lead;
-            S.set(zcell(jj, i), out);
-          }
+      Grp.sync();                                  // everyone has read column j before it is rewritten
+      ATACOM_ROLLED
+      for (int jj = j + sub; jj < N; jj += LPE) {
+        R e[K1];
+        ATACOM_UNROLL
+        for (int i = 0; i < k; ++i) e[i] = S.get(zcell(jj, i));
+        R ek = R(0), er = R(0);
+        ATACOM_UNROLL
+        for (int i = 0; i < k; ++i) {
+          ek = (i == kk) ? e[i] : ek;
+          er = (i == rr) ? e[i] : er;
+        }
+        const R lead = ek * inv;
+        ATACOM_UNROLL
+        for (int i = 0; i < k; ++i) {
+          const R cur = (i == kk) ? er : e[i];                 // swap rr <-> kk (a no-op when kk == rr)
+          const R out = (i == rr) ? lead : cur - f[i] * lead;
+          S.set(zcell(jj, i), out);
         }
       }
+      Grp.sync();
       ++rr;
     }
+    Grp.sync();
     if (rr < k) status |= ST_RANK_DEFICIENT;
     ATACOM_UNROLL
     for (int j = 0; j < N; ++j) {
