@@ -661,7 +661,7 @@ constexpr int FIX_LPE = 4;      // lanes of a warp per deferred environment
 // The lanes of a warp that share one environment in the fix-up kernel (Lapack::project, GRP).
 struct WarpLanes {
   int s;
-  unsigned mask;      // the lanes of the warp that take part in this round
+  unsigned mask;      // the lanes of the warp that share this environment
   __device__ __forceinline__ int sub() const { return s; }
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
@@ -698,9 +698,10 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
   PlainSharedStore<double, CFG::STRIDE> S{reinterpret_cast<double*>(atacom_smem) + slot};
   const bool ec = P.variant == VARIANT_EC;
   for (int t0 = 0; t0 < cnt; t0 += CFG::ENVS) {
-    const bool active = t0 + slot < cnt;
-    const unsigned mask = __ballot_sync(0xffffffffu, active);
-    if (!active) continue;
+    if (t0 + slot >= cnt) continue;
+    // the four lanes of THIS environment: the groups of a warp take different data-dependent paths (pivot or drop,
+    // identity reflectors), so each synchronises on its own
+    const unsigned mask = 0xFu << ((threadIdx.x & 31u) & ~3u);
     const int64_t e = seg[t0 + slot];
     float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
     row_load<n>(a.q, e, q);
@@ -1336,7 +1337,8 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = step_pdl_enabled() ? 1 : 0;
-    const bool ok = cudaLaunchKernelEx(&cfg, atacom_fix_kernel<Env>, f, Pk, Kd) == cudaSuccess;
+    static const bool skip_fix = getenv("ATACOM_DEBUG_SKIP_FIX") != nullptr;     // debugging aid: step kernel alone
+    const bool ok = skip_fix || cudaLaunchKernelEx(&cfg, atacom_fix_kernel<Env>, f, Pk, Kd) == cudaSuccess;
     cudaFreeAsync(scratch, static_cast<cudaStream_t>(stream));
     if (!ok) {
       cudaGetLastError();
