@@ -499,7 +499,9 @@ struct Dual {
   // are an elimination-transformed basis of the remaining null space with Gram matrix >= I, so max |y_i| >=
   // p_j / sqrt(k - r).  Outside that band no column is dropped by either procedure, the pivots are the first k
   // columns, and the result is the basis-free closed form computed here.
-  template <bool defer_general = false, class YS, class LS, typename W>
+  // BAND_ONLY: the same decided at compile time (the step kernels of ATACOM_BASIS_LAPACK): everything from (7) on —
+  // slack pivots, the general routine — is then unreachable and not even compiled into the kernel.
+  template <bool defer_general = false, bool BAND_ONLY = false, class YS, class LS, typename W>
   static ATACOM_HD uint8_t project(YS& Y, LS& Ls, const R* dg, const R* s, const R* r, const R* alpha, R tol,
                                    bool want_null, W* w_mn, R* w_null, bool band_defer = false) {
     uint8_t status = 0;
@@ -743,6 +745,9 @@ struct Dual {
     }
     ATACOM_UNROLL
     for (int i = 0; i < GD; ++i) w_null[n + i] = -s[i] * yv[F + i];
+    if constexpr (BAND_ONLY) {
+      return (band || npiv < k) ? (status | ST_LAPACK_PATH) : status;      // (a rank-deficient Jc is flagged there too)
+    }
     if (band_defer && (band || npiv < k) && !(status & ST_RANK_DEFICIENT)) return status | ST_LAPACK_PATH;
     if (npiv == k) return status;
 

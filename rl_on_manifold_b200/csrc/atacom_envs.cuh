@@ -578,7 +578,7 @@ ATACOM_HD uint8_t finish_step(const ParamsT<T>& P, const DualConsts<HP>& Kd, con
 // Projection + assembly + slack integration + acceleration truncation on operands that are already in place:
 // Y holds the K-scaled dense Jacobian rows, dg the diagonal rows, r the right-hand side (slack terms included),
 // sh the current slacks.  s_new = s + dt w_z in HP (atacom.py:135); ddq clipped (atacom.py:117-121).
-template <class Env, typename T, typename HP, class YS, class LS>
+template <class Env, typename T, typename HP, bool BAND_ONLY = false, class YS, class LS>
 ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const HP* dg, const HP* r,
                             const HP* sh, const T* alpha, const T* dq, T* ddq, HP* s_new, T* w_dbg,
                             HP* coop = nullptr, int coop_slots = 1, int coop_stride = 0) {
@@ -600,9 +600,10 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   // whole launch.  Many askers: each runs the serial routine, all at once.  The warp is converged here (threads
   // past the end of the batch recompute the last environment); a scratch slot is shared by the warps that map to
   // it under the lock stored behind it.
-  constexpr bool COOP = is_shared_store<YS>::value && N >= 2 * n;
+  constexpr bool COOP = is_shared_store<YS>::value && N >= 2 * n && !BAND_ONLY;
   const bool band_defer = P.basis_mode == BASIS_LAPACK && k > 1;     // (k = 1: the null basis is unique up to its sign)
-  uint8_t st = Dual<HP, D, NDIAG>::template project<COOP>(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null, band_defer);
+  uint8_t st = Dual<HP, D, NDIAG>::template project<COOP, BAND_ONLY>(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null,
+                                                                     band_defer);
   if constexpr (COOP) {
     using DU = Dual<HP, D, NDIAG>;
     unsigned pend = __ballot_sync(0xffffffffu, (st & ST_DENSE_PATH) != 0);
@@ -651,7 +652,7 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   return finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, s_new, w_dbg, st);
 }
 
-template <class Env, typename T, typename HP, class YS, class LS, class Fetch>
+template <class Env, typename T, typename HP, bool BAND_ONLY = false, class YS, class LS, class Fetch>
 ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q,
                                  const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg, HP* coop = nullptr,
                                  int coop_slots = 1, int coop_stride = 0) {
@@ -666,8 +667,8 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   sink.add_slack_terms(sh);
-  const uint8_t st = dual_tail<Env, T, HP>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg, coop, coop_slots,
-                                           coop_stride);
+  const uint8_t st = dual_tail<Env, T, HP, BAND_ONLY>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg, coop,
+                                                      coop_slots, coop_stride);
   if (st & (ST_DENSE_PATH | ST_LAPACK_PATH)) return st;
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
@@ -724,13 +725,57 @@ ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>
   return st;
 }
 
+// Sink of the LAPACK path: the K-scaled Jacobian entries go straight to their cells of Jc (row i is written by lane
+// i mod LPE of the group), the three scalar streams are folded into the right-hand side as they arrive (DualSink's
+// rule), so no C x n array is ever live in registers.
+template <typename T, typename HP, class D, int LPE, class ST>
+struct LapackSink {
+  using JT = HP;
+  using LP = Lapack<HP, D>;
+  const DualConsts<HP>& Kd;
+  ST& S;
+  int lane;
+  HP r[at_least_1<D::C>::value];
+  ATACOM_HD LapackSink(const DualConsts<HP>& Kd_, ST& S_, int lane_) : Kd(Kd_), S(S_), lane(lane_) {
+    ATACOM_UNROLL
+    for (int i = 0; i < D::C; ++i) r[i] = HP(0);
+  }
+  ATACOM_HD void put_c(int i, HP v) { r[i] += Kd.K_c[i] * v; }
+  ATACOM_HD void put_Jdq(int i, HP v) { r[i] += Kd.wJ[i] * v; }
+  ATACOM_HD void put_b(int i, T v) { r[i] += Kd.wb[i] * cvt<HP>(v); }
+  ATACOM_HD void put_J(int i, int j, HP v) {
+    if (LPE == 1 || (i % LPE) == lane) S.set(LP::a(i, j), Kd.K[i] * v);                  // constraints.py:39-40
+  }
+};
+
 template <class Env, typename T, typename HP, int LPE = 1, class ST, class GRP = SoloGroup>
 ATACOM_HD uint8_t step_lapack(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST& S, const T* q, const T* dq, const T* s,
                               const T* alpha, T* ddq, T* s_out, T* w_dbg, const GRP& Grp = GRP()) {
   using D = typename Env::D;
-  RawConstraints<T, HP, D, HP> R;
-  Env::template eval<T, HP>(P, q, dq, R);
-  return step_lapack_from_raw<D, T, HP, LPE>(P, Kd, S, R, dq, s, alpha, ddq, s_out, w_dbg, Grp);
+  using LP = Lapack<HP, D>;
+  constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
+  const bool ec = P.variant == VARIANT_EC;
+  LapackSink<T, HP, D, LPE, ST> sink(Kd, S, Grp.sub());
+  Env::template eval<T, HP>(P, q, dq, sink);
+  HP sh[at_least_1<G>::value], sn[at_least_1<G>::value];
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
+  ATACOM_UNROLL
+  for (int i = 0; i < C; ++i) {
+    if (LPE == 1 || (i % LPE) == Grp.sub()) {
+      ATACOM_UNROLL
+      for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
+    }
+    if (i >= F) sink.r[i] += HP(0.5) * Kd.K_c[i] * sh[i >= F ? i - F : 0] * sh[i >= F ? i - F : 0];      // atacom.py:195
+  }
+  HP ah[at_least_1<k>::value], w_mn[N], w_null[N];
+  ATACOM_UNROLL
+  for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
+  uint8_t st = LP::template project<LPE>(S, sink.r, ah, Kd.tol, !ec, w_mn, w_null, Grp) | ST_LAPACK_PATH;
+  st = finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, sn, w_dbg, st);
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
+  return st;
 }
 
 // atacom.py:145-149

@@ -286,8 +286,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // spreads evenly over the SMs in as few waves as possible — 65 536 environments are one block of 448 per SM.
 // No block barrier anywhere on the main path: warps drift apart on purpose (while one waits for its loads
 // another is in the FP64-heavy part of the projection).  Timing model and measurements: DESIGN.md §6.
-template <class Env, int IO>   // 0: direct rows, 1: bulk loads and stores, 2: direct loads, bulk stores,
-                              // 3: q, dq direct; s, alpha bulk-copied in the background of the kinematics
+template <class Env, int IO, bool BAND>   // IO 0: direct rows, 1: bulk loads and stores, 2: direct loads, bulk stores,
+                                         // 3: q, dq direct; s, alpha bulk-copied in the background of the kinematics
+                                         // BAND: ATACOM_BASIS_LAPACK — environments inside rref's tolerance band are
+                                         // left to the fix-up kernel (the slack-pivot phases are not compiled in)
 __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid_constant__ StepArgs a,
                                                                     const __grid_constant__ ParamsT<float> P,
                                                                     const __grid_constant__ DualConsts<double> Kd) {
@@ -426,8 +428,8 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < n; ++j) a_row[j] = al[j];
   };
-  const uint8_t st = step_dual_lazy<Env, float, double>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg, SC::coop(atacom_smem),
-                                                                SC::COOP_SLOTS, SC::COOP_STRIDE);
+  const uint8_t st = step_dual_lazy<Env, float, double, BAND>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg,
+                                                              SC::coop(atacom_smem), SC::COOP_SLOTS, SC::COOP_STRIDE);
 #else
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
@@ -1238,17 +1240,33 @@ int check_common(int64_t B, const AtacomParams* p) {
 
 // Opt the kernel in to its dynamic shared memory: the attribute belongs to the (function, device) pair, so
 // once per instantiation AND device (a process that first runs on cuda:0 and then on cuda:1 needs both).
-template <class Env, int IO>
+template <class Env, int IO, bool BAND = false>
 bool configure_step_kernel() {
   static std::atomic<int> states[MAX_DEVICES];   // 0: not yet, 1: done, -1: failed
   std::atomic<int>& state = states[current_device()];
   if (state.load(std::memory_order_acquire) == 0) {
     constexpr size_t smem = StepScratch<Env>::BYTES;
     state.store((smem <= 48 * 1024 ||
-                 cudaFuncSetAttribute(atacom_step_kernel<Env, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                 cudaFuncSetAttribute(atacom_step_kernel<Env, IO, BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)) == cudaSuccess) ? 1 : -1, std::memory_order_release);
   }
   return state.load(std::memory_order_acquire) == 1;
+}
+
+// The per-launch scratch comes from the device's default stream-ordered pool, whose release threshold is zero by
+// default: every synchronisation would hand the memory back to the OS and the next launch would pay for a fresh
+// mapping.  Raised once per device, so that the pool keeps what it has.
+void keep_scratch_pool_warm() {
+  static std::atomic<int> done[MAX_DEVICES];
+  const int dev = current_device();
+  if (done[dev].load(std::memory_order_acquire)) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = 64ull << 20;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[dev].store(1, std::memory_order_release);
 }
 
 template <class Env>
@@ -1303,16 +1321,20 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   const int tpb = (tpb_override >= 32 && tpb_override <= STEP_MAX_TPB) ? tpb_override / 32 * 32 : step_block_size(B);
   const unsigned grid = static_cast<unsigned>((B + tpb - 1) / tpb);
   const size_t smem = StepScratch<Env>::bytes(tpb);
-  if (!configure_step_kernel<Env, IO>()) return ATACOM_ERR_CUDA;
   NvtxRange range("atacom_step");
   // ATACOM_BASIS_LAPACK (default): the step kernel leaves the environments inside the tolerance band of rref to the
   // fix-up kernel.  The per-block lists live in stream-ordered scratch memory (capturable in a CUDA graph).
   const bool two_pass = p->basis_mode == ATACOM_BASIS_LAPACK && p->variant == ATACOM_VARIANT_ATACOM && D::k > 1;
+  constexpr bool CAN_BAND = D::k > 1;          // (k = 1: the null basis is unique up to its sign, nothing to defer)
+  if (!(two_pass ? configure_step_kernel<Env, IO, CAN_BAND>() : configure_step_kernel<Env, IO, false>())) return ATACOM_ERR_CUDA;
+  const void* kernel = two_pass ? reinterpret_cast<const void*>(&atacom_step_kernel<Env, IO, CAN_BAND>)
+                                : reinterpret_cast<const void*>(&atacom_step_kernel<Env, IO, false>);
   if (p->basis_mode != ATACOM_BASIS_LAPACK && p->basis_mode != ATACOM_BASIS_CANONICAL) return ATACOM_ERR_BAD_PARAM;
   if (two_pass && local_sync) return ATACOM_ERR_BAD_PARAM;   // the in-kernel barrier would publish the step before the fix-up
   int32_t* scratch = nullptr;
   if (two_pass) {
     if (!configure_fix_kernel<Env>()) return ATACOM_ERR_CUDA;
+    keep_scratch_pool_warm();
     const size_t bytes = sizeof(int32_t) * (static_cast<size_t>(grid) * tpb + grid);
     if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
       cudaGetLastError();
@@ -1363,7 +1385,8 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     cfg.numAttrs = 1;
     const ParamsT<float> Pk = as_params(p);
     const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
-    if (cudaLaunchKernelEx(&cfg, atacom_step_kernel<Env, IO>, a, Pk, Kd) != cudaSuccess) {
+    void* kargs[3] = {const_cast<StepArgs*>(&a), const_cast<ParamsT<float>*>(&Pk), const_cast<DualConsts<double>*>(&Kd)};
+    if (cudaLaunchKernelExC(&cfg, kernel, kargs) != cudaSuccess) {
       cudaGetLastError();
       if (scratch) cudaFreeAsync(scratch, static_cast<cudaStream_t>(stream));
       return ATACOM_ERR_CUDA;
@@ -1371,8 +1394,12 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return fix_up();
   }
-  atacom_step_kernel<Env, IO><<<grid, tpb, smem, static_cast<cudaStream_t>(stream)>>>(
-      a, as_params(p), make_dual_consts<float, double>(as_params(p), D::F, D::G));
+  {
+    const ParamsT<float> Pk = as_params(p);
+    const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
+    void* kargs[3] = {&a, const_cast<ParamsT<float>*>(&Pk), const_cast<DualConsts<double>*>(&Kd)};
+    cudaLaunchKernel(kernel, dim3(grid), dim3(static_cast<unsigned>(tpb)), kargs, smem, static_cast<cudaStream_t>(stream));
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   rc = check_launch();
   if (rc != ATACOM_OK) {
@@ -2058,8 +2085,10 @@ static int step_host(AtacomHostCtx* c, int family_id, const float* q, const floa
   if (!q || !dq || !ddq || (D::G > 0 && (!s_in || !s_out)) || (na > 0 && !alpha)) return ATACOM_ERR_NULL_POINTER;
   // every kernel instantiation the call may use opts in to its shared memory now, not while capturing
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+  constexpr bool CB = D::k > 1;
   if (!configure_step_kernel<Env, ATACOM_STEP_DEVICE_IO>() || !configure_step_kernel<Env, HOST_IO>() ||
-      !configure_step_kernel<Env, 2>() || !configure_fix_kernel<Env>())
+      !configure_step_kernel<Env, 2>() || !configure_step_kernel<Env, ATACOM_STEP_DEVICE_IO, CB>() ||
+      !configure_step_kernel<Env, HOST_IO, CB>() || !configure_step_kernel<Env, 2, CB>() || !configure_fix_kernel<Env>())
     return ATACOM_ERR_CUDA;
   step_block_size(1);
   HostCall call = {};

@@ -115,14 +115,12 @@ struct Lapack {
       tau_s[i] = tau;
       ATACOM_UNROLL
       for (int j = i + 1; j < N; ++j) v[j] *= sc;
-      if (sub == 0) {
+      if (sub == 0) {                              // (tau = 0, the identity: x = 0 = v, every update below is a no-op)
         S.set(a(i, i), beta);
-        if (tau != R(0)) {
-          ATACOM_UNROLL
-          for (int j = i + 1; j < N; ++j) S.set(a(i, j), v[j]);
-        }
+        ATACOM_UNROLL
+        for (int j = i + 1; j < N; ++j) S.set(a(i, j), v[j]);
       }
-      if (tau != R(0)) {
+      {
         ATACOM_ROLLED
         for (int l = i + 1 + sub; l < C; l += LPE) {      // rows below: A <- A G_i, one load and one store per entry
           R row[N];
@@ -153,7 +151,7 @@ struct Lapack {
         R betaq, tauq, scq;
         larfg(c0, un2, &betaq, &tauq, &scq);
         if (sub == 0) S.set(a(i + 1 < C ? i + 1 : 0, i), betaq);     // (u itself is not needed again: it is applied to r here)
-        if (tauq != R(0)) {
+        {
           ATACOM_UNROLL
           for (int l = i + 2; l < C; ++l) u[l] *= scq;
           ATACOM_ROLLED
@@ -206,54 +204,46 @@ struct Lapack {
         t[i] = R(0);
       }
     }
-    // Z = G_0 ... G_{C-1} [0; I]: the null basis as gesdd returns it (columns of Z = rows C.. of VT).  The reflectors
-    // are applied to the minimum-norm vector and to this lane's columns of Z in one sweep (every index static).
-    constexpr int CPL = (k + LPE - 1) / LPE;       // columns of Z per lane
-    R Z[CPL > 0 ? CPL : 1][N];
+    // P = G_0 ... G_{C-1} applied to k + 1 vectors in one sweep over the reflectors (every index static): vector 0 is
+    // [y; 0], which becomes the minimum-norm solution; vectors 1..k are the unit vectors e_C .. e_{N-1}, which become
+    // the columns of Z — the null basis as gesdd returns it (rows C.. of VT).  The lanes take the vectors round robin.
+    const bool null_part = want_null && k > 0;
+    constexpr int CPL = (k + 1 + LPE - 1) / LPE;   // vectors per lane
+    R X[CPL][N];
     ATACOM_UNROLL
     for (int cc = 0; cc < CPL; ++cc) {
       ATACOM_UNROLL
-      for (int j = 0; j < N; ++j) Z[cc][j] = (j - C == sub + cc * LPE) ? R(1) : R(0);
+      for (int j = 0; j < N; ++j) X[cc][j] = (sub + cc * LPE == 0) ? t[j] : ((j - C == sub + cc * LPE - 1) ? R(1) : R(0));
     }
-    const bool null_part = want_null && k > 0;
     ATACOM_UNROLL
     for (int i = C - 1; i >= 0; --i) {
       R vi[N];
       ATACOM_UNROLL
       for (int j = i + 1; j < N; ++j) vi[j] = S.get(a(i, j));
-      R w = t[i];
       ATACOM_UNROLL
-      for (int j = i + 1; j < N; ++j) w += vi[j] * t[j];
-      w *= tau_s[i];
-      t[i] -= w;
-      ATACOM_UNROLL
-      for (int j = i + 1; j < N; ++j) t[j] -= w * vi[j];
-      if (null_part) {
+      for (int cc = 0; cc < CPL; ++cc) {
+        R w = X[cc][i];
         ATACOM_UNROLL
-        for (int cc = 0; cc < CPL; ++cc) {
-          R wz = R(0);                             // (row i of Z is zero before reflector i)
-          ATACOM_UNROLL
-          for (int j = i + 1; j < N; ++j) wz += vi[j] * Z[cc][j];
-          wz *= tau_s[i];
-          Z[cc][i] = -wz;
-          ATACOM_UNROLL
-          for (int j = i + 1; j < N; ++j) Z[cc][j] -= wz * vi[j];
-        }
+        for (int j = i + 1; j < N; ++j) w += vi[j] * X[cc][j];
+        w *= tau_s[i];
+        X[cc][i] -= w;
+        ATACOM_UNROLL
+        for (int j = i + 1; j < N; ++j) X[cc][j] -= w * vi[j];
       }
     }
     ATACOM_UNROLL
     for (int i = 0; i < N; ++i) {
-      w_mn[i] = t[i];
+      w_mn[i] = X[0][i];                           // (the minimum-norm part: lane 0's first vector)
       w_null[i] = R(0);
     }
     if (!null_part) return status;
     Grp.sync();                                    // every lane has read the last reflector: its cells may be reused
     ATACOM_UNROLL
     for (int cc = 0; cc < CPL; ++cc) {
-      const int c = sub + cc * LPE;
-      if (c < k) {
+      const int c = sub + cc * LPE - 1;
+      if (c >= 0 && c < k) {
         ATACOM_UNROLL
-        for (int j = 0; j < N; ++j) S.set(zcell(j, c), Z[cc][j]);
+        for (int j = 0; j < N; ++j) S.set(zcell(j, c), X[cc][j]);
       }
     }
     Grp.sync();
@@ -289,37 +279,27 @@ struct Lapack {
         continue;
       }
       if (j >= n) status |= ST_SLACK_PIVOT;
-      R piv = R(0), other = R(0);                  // entries of column j in rows kk (the pivot) and rr
-      ATACOM_UNROLL
-      for (int i = 0; i < k; ++i) {
-        piv = (i == kk) ? colj[i] : piv;
-        other = (i == rr) ? colj[i] : other;
-      }
+      // entries of column j in rows kk (the pivot) and rr: the row index is just an address here
+      const R piv = S.get(zcell(j, kk)), other = S.get(zcell(j, rr));
       const R inv = R(1) / piv;
       // multipliers of the elimination: row i loses f_i times the scaled pivot row; after the swap row kk holds what
-      // was row rr
+      // was row rr (its multiplier is `fk`; rows rr and kk are rewritten after the generic update below)
       R f[K1];
       ATACOM_UNROLL
-      for (int i = 0; i < k; ++i) f[i] = (i == rr) ? R(0) : ((i == kk) ? other : colj[i]);
+      for (int i = 0; i < k; ++i) f[i] = colj[i];
+      const R fk = (kk == rr) ? R(0) : other;
       Grp.sync();                                  // everyone has read column j before it is rewritten
       ATACOM_ROLLED
       for (int jj = j + sub; jj < N; jj += LPE) {
         R e[K1];
         ATACOM_UNROLL
         for (int i = 0; i < k; ++i) e[i] = S.get(zcell(jj, i));
-        R ek = R(0), er = R(0);
-        ATACOM_UNROLL
-        for (int i = 0; i < k; ++i) {
-          ek = (i == kk) ? e[i] : ek;
-          er = (i == rr) ? e[i] : er;
-        }
+        const R ek = S.get(zcell(jj, kk)), er = S.get(zcell(jj, rr));
         const R lead = ek * inv;
         ATACOM_UNROLL
-        for (int i = 0; i < k; ++i) {
-          const R cur = (i == kk) ? er : e[i];                 // swap rr <-> kk (a no-op when kk == rr)
-          const R out = (i == rr) ? lead : cur - f[i] * lead;
-          S.set(zcell(jj, i), out);
-        }
+        for (int i = 0; i < k; ++i) S.set(zcell(jj, i), e[i] - f[i] * lead);
+        S.set(zcell(jj, kk), er - fk * lead);      // swap rr <-> kk: row kk takes over what was row rr ...
+        S.set(zcell(jj, rr), lead);                // ... and row rr becomes the scaled pivot row (also when kk == rr)
       }
       Grp.sync();
       ++rr;
