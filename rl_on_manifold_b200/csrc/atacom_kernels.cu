@@ -658,7 +658,11 @@ struct FixArgs {
   int32_t n_peers;
 };
 
-constexpr int FIX_LPE = 4;      // lanes of a warp per deferred environment
+#ifndef ATACOM_FIX_LPE
+#define ATACOM_FIX_LPE 2
+#endif
+constexpr int FIX_LPE = ATACOM_FIX_LPE;      // lanes of a warp per deferred environment (2 or 4; measured: DESIGN.md)
+static_assert(FIX_LPE == 2 || FIX_LPE == 4, "lanes per environment of the fix-up kernel");
 
 // The lanes of a warp that share one environment in the fix-up kernel (Lapack::project, GRP).
 struct WarpLanes {
@@ -672,12 +676,13 @@ template <class Env>
 struct FixCfg {
   using LP = Lapack<double, typename Env::D>;
   static constexpr size_t SMEM_MAX = 227 * 1024;
-  // environments per block: a multiple of 8 (a warp holds 8 groups of 4 lanes); the [cell][environment] array is
-  // padded to a stride = 4 mod 16, so that the 16 threads of a half-warp — 4 environments x 4 lanes, the lanes on
-  // cells 17 (rows) or 1 (columns) apart — hit 16 different pairs of banks
-  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE)) - 4;
-  static constexpr int ENVS = FIT >= 128 ? 128 : (FIT / 16) * 16;      // iiwa-6: 128, iiwa-7: 112
-  static constexpr int STRIDE = ENVS + 4;
+  // environments per block: a multiple of 16; the [cell][environment] array is padded to a stride = 16 / LPE mod 16,
+  // so that the 16 threads of a half-warp — 16 / LPE environments x LPE lanes, the lanes on cells 17 (rows) or 1
+  // (columns) apart — hit 16 different pairs of banks
+  static constexpr int PAD = 16 / FIX_LPE;
+  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE)) - PAD;
+  static constexpr int ENVS = FIT >= 128 ? 128 : (FIT / 16) * 16;      // iiwa-6: 128, iiwa-7: 112 (LPE 4) / 96 (LPE 2)
+  static constexpr int STRIDE = ENVS + PAD;
   static constexpr int TPB = ENVS * FIX_LPE;
   static_assert(ENVS >= 16, "the LAPACK working arrays do not fit into shared memory");
   static constexpr size_t BYTES = sizeof(double) * LP::SIZE * STRIDE;
@@ -701,9 +706,9 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
   const bool ec = P.variant == VARIANT_EC;
   for (int t0 = 0; t0 < cnt; t0 += CFG::ENVS) {
     if (t0 + slot >= cnt) continue;
-    // the four lanes of THIS environment: the groups of a warp take different data-dependent paths (pivot or drop,
+    // the lanes of THIS environment: the groups of a warp take different data-dependent paths (pivot or drop,
     // identity reflectors), so each synchronises on its own
-    const unsigned mask = 0xFu << ((threadIdx.x & 31u) & ~3u);
+    const unsigned mask = ((1u << FIX_LPE) - 1u) << ((threadIdx.x & 31u) & ~static_cast<unsigned>(FIX_LPE - 1));
     const int64_t e = seg[t0 + slot];
     float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
     row_load<n>(a.q, e, q);
