@@ -69,6 +69,9 @@ def test_point_reach_vs_oracle_full_batch(cuda_device, tmp_path):
     # 2.4e-6: a candidate in between (not the exact zeros of a structurally dependent column) is decided differently
     # and is outside the parity domain
     ok = ~ref["rank_def"] & ~ref["ambiguous"]
+    # an agent exactly inside an obstacle (s_i = 0 with a dependent row) leaves Jc singular to working precision: the
+    # reference's own output is then ~1e15 and decided by rounding — a handful per batch, outside the parity domain
+    ok &= np.abs(ref["w"]).max(1) < 1e8
     e_w = helpers.rel_err(w.cpu().numpy(), ref["w"][:, :2], ref["w"])
     e_s = helpers.rel_err(s_out.cpu().numpy(), ref["s_new"])
     print("\n[point_reach] B=%d: parity domain %d (excluded %d); max rel err w %.2e s %.2e"
