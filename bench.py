@@ -348,12 +348,13 @@ def ours(args):
         if world > 1:
             dist.all_gather_into_tensor(gathered, sets[i % ring]["out"])
 
-    fused, fused_note = None, None
+    fused, fused_note, fused_other = None, None, None
     if world > 1 and wl == "iiwa" and args.gather != "nccl":
         try:
             from rl_on_manifold_b200.sharding import SymmetricGather
             fused = SymmetricGather(B, n_out, deferred=(args.gather == "fused-deferred"))
             fused_note = fused.describe()
+            fused_other = SymmetricGather(B, n_out, deferred=(args.gather != "fused-deferred"))     # the other schedule, for comparison
         except Exception as exc:
             fused_note = "fused gather unavailable (%s: %s); NCCL all-gather used" % (type(exc).__name__, exc)
 
@@ -451,11 +452,16 @@ def ours(args):
     launches = K * len(replay_ms) if not args.no_graph else launches_eager
 
     # ---- comparison paths at N > 1 (reported in config, never substituted for the default path)
-    nccl_ms = kernel_ms_list = None
+    nccl_ms = kernel_ms_list = other_ms = None
     if world > 1:
         kernel_ms_list = [eager_ms] if args.no_graph else timed_graphs(kernel_only)
         if fused is not None:
             nccl_ms = statistics.median([timed_eager(step_nccl)] if args.no_graph else timed_graphs(step_nccl))
+        if fused_other is not None and not args.no_graph:
+            def step_other(i):
+                d = sets[i % ring]
+                fused_other.step(d["q"], d["dq"], d["s"], d["alpha"], params, n_ctrl_joints=N_JOINTS, s_out=d["s_out"])
+            other_ms = statistics.median(timed_graphs(step_other, fused_other.finish, fused_other.reset))
     else:
         kernel_ms_list = replay_ms
     kernel_ms = statistics.median(kernel_ms_list)
@@ -561,6 +567,9 @@ def ours(args):
                         parallelism="env-shard x%d; %s" % (world, gather_mode) if world > 1 else "single GPU",
                         gather_verified=gather_verified,
                         nccl_all_gather_ms_per_step=(nccl_ms / K) if nccl_ms else None,
+                        other_fused_schedule_ms_per_step=(other_ms / K) if other_ms else None,
+                        other_fused_schedule=fused_other.describe() if (fused_other is not None and other_ms) else None,
+                        kernels_only_ms_per_step=(kernel_ms / K) if world > 1 else None,
                         cold_inputs="ring of %d distinct batches (%.0f MB > 2x L2) rotated every step"
                                     % (ring, ring * B * bytes_env / 1e6),
                         bytes_per_env_step=bytes_env, launch=launch_mode, replays=len(replay_ms),
@@ -623,7 +632,9 @@ def main():
     ap.add_argument("--replays", type=int, default=7)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "fused-deferred", "nccl"])
+    ap.add_argument("--gather", default="fused-deferred", choices=["fused", "fused-deferred", "nccl"],
+                    help="N > 1: fused peer-store epilogue with the barrier of step t deferred behind kernel t+1 (default), "
+                         "with the barrier on the kernel's stream, or a plain NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
