@@ -1,9 +1,16 @@
 #!/usr/bin/env python
 """Turn an Nsight Compute report into the small text summary committed under profiles/.
 
-    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/r01_step_kernel.txt
+    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/r02_step_kernels_ncu.txt
+    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep --traffic iiwa 65536 profiles/r02_step_kernels_ncu.txt
+
+The second form also (re)writes the workload's entry of profiles/dram_traffic.json — the DRAM bytes per step
+(dram__bytes_read.sum + dram__bytes_write.sum, summed over the kernels of one step) that bench.py reports as
+roofline.traffic — straight from the report, so the number in the bench line is the measured one.
 
 Needs `ncu` on PATH (no GPU required to read a report)."""
+import json
+import os
 import collections
 import csv
 import io
@@ -64,5 +71,33 @@ def main(rep):
             print("  %5.1f %%  %s" % (100.0 * v / tot, f))
 
 
+def traffic(rep, workload, batch, source):
+    rows = ncu_csv(rep, "raw")
+    hdr, data = rows[0], rows[2:]
+    name_i, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    units = rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_kernel = collections.OrderedDict()
+    for r in data:                       # first profiled launch of every kernel = one step
+        k = r[name_i].split("(")[0]
+        if k not in per_kernel:
+            per_kernel[k] = (float(r[rd]) * scale.get(units[rd], 1.0), float(r[wr]) * scale.get(units[wr], 1.0))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dram_traffic.json")
+    try:
+        table = json.load(open(path))
+        if "bytes_per_launch" in table:  # round-1 layout (one hand-filled entry)
+            table = {}
+    except Exception:
+        table = {}
+    table[workload] = dict(batch=int(batch), bytes_per_launch=int(sum(a + b for a, b in per_kernel.values())),
+                           kernels={k: dict(dram_bytes_read=int(a), dram_bytes_write=int(b)) for k, (a, b) in per_kernel.items()},
+                           source="%s (ncu --set full --clock-control none of `bench.py`, first profiled launch of each "
+                                  "kernel of one step; written by profiles/summarize_ncu.py)" % source)
+    json.dump(table, open(path, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+        traffic(sys.argv[1], sys.argv[3], sys.argv[4], sys.argv[5])
+    else:
+        main(sys.argv[1])
