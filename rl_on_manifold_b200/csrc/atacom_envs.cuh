@@ -578,10 +578,20 @@ ATACOM_HD uint8_t finish_step(const ParamsT<T>& P, const DualConsts<HP>& Kd, con
 // Projection + assembly + slack integration + acceleration truncation on operands that are already in place:
 // Y holds the K-scaled dense Jacobian rows, dg the diagonal rows, r the right-hand side (slack terms included),
 // sh the current slacks.  s_new = s + dt w_z in HP (atacom.py:135); ddq clipped (atacom.py:117-121).
-template <class Env, typename T, typename HP, bool BAND_ONLY = false, class YS, class LS>
+// Where the minimum-norm part of an environment that is left to the LAPACK-basis routine goes: `row()` returns the N
+// HP values of this environment or null.  A functor, so that a kernel can work the address out only when it is needed
+// (nothing stays live in registers across the projection).
+template <typename HP>
+struct WmnRow {
+  HP* p;
+  ATACOM_HD HP* row() const { return p; }
+};
+
+template <class Env, typename T, typename HP, bool BAND_ONLY = false, class YS, class LS, class WO = WmnRow<HP>>
 ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const HP* dg, const HP* r,
                             const HP* sh, const T* alpha, const T* dq, T* ddq, HP* s_new, T* w_dbg,
-                            HP* coop = nullptr, int coop_slots = 1, int coop_stride = 0) {
+                            HP* coop = nullptr, int coop_slots = 1, int coop_stride = 0,
+                            const WO& wmn_out = WO{nullptr}) {
   // coop: the first of the block's coop_slots scratch slots (coop_stride doubles apart) of the warp-cooperative
   // general routine, on the device when Y and L live in shared memory
   using D = typename Env::D;
@@ -648,14 +658,24 @@ ATACOM_HD uint8_t dual_tail(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
   const bool band_defer = P.basis_mode == BASIS_LAPACK && k > 1;
   uint8_t st = Dual<HP, D, NDIAG>::project(Y, Ls, dg, sh, r, ah, Kd.tol, !ec, w_mn, w_null, band_defer);
 #endif
-  if (st & (ST_DENSE_PATH | ST_LAPACK_PATH)) return st;     // (only after the warp-wide ballot above)
+  if (st & ST_LAPACK_PATH) {
+    // left to the LAPACK-basis routine: the minimum-norm part does not depend on the basis and is handed on
+    HP* out = wmn_out.row();
+    if (out != nullptr) {
+      ATACOM_UNROLL
+      for (int i = 0; i < N; ++i) out[i] = w_mn[i];
+    }
+    return st;
+  }
+  if (st & ST_DENSE_PATH) return st;     // (only after the warp-wide ballot above)
   return finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, s_new, w_dbg, st);
 }
 
-template <class Env, typename T, typename HP, bool BAND_ONLY = false, class YS, class LS, class Fetch>
+template <class Env, typename T, typename HP, bool BAND_ONLY = false, class YS, class LS, class Fetch,
+          class WO = WmnRow<HP>>
 ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q,
                                  const T* dq, Fetch&& fetch, T* ddq, T* s_out, T* w_dbg, HP* coop = nullptr,
-                                 int coop_slots = 1, int coop_stride = 0) {
+                                 int coop_slots = 1, int coop_stride = 0, const WO& wmn_out = WO{nullptr}) {
   using D = typename Env::D;
   constexpr int NDIAG = Env::NDIAG;
   constexpr int n = D::n, G = D::G;
@@ -668,7 +688,7 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   sink.add_slack_terms(sh);
   const uint8_t st = dual_tail<Env, T, HP, BAND_ONLY>(P, Kd, Y, Ls, sink.dg, sink.r, sh, alpha, dq, ddq, sn, w_dbg, coop,
-                                                      coop_slots, coop_stride);
+                                                      coop_slots, coop_stride, wmn_out);
   if (st & (ST_DENSE_PATH | ST_LAPACK_PATH)) return st;
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
@@ -677,7 +697,7 @@ ATACOM_HD uint8_t step_dual_lazy(const ParamsT<T>& P, const DualConsts<HP>& Kd, 
 
 template <class Env, typename T, typename HP, class YS, class LS>
 ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y, LS& Ls, const T* q, const T* dq,
-                            const T* s, const T* alpha, T* ddq, T* s_out, T* w_dbg) {
+                            const T* s, const T* alpha, T* ddq, T* s_out, T* w_dbg, HP* wmn_out = nullptr) {
   using D = typename Env::D;
   auto fetch = [&](T* s_row, T* a_row) {
     ATACOM_UNROLL
@@ -685,7 +705,7 @@ ATACOM_HD uint8_t step_dual(const ParamsT<T>& P, const DualConsts<HP>& Kd, YS& Y
     ATACOM_UNROLL
     for (int j = 0; j < D::n; ++j) a_row[j] = alpha[j];
   };
-  return step_dual_lazy<Env, T, HP>(P, Kd, Y, Ls, q, dq, fetch, ddq, s_out, w_dbg);
+  return step_dual_lazy<Env, T, HP>(P, Kd, Y, Ls, q, dq, fetch, ddq, s_out, w_dbg, nullptr, 1, 0, WmnRow<HP>{wmn_out});
 }
 
 // The whole step on the LAPACK-basis routine (atacom_lapack.cuh): what the step kernels run for the environments
@@ -772,6 +792,55 @@ ATACOM_HD uint8_t step_lapack(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST&
   ATACOM_UNROLL
   for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
   uint8_t st = LP::template project<LPE>(S, sink.r, ah, Kd.tol, !ec, w_mn, w_null, Grp) | ST_LAPACK_PATH;
+  st = finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, sn, w_dbg, st);
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);
+  return st;
+}
+
+// The fix-up kernel's step: only the NULL part is redone with the LAPACK basis.  The minimum-norm part -Jc^+ r is the
+// same for every basis; the dual path of the step kernel has computed it already and hands it on (`w_mn`, N values in
+// HP), so the right-hand side is not even assembled here: the sink keeps the K-scaled Jacobian entries and drops the
+// three scalar streams (what only they depend on — the bias terms, the constraint values — is dead code).
+template <typename T, typename HP, class D, int LPE, class ST>
+struct NullOnlySink {
+  using JT = HP;
+  using LP = Lapack<HP, D>;
+  const DualConsts<HP>& Kd;
+  ST& S;
+  int lane;
+  ATACOM_HD NullOnlySink(const DualConsts<HP>& Kd_, ST& S_, int lane_) : Kd(Kd_), S(S_), lane(lane_) {}
+  ATACOM_HD void put_c(int, HP) {}
+  ATACOM_HD void put_Jdq(int, HP) {}
+  ATACOM_HD void put_b(int, T) {}
+  ATACOM_HD void put_J(int i, int j, HP v) {
+    if (LPE == 1 || (i % LPE) == lane) S.set(LP::a(i, j), Kd.K[i] * v);                  // constraints.py:39-40
+  }
+};
+
+template <class Env, typename T, typename HP, int LPE = 1, class ST, class GRP = SoloGroup>
+ATACOM_HD uint8_t step_lapack_null(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST& S, const T* q, const T* dq,
+                                   const T* s, const T* alpha, const HP* w_mn, T* ddq, T* s_out, T* w_dbg,
+                                   const GRP& Grp = GRP()) {
+  using D = typename Env::D;
+  using LP = Lapack<HP, D>;
+  constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
+  NullOnlySink<T, HP, D, LPE, ST> sink(Kd, S, Grp.sub());
+  Env::template eval<T, HP>(P, q, dq, sink);
+  HP sh[at_least_1<G>::value], sn[at_least_1<G>::value];
+  ATACOM_UNROLL
+  for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
+  ATACOM_UNROLL
+  for (int i = 0; i < C; ++i) {
+    if (LPE == 1 || (i % LPE) == Grp.sub()) {
+      ATACOM_UNROLL
+      for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
+    }
+  }
+  HP ah[at_least_1<k>::value], w_null[N];
+  ATACOM_UNROLL
+  for (int l = 0; l < k; ++l) ah[l] = cvt<HP>(alpha[l]);
+  uint8_t st = LP::template project<LPE, false>(S, nullptr, ah, Kd.tol, true, nullptr, w_null, Grp) | ST_LAPACK_PATH;
   st = finish_step<D, T, HP>(P, Kd, w_mn, w_null, sh, alpha, dq, ddq, sn, w_dbg, st);
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) s_out[i] = cvt<T>(sn[i]);

@@ -147,6 +147,9 @@ struct StepArgs {
   // the fix-up kernel (same grid) then redoes exactly those.  Null: nothing is deferred (canonical basis).
   int32_t* fix_list;
   int32_t* fix_count;
+  // ... and their minimum-norm parts ([B, N] doubles, written for the deferred environments only): the same for every
+  // null basis, so the fix-up kernel redoes the null part alone
+  double* fix_wmn;
 };
 
 // ------------------------------------------------------------------ row access
@@ -428,8 +431,23 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < n; ++j) a_row[j] = al[j];
   };
+  // the row of fix_wmn this thread's environment owns, worked out when (and only if) the environment is deferred
+  struct WmnOut {
+    double* base;
+    const uint32_t* ticket;     // ordered admission: the block's ticket replaces blockIdx.x
+    __device__ __forceinline__ double* row() const {
+      if (base == nullptr) return nullptr;
+      unsigned t;
+      asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+      const unsigned b = ticket ? *reinterpret_cast<const volatile uint32_t*>(ticket) : blockIdx.x;
+      return base + (static_cast<int64_t>(b) * blockDim.x + t) * N;
+    }
+  };
+  const WmnOut wmn_out{BAND ? a.fix_wmn : nullptr,
+                       (IO == 1 && a.gate != nullptr) ? reinterpret_cast<const uint32_t*>(atacom_smem + SC::TICKET_OFFSET) : nullptr};
   const uint8_t st = step_dual_lazy<Env, float, double, BAND>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, dbg,
-                                                              SC::coop(atacom_smem), SC::COOP_SLOTS, SC::COOP_STRIDE);
+                                                              SC::coop(atacom_smem), SC::COOP_SLOTS, SC::COOP_STRIDE,
+                                                              wmn_out);
 #else
   RawConstraints<float, double, D> R;
   Env::template eval<float, double>(P, q, dq, R);
@@ -652,6 +670,7 @@ struct FixArgs {
   float* w_dbg;
   const int32_t* fix_list;
   const int32_t* fix_count;
+  const double* fix_wmn;    // [B, N]: the minimum-norm parts the step kernel handed on
   int32_t seg_stride;       // block size of the step kernel = length of a segment
   float* peer[ATACOM_MAX_PEERS];
   int64_t gather_row0;
@@ -661,15 +680,23 @@ struct FixArgs {
 #ifndef ATACOM_FIX_LPE
 #define ATACOM_FIX_LPE 2
 #endif
+#ifndef ATACOM_FIX_NULL_ONLY
+#define ATACOM_FIX_NULL_ONLY 1     // 0: the fix-up kernel redoes the minimum-norm part too (A/B builds)
+#endif
 constexpr int FIX_LPE = ATACOM_FIX_LPE;      // lanes of a warp per deferred environment (2 or 4; measured: DESIGN.md)
 static_assert(FIX_LPE == 2 || FIX_LPE == 4, "lanes per environment of the fix-up kernel");
 
-// The lanes of a warp that share one environment in the fix-up kernel (Lapack::project, GRP).
+// The lanes of a warp that share one environment in the fix-up kernel (Lapack::project, GRP).  The groups of a warp
+// synchronise TOGETHER, with the full mask: a group-sized mask makes the compiler wrap every __syncwarp in a
+// MATCH / vote loop (~15 instructions at each of the 31 synchronisation points of the routine), and the groups run the
+// same instruction stream anyway.  Every lane of a live warp therefore takes part from start to end — slots past the
+// end of the list redo the last environment and store nothing — and the routine passes the same synchronisation
+// points whatever an environment's data decide.
 struct WarpLanes {
   int s;
-  unsigned mask;      // the lanes of the warp that share this environment
   __device__ __forceinline__ int sub() const { return s; }
-  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
 };
 
 template <class Env>
@@ -704,12 +731,11 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
   const int slot = threadIdx.x / FIX_LPE, sub = threadIdx.x % FIX_LPE;
   PlainSharedStore<double, CFG::STRIDE> S{reinterpret_cast<double*>(atacom_smem) + slot};
   const bool ec = P.variant == VARIANT_EC;
+  const int warp_slot0 = static_cast<int>(threadIdx.x & ~31u) / FIX_LPE;      // first slot of this warp
   for (int t0 = 0; t0 < cnt; t0 += CFG::ENVS) {
-    if (t0 + slot >= cnt) continue;
-    // the lanes of THIS environment: the groups of a warp take different data-dependent paths (pivot or drop,
-    // identity reflectors), so each synchronises on its own
-    const unsigned mask = ((1u << FIX_LPE) - 1u) << ((threadIdx.x & 31u) & ~static_cast<unsigned>(FIX_LPE - 1));
-    const int64_t e = seg[t0 + slot];
+    if (t0 + warp_slot0 >= cnt) continue;              // (the whole warp)
+    const bool live = t0 + slot < cnt;                 // a slot past the end runs along on the last environment
+    const int64_t e = seg[live ? t0 + slot : cnt - 1];
     float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
     row_load<n>(a.q, e, q);
     row_load<n>(a.dq, e, dq);
@@ -722,16 +748,22 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
 #pragma unroll
       for (int j = 0; j < n; ++j) al[j] = j < k ? ak[j < k ? j : 0] : 0.f;
     }
-    float* dbg = (a.w_dbg && sub == 0) ? a.w_dbg + e * (2 * N) : nullptr;
-    const WarpLanes grp{sub, mask};
+    float* dbg = (a.w_dbg && sub == 0 && live) ? a.w_dbg + e * (2 * N) : nullptr;
+    const WarpLanes grp{sub};
+#if ATACOM_FIX_NULL_ONLY
+    // the minimum-norm part is the step kernel's (basis-free); only the null part is redone here
+    const uint8_t st = step_lapack_null<Env, float, double, FIX_LPE>(P, Kd, S, q, dq, s, al, a.fix_wmn + e * N, ddq, so,
+                                                                     dbg, grp);
+#else
     const uint8_t st = step_lapack<Env, float, double, FIX_LPE>(P, Kd, S, q, dq, s, al, ddq, so, dbg, grp);
-    if (sub == 0) {
+#endif
+    if (sub == 0 && live) {
       if (a.status) a.status[e] = st;
       if (a.ddq) row_store<n>(a.ddq, e, ddq);
       if (G > 0) row_store<G1>(a.s_out, e, so);
       for (int w = 0; w < a.n_peers; ++w) row_store<n>(a.peer[w], a.gather_row0 + e, ddq);
     }
-    __syncwarp(mask);      // the next round reuses the group's array
+    __syncwarp();          // the next round reuses the group's array
   }
 }
 
@@ -1340,17 +1372,22 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
   if (two_pass) {
     if (!configure_fix_kernel<Env>()) return ATACOM_ERR_CUDA;
     keep_scratch_pool_warm();
-    const size_t bytes = sizeof(int32_t) * (static_cast<size_t>(grid) * tpb + grid);
+    // [grid * tpb] indices, [grid] counts, then (8-byte aligned) [grid * tpb, N] minimum-norm parts
+    const size_t n_idx = (static_cast<size_t>(grid) * tpb + grid + 1) / 2 * 2;
+    const size_t bytes = sizeof(int32_t) * n_idx +
+                         (ATACOM_FIX_NULL_ONLY ? sizeof(double) * static_cast<size_t>(grid) * tpb * D::N : 0);
     if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
       cudaGetLastError();
       return ATACOM_ERR_CUDA;
     }
     a.fix_list = scratch;
     a.fix_count = scratch + static_cast<size_t>(grid) * tpb;
+    a.fix_wmn = ATACOM_FIX_NULL_ONLY ? reinterpret_cast<double*>(scratch + n_idx) : nullptr;
   }
   auto fix_up = [&]() -> int {      // second launch + release of the scratch, after the step kernel is in the stream
     if (!two_pass) return ATACOM_OK;
-    FixArgs f{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, a.fix_list, a.fix_count, tpb, {}, gather_row0, n_peers};
+    FixArgs f{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, a.fix_list, a.fix_count, a.fix_wmn, tpb, {}, gather_row0,
+              n_peers};
     for (int w = 0; w < n_peers; ++w) f.peer[w] = peers[w];
     const ParamsT<float> Pk = as_params(p);
     const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);

@@ -91,6 +91,8 @@ static ParamsT<T> unpack(const double* f) {
 
 static int g_general_path = 0;
 extern "C" void harness_set_general_path(int on) { g_general_path = on; }
+static int g_fix_full = 0;
+extern "C" void harness_set_fix_full(int on) { g_fix_full = on; }
 
 template <typename T, class Env>
 static void run_step(int64_t B, const double* params, const T* q, const T* dq, const T* s, const T* alpha, T* ddq,
@@ -121,12 +123,17 @@ static void run_step(int64_t B, const double* params, const T* q, const T* dq, c
       using DU = Dual<double, D, Env::NDIAG>;
       LocalStore<double, DU::Y_SIZE> Ys;
       LocalStore<double, DU::L_SIZE> Ls;
+      double wmn[D::N];          // the minimum-norm part the dual path hands on for a deferred environment
       uint8_t st = step_dual<Env, T, double>(P, Kd, Ys, Ls, q + b * D::n, dq + b * D::n, s + b * D::G, al,
-                                             ddq + b * D::n, s_out + b * D::G, w_dbg + b * 2 * D::N);
+                                             ddq + b * D::n, s_out + b * D::G, w_dbg + b * 2 * D::N, wmn);
       if (st & ST_LAPACK_PATH) {   // what the fix-up kernel does for the environments the dual path flagged
         ArrayStore<double, Lapack<double, D>::SIZE> S;
-        st = step_lapack<Env, T, double>(P, Kd, S, q + b * D::n, dq + b * D::n, s + b * D::G, al, ddq + b * D::n,
-                                         s_out + b * D::G, w_dbg + b * 2 * D::N);
+        if (g_fix_full)          // (A/B: the LAPACK routine redoes the minimum-norm part too)
+          st = step_lapack<Env, T, double>(P, Kd, S, q + b * D::n, dq + b * D::n, s + b * D::G, al, ddq + b * D::n,
+                                           s_out + b * D::G, w_dbg + b * 2 * D::N);
+        else
+          st = step_lapack_null<Env, T, double>(P, Kd, S, q + b * D::n, dq + b * D::n, s + b * D::G, al, wmn,
+                                                ddq + b * D::n, s_out + b * D::G, w_dbg + b * 2 * D::N);
       }
       status[b] = st;
     }
