@@ -725,7 +725,7 @@ ATACOM_HD uint8_t step_lapack_from_raw(const ParamsT<T>& P, const DualConsts<HP>
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   ATACOM_UNROLL
   for (int i = 0; i < C; ++i) {
-    if (LPE == 1 || (i % LPE) == Grp.sub()) {
+    if (LPE == 1 || Grp.write_lane() < 0 || (i % LPE) == Grp.write_lane()) {
       ATACOM_UNROLL
       for (int j = 0; j < n; ++j) S.set(LP::a(i, j), Kd.K[i] * R.J[i][j]);               // constraints.py:39-40
       ATACOM_UNROLL
@@ -764,7 +764,7 @@ struct LapackSink {
   ATACOM_HD void put_Jdq(int i, HP v) { r[i] += Kd.wJ[i] * v; }
   ATACOM_HD void put_b(int i, T v) { r[i] += Kd.wb[i] * cvt<HP>(v); }
   ATACOM_HD void put_J(int i, int j, HP v) {
-    if (LPE == 1 || (i % LPE) == lane) S.set(LP::a(i, j), Kd.K[i] * v);                  // constraints.py:39-40
+    if (LPE == 1 || lane < 0 || (i % LPE) == lane) S.set(LP::a(i, j), Kd.K[i] * v);                  // constraints.py:39-40
   }
 };
 
@@ -775,14 +775,14 @@ ATACOM_HD uint8_t step_lapack(const ParamsT<T>& P, const DualConsts<HP>& Kd, ST&
   using LP = Lapack<HP, D>;
   constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
   const bool ec = P.variant == VARIANT_EC;
-  LapackSink<T, HP, D, LPE, ST> sink(Kd, S, Grp.sub());
+  LapackSink<T, HP, D, LPE, ST> sink(Kd, S, Grp.write_lane());
   Env::template eval<T, HP>(P, q, dq, sink);
   HP sh[at_least_1<G>::value], sn[at_least_1<G>::value];
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   ATACOM_UNROLL
   for (int i = 0; i < C; ++i) {
-    if (LPE == 1 || (i % LPE) == Grp.sub()) {
+    if (LPE == 1 || Grp.write_lane() < 0 || (i % LPE) == Grp.write_lane()) {
       ATACOM_UNROLL
       for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
     }
@@ -814,7 +814,7 @@ struct NullOnlySink {
   ATACOM_HD void put_Jdq(int, HP) {}
   ATACOM_HD void put_b(int, T) {}
   ATACOM_HD void put_J(int i, int j, HP v) {
-    if (LPE == 1 || (i % LPE) == lane) S.set(LP::a(i, j), Kd.K[i] * v);                  // constraints.py:39-40
+    if (LPE == 1 || lane < 0 || (i % LPE) == lane) S.set(LP::a(i, j), Kd.K[i] * v);                  // constraints.py:39-40
   }
 };
 
@@ -825,14 +825,14 @@ ATACOM_HD uint8_t step_lapack_null(const ParamsT<T>& P, const DualConsts<HP>& Kd
   using D = typename Env::D;
   using LP = Lapack<HP, D>;
   constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
-  NullOnlySink<T, HP, D, LPE, ST> sink(Kd, S, Grp.sub());
+  NullOnlySink<T, HP, D, LPE, ST> sink(Kd, S, Grp.write_lane());
   Env::template eval<T, HP>(P, q, dq, sink);
   HP sh[at_least_1<G>::value], sn[at_least_1<G>::value];
   ATACOM_UNROLL
   for (int i = 0; i < G; ++i) sh[i] = cvt<HP>(s[i]);
   ATACOM_UNROLL
   for (int i = 0; i < C; ++i) {
-    if (LPE == 1 || (i % LPE) == Grp.sub()) {
+    if (LPE == 1 || Grp.write_lane() < 0 || (i % LPE) == Grp.write_lane()) {
       ATACOM_UNROLL
       for (int j = n; j < N; ++j) S.set(LP::a(i, j), (i >= F && j - n == i - F) ? sh[i >= F ? i - F : 0] : HP(0));   // atacom.py:151-165
     }

@@ -683,8 +683,12 @@ struct FixArgs {
 #ifndef ATACOM_FIX_NULL_ONLY
 #define ATACOM_FIX_NULL_ONLY 1     // 0: the fix-up kernel redoes the minimum-norm part too (A/B builds)
 #endif
-constexpr int FIX_LPE = ATACOM_FIX_LPE;      // lanes of a warp per deferred environment (2 or 4; measured: DESIGN.md)
-static_assert(FIX_LPE == 2 || FIX_LPE == 4, "lanes per environment of the fix-up kernel");
+// Lanes of a warp per deferred environment (2, 3 or 4).  Measured: 2 lanes 51.5 us per step,
+// 3 lanes (10 environments per warp, two lanes left over) 54.4 us, 4 lanes 61.5 us — the sweeps get shorter with more
+// lanes, but everything that is not a sweep (kinematics, forming the reflectors, the rref) is repeated by every warp
+// and the kernel pays for the warp-instructions it issues as well as for the length of one environment's chain.
+constexpr int FIX_LPE_WANTED = ATACOM_FIX_LPE;
+static_assert(FIX_LPE_WANTED >= 2 && FIX_LPE_WANTED <= 4, "lanes per environment of the fix-up kernel");
 
 // The lanes of a warp that share one environment in the fix-up kernel (Lapack::project, GRP).  The groups of a warp
 // synchronise TOGETHER, with the full mask: a group-sized mask makes the compiler wrap every __syncwarp in a
@@ -695,24 +699,44 @@ static_assert(FIX_LPE == 2 || FIX_LPE == 4, "lanes per environment of the fix-up
 struct WarpLanes {
   int s;
   __device__ __forceinline__ int sub() const { return s; }
+  __device__ __forceinline__ int write_lane() const { return s; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
 };
 
-template <class Env>
-struct FixCfg {
+// Block shape of the fix-up kernel for LPE lanes per environment.  A warp holds EPW = 32 / LPE environments (when 32
+// is not a multiple of LPE the lanes left over shadow the warp's first environment).
+// The [cell][column] array is padded to a stride = TARGET (mod 16) doubles, chosen so that the 16 threads of a
+// half-warp — lanes of one environment are 17 cells (rows) or 1 cell (columns) apart — hit 16 different pairs of banks.
+template <class Env, int LPE>
+struct FixShape {
   using LP = Lapack<double, typename Env::D>;
-  static constexpr size_t SMEM_MAX = 227 * 1024;
-  // environments per block: a multiple of 16; the [cell][environment] array is padded to a stride = 16 / LPE mod 16,
-  // so that the 16 threads of a half-warp — 16 / LPE environments x LPE lanes, the lanes on cells 17 (rows) or 1
-  // (columns) apart — hit 16 different pairs of banks
-  static constexpr int PAD = 16 / FIX_LPE;
-  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE)) - PAD;
-  static constexpr int ENVS = FIT >= 128 ? 128 : (FIT / 16) * 16;      // iiwa-6: 128, iiwa-7: 112 (LPE 4) / 96 (LPE 2)
-  static constexpr int STRIDE = ENVS + PAD;
-  static constexpr int TPB = ENVS * FIX_LPE;
-  static_assert(ENVS >= 16, "the LAPACK working arrays do not fit into shared memory");
+  static constexpr size_t SMEM_MAX = 225 * 1024;           // (2 KB short of the limit: the block's small static tables)
+  static constexpr int EPW = 32 / LPE;
+  static constexpr int CPW = EPW;                          // shared-memory columns per warp
+  static constexpr int TARGET = LPE == 2 ? 8 : LPE == 3 ? 11 : 4;
+  static constexpr int WARPS_WANTED = LPE == 2 ? 8 : LPE == 3 ? 10 : 16;
+  static constexpr int FIT = static_cast<int>(SMEM_MAX / (sizeof(double) * LP::SIZE));     // columns that fit
+  static constexpr int stride_for(int cols) { return cols + ((TARGET - cols % 16) + 16) % 16; }
+  static constexpr int warps_that_fit() {
+    int w = WARPS_WANTED;
+    while (w > 1 && stride_for(w * CPW) > FIT) --w;
+    return w;
+  }
+  static constexpr int WARPS = warps_that_fit();
+  static constexpr int ENVS = WARPS * EPW;                 // environments per block and round
+  static constexpr int STRIDE = stride_for(WARPS * CPW);
+  static constexpr int TPB = WARPS * 32;
   static constexpr size_t BYTES = sizeof(double) * LP::SIZE * STRIDE;
+  static constexpr bool FITS = STRIDE <= FIT;
+};
+// The wanted number of lanes if the block then still takes the ~92 environments per SM of the benchmark's mix in one
+// round, else 2 lanes (iiwa-7: 96 environments per block).
+template <class Env>
+struct FixCfg : FixShape<Env, (FixShape<Env, FIX_LPE_WANTED>::WARPS == FixShape<Env, FIX_LPE_WANTED>::WARPS_WANTED) ? FIX_LPE_WANTED : 2> {
+  static constexpr int LPE = (FixShape<Env, FIX_LPE_WANTED>::WARPS == FixShape<Env, FIX_LPE_WANTED>::WARPS_WANTED) ? FIX_LPE_WANTED : 2;
+  using SH = FixShape<Env, LPE>;
+  static_assert(SH::FITS && SH::ENVS >= 10, "the LAPACK working arrays do not fit into shared memory");
 };
 
 template <class Env>
@@ -726,16 +750,78 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
   extern __shared__ __align__(128) unsigned char atacom_smem[];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");      // the step kernel has completed: list, counts and its outputs are visible
-  const int cnt = a.fix_count[blockIdx.x];
-  const int32_t* seg = a.fix_list + static_cast<int64_t>(blockIdx.x) * a.seg_stride;
-  const int slot = threadIdx.x / FIX_LPE, sub = threadIdx.x % FIX_LPE;
+  // The step kernel's block b queued its deferred environments in segment b.  The segments differ in length (a
+  // binomial spread, 70..115 of 448 at the benchmark's mix) and the duration of this kernel is that of its fullest
+  // block, so the environments are dealt out evenly instead: the concatenation of all segments is cut into gridDim.x
+  // equal ranges.  Warp 0 sums the counts, then walks them once more and notes the segments that overlap this block's
+  // range [lo, hi) (a handful) in a small table; every slot then finds its environment there.
+  constexpr int TABN = FixCfg<Env>::ENVS + 2;
+  __shared__ int tab_seg[TABN], tab_beg[TABN];
+  __shared__ int tab_n, range_lo, range_hi;
+  const int nseg = static_cast<int>(gridDim.x);
+  if (threadIdx.x < 32) {
+    const int lane = static_cast<int>(threadIdx.x);
+    int sum = 0;
+    for (int b = lane; b < nseg; b += 32) sum += a.fix_count[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int per = (sum + nseg - 1) / nseg;
+    const int64_t lo64 = static_cast<int64_t>(blockIdx.x) * per;
+    const int lo = lo64 < sum ? static_cast<int>(lo64) : sum;
+    const int hi = lo + per < sum ? lo + per : sum;
+    int run = 0, ntab = 0;
+    for (int base = 0; base < nseg && run < hi; base += 32) {
+      const int c = base + lane < nseg ? a.fix_count[base + lane] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const int beg = run + incl - c;
+      const bool ov = c > 0 && beg < hi && beg + c > lo;
+      const unsigned m = __ballot_sync(0xffffffffu, ov);
+      if (ov) {
+        const int idx = ntab + __popc(m & ((1u << lane) - 1u));
+        if (idx < TABN) {
+          tab_seg[idx] = base + lane;
+          tab_beg[idx] = beg;
+        }
+      }
+      ntab += __popc(m);
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      tab_n = ntab < TABN ? ntab : TABN;
+      range_lo = lo;
+      range_hi = hi;
+    }
+  }
+  __syncthreads();
+  const int cnt = range_hi - range_lo;
+  constexpr int LPE = CFG::LPE;
+  const int warp = static_cast<int>(threadIdx.x >> 5), lane = static_cast<int>(threadIdx.x & 31u);
+  // lanes left over (32 is not a multiple of LPE) shadow the warp's first environment: same column, same loads, same
+  // decisions — and a lane number no row, column or vector is dealt to, so they never write
+  const bool spare = lane / LPE >= CFG::EPW;
+  const int grp_in_warp = spare ? 0 : lane / LPE, sub = spare ? 64 : lane % LPE;
+  const int slot = warp * CFG::EPW + grp_in_warp;
   PlainSharedStore<double, CFG::STRIDE> S{reinterpret_cast<double*>(atacom_smem) + slot};
   const bool ec = P.variant == VARIANT_EC;
-  const int warp_slot0 = static_cast<int>(threadIdx.x & ~31u) / FIX_LPE;      // first slot of this warp
+  const int warp_slot0 = warp * CFG::EPW;              // first slot of this warp
   for (int t0 = 0; t0 < cnt; t0 += CFG::ENVS) {
     if (t0 + warp_slot0 >= cnt) continue;              // (the whole warp)
-    const bool live = t0 + slot < cnt;                 // a slot past the end runs along on the last environment
-    const int64_t e = seg[live ? t0 + slot : cnt - 1];
+    const bool in_range = t0 + slot < cnt;             // a slot past the end runs along on the last environment
+    const bool live = !spare && in_range;
+    const int gi = range_lo + (in_range ? t0 + slot : cnt - 1);
+    int ts = tab_seg[0], tb = tab_beg[0];
+    for (int u = 1; u < tab_n; ++u) {
+      if (tab_beg[u] <= gi) {
+        ts = tab_seg[u];
+        tb = tab_beg[u];
+      }
+    }
+    const int64_t e = a.fix_list[static_cast<int64_t>(ts) * a.seg_stride + (gi - tb)];
     float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
     row_load<n>(a.q, e, q);
     row_load<n>(a.dq, e, dq);
@@ -752,10 +838,10 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
     const WarpLanes grp{sub};
 #if ATACOM_FIX_NULL_ONLY
     // the minimum-norm part is the step kernel's (basis-free); only the null part is redone here
-    const uint8_t st = step_lapack_null<Env, float, double, FIX_LPE>(P, Kd, S, q, dq, s, al, a.fix_wmn + e * N, ddq, so,
+    const uint8_t st = step_lapack_null<Env, float, double, LPE>(P, Kd, S, q, dq, s, al, a.fix_wmn + e * N, ddq, so,
                                                                      dbg, grp);
 #else
-    const uint8_t st = step_lapack<Env, float, double, FIX_LPE>(P, Kd, S, q, dq, s, al, ddq, so, dbg, grp);
+    const uint8_t st = step_lapack<Env, float, double, LPE>(P, Kd, S, q, dq, s, al, ddq, so, dbg, grp);
 #endif
     if (sub == 0 && live) {
       if (a.status) a.status[e] = st;

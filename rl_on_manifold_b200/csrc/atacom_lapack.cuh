@@ -25,6 +25,12 @@
 
 #include "atacom_core.cuh"
 
+#if defined(__CUDA_ARCH__) && ATACOM_LAPACK_SWEEP_UNROLL == 2
+#define ATACOM_SWEEP_LOOP _Pragma("unroll 2")
+#else
+#define ATACOM_SWEEP_LOOP ATACOM_ROLLED
+#endif
+
 namespace atacom {
 
 constexpr uint8_t ST_LAPACK_PATH = 32;   // the fast path left this environment to the LAPACK-basis routine
@@ -43,6 +49,7 @@ struct SoloGroup {
   ATACOM_HD int sub() const { return 0; }
   ATACOM_HD void sync() const {}
   ATACOM_HD bool all(bool p) const { return p; }      // true when p holds for every environment that syncs along
+  ATACOM_HD int write_lane() const { return 0; }      // which rows of Jc this lane fills in: i % LPE == write_lane(); < 0: all
 };
 
 template <typename R, class D>
@@ -50,6 +57,13 @@ struct Lapack {
   static constexpr int n = D::n, F = D::F, G = D::G, C = D::C, N = D::N, k = D::k;
   static constexpr int C1 = at_least_1<C>::value, K1 = at_least_1<k>::value;
   static constexpr bool LQ_PATH = N >= (C * 11) / 6;            // gesdd: MNTHR = int(minmn * 11 / 6)
+#ifndef ATACOM_LAPACK_NACC
+#define ATACOM_LAPACK_NACC 2      // (4 measured equal: 52.1 against 52.0 us per step)
+#endif
+#ifndef ATACOM_LAPACK_SWEEP_UNROLL
+#define ATACOM_LAPACK_SWEEP_UNROLL 1
+#endif
+  static constexpr int NACC = ATACOM_LAPACK_NACC;               // partial sums per dot product
   // Z (N x k) lives in dead cells of the C x N array when the shape allows it (see zcell), else behind it
   static constexpr bool Z_OVERLAY = (C >= 2 * k - 1) && (N >= 2 * k) && (k > 0);
   // w_null is produced column by column at run-time indices: N more cells, in columns k and k + 1 of the array (dead
@@ -162,15 +176,18 @@ struct Lapack {
     for (int i = 0; i < C; ++i) {
       Grp.sync();                                  // row i is final: the previous reflectors have been applied to it
       R v[N];                                      // row i right of the diagonal, then the reflector vector
-      R xn2 = R(0), xn2b = R(0);
+      R xs[NACC];                                  // NACC partial sums: the dependent chains are what bounds a warp here
+      ATACOM_UNROLL
+      for (int t = 0; t < NACC; ++t) xs[t] = R(0);
       const R x0 = S.get(a(i, i));
       ATACOM_UNROLL
       for (int j = i + 1; j < N; ++j) {
         v[j] = S.get(a(i, j));
-        if ((j - i) & 1) xn2 += v[j] * v[j];
-        else xn2b += v[j] * v[j];
+        xs[(j - i - 1) % NACC] += v[j] * v[j];
       }
-      xn2 += xn2b;
+      R xn2 = xs[0];
+      ATACOM_UNROLL
+      for (int t = 1; t < NACC; ++t) xn2 += xs[t];
       R beta, tau, sc;
       larfg(x0, xn2, &beta, &tau, &sc);
       {
@@ -187,18 +204,20 @@ struct Lapack {
         for (int j = i + 1; j < N; ++j) S.set(a(i, j), v[j]);
       }
       {
-        ATACOM_ROLLED
+        ATACOM_SWEEP_LOOP
         for (int l = i + 1 + sub; l < C; l += LPE) {      // rows below: A <- A G_i, one load and one store per entry
           R row[N];
           ATACOM_UNROLL
           for (int j = i; j < N; ++j) row[j] = S.get(a(l, j));
-          R w0 = row[i], w1 = R(0);
+          R ws[NACC];
           ATACOM_UNROLL
-          for (int j = i + 1; j < N; ++j) {
-            if ((j - i) & 1) w1 += row[j] * v[j];
-            else w0 += row[j] * v[j];
-          }
-          const R w = (w0 + w1) * tau;
+          for (int t = 0; t < NACC; ++t) ws[t] = (t == 0) ? row[i] : R(0);
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) ws[(j - i) % NACC] += row[j] * v[j];
+          R wsum = ws[0];
+          ATACOM_UNROLL
+          for (int t = 1; t < NACC; ++t) wsum += ws[t];
+          const R w = wsum * tau;
           S.set(a(l, i), row[i] - w);
           ATACOM_UNROLL
           for (int j = i + 1; j < N; ++j) S.set(a(l, j), row[j] - w * v[j]);
@@ -207,31 +226,38 @@ struct Lapack {
       if (!LQ_PATH && i + 1 < C) {
         Grp.sync();                                // column i is final
         R u[C1];                                   // column i below the subdiagonal, then the reflector vector
-        R un2 = R(0);
+        R us[NACC];
+        ATACOM_UNROLL
+        for (int t = 0; t < NACC; ++t) us[t] = R(0);
         const R c0 = S.get(a(i + 1 < C ? i + 1 : 0, i));
         ATACOM_UNROLL
         for (int l = i + 2; l < C; ++l) {
           u[l] = S.get(a(l, i));
-          un2 += u[l] * u[l];
+          us[(l - i) % NACC] += u[l] * u[l];
         }
+        R un2 = us[0];
+        ATACOM_UNROLL
+        for (int t = 1; t < NACC; ++t) un2 += us[t];
         R betaq, tauq, scq;
         larfg(c0, un2, &betaq, &tauq, &scq);
         if (WITH_MN && sub == 0) S.set(a(i + 1 < C ? i + 1 : 0, i), betaq);     // (u itself is not needed again: it is applied to r here)
         {
           ATACOM_UNROLL
           for (int l = i + 2; l < C; ++l) u[l] *= scq;
-          ATACOM_ROLLED
+          ATACOM_SWEEP_LOOP
           for (int j = i + 1 + sub; j < N; j += LPE) {    // columns to the right: A <- H_i A
             R col[C1];
             ATACOM_UNROLL
             for (int l = i + 1; l < C; ++l) col[l] = S.get(a(l, j));
-            R w0 = col[i + 1 < C ? i + 1 : 0], w1 = R(0);
+            R ws[NACC];
             ATACOM_UNROLL
-            for (int l = i + 2; l < C; ++l) {
-              if ((l - i) & 1) w1 += col[l] * u[l];
-              else w0 += col[l] * u[l];
-            }
-            const R w = (w0 + w1) * tauq;
+            for (int t = 0; t < NACC; ++t) ws[t] = (t == 0) ? col[i + 1 < C ? i + 1 : 0] : R(0);
+            ATACOM_UNROLL
+            for (int l = i + 2; l < C; ++l) ws[(l - i - 1) % NACC] += col[l] * u[l];
+            R wsum = ws[0];
+            ATACOM_UNROLL
+            for (int t = 1; t < NACC; ++t) wsum += ws[t];
+            const R w = wsum * tauq;
             S.set(a(i + 1 < C ? i + 1 : 0, j), col[i + 1 < C ? i + 1 : 0] - w);
             ATACOM_UNROLL
             for (int l = i + 2; l < C; ++l) S.set(a(l, j), col[l] - w * u[l]);
@@ -302,10 +328,13 @@ struct Lapack {
       const R taui = WITH_MN ? tau_s[WITH_MN ? i : 0] : S.get(a(i, i));
       ATACOM_UNROLL
       for (int cc = 0; cc < CPL; ++cc) {
-        R w = X[cc][i];
+        R wa = X[cc][i], wb = R(0);
         ATACOM_UNROLL
-        for (int j = i + 1; j < N; ++j) w += vi[j] * X[cc][j];
-        w *= taui;
+        for (int j = i + 1; j < N; ++j) {
+          if ((j - i) & 1) wb += vi[j] * X[cc][j];
+          else wa += vi[j] * X[cc][j];
+        }
+        R w = (wa + wb) * taui;
         X[cc][i] -= w;
         ATACOM_UNROLL
         for (int j = i + 1; j < N; ++j) X[cc][j] -= w * vi[j];
@@ -332,98 +361,104 @@ struct Lapack {
     // walks the columns; the pivot candidate is the first largest |.| among the rows not used yet; <= tol: zero those
     // entries and move on; else swap, scale the pivot row, eliminate the column from every other row.  All of that are
     // row operations, so the current column j is E z_j — z_j the ORIGINAL column (row j of Z), E the k x k product of
-    // the row operations so far — and the matrix itself is never rewritten: a pivot step is a rank-one update of E
-    // (25 fused multiply-adds for k = 5 against an elimination sweep over every remaining column in shared memory).
-    // What the finished matrix holds in column j: the unit vector of its pivot row (a pivot column); its state when
-    // it was dropped, the rows not yet used zeroed (later operations only combine rows that are zero there);
-    // E_final z_j for the columns behind the last pivot.  w_null[j] = sum_l alpha_l R[l][j] follows column by
-    // column.  Rows are tracked physically: `pos[i]` is the position the reference's swaps have given row i (it
-    // decides which of two equal candidates is "first"), `coef[i]` the alpha of the pivot the row carries (0: unused).
-    // Every lane of a group runs this redundantly — no shared-memory writes but its own results, no synchronisation.
-    R E[K1][K1], coef[K1];
-    int pos[K1];
+    // the row operations so far — and the matrix itself is never rewritten: a pivot step updates E alone (k x k
+    // against an elimination sweep over every remaining column in shared memory).  What the finished matrix holds in
+    // column j: the unit vector of its pivot row (a pivot column); its state when it was dropped, the rows not yet
+    // used zeroed (later operations only combine rows that are zero there); E_final z_j for the columns behind the
+    // last pivot.  So w_null[j] = sum_l alpha_l R[l][j] is alpha_r for the r-th pivot column and g . z_j otherwise,
+    // g = sum over the rows used so far of alpha_l E[l].
+    // One stage per pivot, unrolled: in stage r only the rows r.. are candidates, so a column costs (k - r) dot
+    // products, and the stages that walk through many dropped columns (the last pivot of an environment with an
+    // active constraint is a slack column) are the cheap ones.  Every lane of a group runs this redundantly — no
+    // shared-memory writes but its own results, no synchronisation.
+    R E[K1][K1], g[K1];
     ATACOM_UNROLL
     for (int i = 0; i < k; ++i) {
       ATACOM_UNROLL
       for (int m = 0; m < k; ++m) E[i][m] = (i == m) ? R(1) : R(0);
-      coef[i] = R(0);
-      pos[i] = i;
+      g[i] = R(0);
     }
-    unsigned used = 0u;
-    int rr = 0, j = 0;
-    ATACOM_ROLLED
-    for (; j < N && rr < k; ++j) {
-      R z[K1], c[K1];
-      ATACOM_UNROLL
-      for (int m = 0; m < k; ++m) z[m] = S.get(zcell(j, m));
-      ATACOM_UNROLL
-      for (int i = 0; i < k; ++i) {
-        R acc = E[i][0] * z[0];
-        ATACOM_UNROLL
-        for (int m = 1; m < k; ++m) acc += E[i][m] * z[m];
-        c[i] = acc;
-      }
-      R p = R(-1), piv = R(1), wdrop = R(0);
-      int pk = 0, ppos = k;
-      ATACOM_UNROLL
-      for (int i = 0; i < k; ++i) {
-        const bool un = ((used >> i) & 1u) == 0u;
-        const R av = num<R>::abs(c[i]);
-        const bool better = un && (av > p || (av == p && pos[i] < ppos));
-        p = better ? av : p;
-        piv = better ? c[i] : piv;
-        pk = better ? i : pk;
-        ppos = better ? pos[i] : ppos;
-        wdrop += coef[i] * c[i];                   // (what a dropped column keeps: the rows used so far)
-      }
-      const bool pivot = p > tol;
-      status |= pivot ? (j >= n ? ST_SLACK_PIVOT : 0) : ST_COLUMN_DROPPED;
-      R arr = R(0);                                // alpha of this pivot
-      ATACOM_UNROLL
-      for (int l = 0; l < k; ++l) arr = (l == rr) ? alpha[l] : arr;
-      S.set(wcell(j), pivot ? arr : wdrop);
-      // pivot: row pk becomes E[pk] / piv and every other row i loses c_i times that — for all rows at once
-      // E -= d (x) prow with d_i = c_i - [i == pk]; no pivot: d = 0, nothing changes
-      const R inv = pivot ? rcp(piv) : R(0);
-      R prow[K1], d[K1];
-      ATACOM_UNROLL
-      for (int m = 0; m < k; ++m) {
-        R e = E[0][m];
-        ATACOM_UNROLL
-        for (int i = 1; i < k; ++i) e = (i == pk) ? E[i][m] : e;
-        prow[m] = e * inv;
-      }
-      ATACOM_UNROLL
-      for (int i = 0; i < k; ++i) {
-        d[i] = pivot ? ((i == pk) ? c[i] - R(1) : c[i]) : R(0);
-        ATACOM_UNROLL
-        for (int m = 0; m < k; ++m) E[i][m] -= d[i] * prow[m];
-        // the swap: the row that sat at position rr takes the pivot row's old position
-        const bool un = ((used >> i) & 1u) == 0u;
-        if (pivot && un && pos[i] == rr) pos[i] = ppos;
-        if (pivot && i == pk) {
-          pos[i] = rr;
-          coef[i] = arr;
-        }
-      }
-      used |= pivot ? (1u << pk) : 0u;
-      rr += pivot ? 1 : 0;
-    }
-    if (rr < k) status |= ST_RANK_DEFICIENT;
-    // columns behind the last pivot: w_null[j] = sum_i coef_i (E z_j)_i = g . z_j
-    R g[K1];
+    int j = 0;
     ATACOM_UNROLL
-    for (int m = 0; m < k; ++m) {
-      R acc = R(0);
-      ATACOM_UNROLL
-      for (int i = 0; i < k; ++i) acc += coef[i] * E[i][m];
-      g[m] = acc;
+    for (int rr = 0; rr < k; ++rr) {
+      bool found = false;
+      ATACOM_ROLLED
+      while (j < N && !found) {
+        R z[K1], c[K1];
+        ATACOM_UNROLL
+        for (int m = 0; m < k; ++m) z[m] = S.get(zcell(j, m));
+        R gz = g[0] * z[0];
+        ATACOM_UNROLL
+        for (int m = 1; m < k; ++m) gz += g[m] * z[m];
+        R p = R(-1);
+        int kk = rr;
+        ATACOM_UNROLL
+        for (int i = rr; i < k; ++i) {
+          R acc = E[i][0] * z[0];
+          ATACOM_UNROLL
+          for (int m = 1; m < k; ++m) acc += E[i][m] * z[m];
+          c[i] = acc;
+          const R av = num<R>::abs(acc);
+          if (av > p) {                            // (strict: the first of equal candidates, as np.argmax)
+            p = av;
+            kk = i;
+          }
+        }
+        if (p > tol) {
+          found = true;
+          if (j >= n) status |= ST_SLACK_PIVOT;
+          S.set(wcell(j), alpha[rr]);
+          // rows rr and kk change places; the pivot row is scaled
+          R ckk = c[rr];
+          ATACOM_UNROLL
+          for (int i = rr + 1; i < k; ++i) {
+            const R ci = c[i];
+            c[i] = (i == kk) ? c[rr] : ci;
+            ckk = (i == kk) ? ci : ckk;
+          }
+          const R inv = rcp(ckk);
+          ATACOM_UNROLL
+          for (int m = 0; m < k; ++m) {
+            R e = E[rr][m];
+            ATACOM_UNROLL
+            for (int i = rr + 1; i < k; ++i) {
+              const R ei = E[i][m];
+              E[i][m] = (i == kk) ? E[rr][m] : ei;
+              e = (i == kk) ? ei : e;
+            }
+            E[rr][m] = e * inv;
+          }
+          // ... and is eliminated from the rows still to come and from the rows used before
+          ATACOM_UNROLL
+          for (int i = 0; i < k; ++i) {
+            if (i == rr) continue;
+            R ci;
+            if (i > rr) {
+              ci = c[i];
+            } else {
+              ci = E[i][0] * z[0];
+              ATACOM_UNROLL
+              for (int m = 1; m < k; ++m) ci += E[i][m] * z[m];
+            }
+            ATACOM_UNROLL
+            for (int m = 0; m < k; ++m) E[i][m] -= ci * E[rr][m];
+          }
+          const R dg = alpha[rr] - gz;             // g = sum_{l <= rr} alpha_l E[l] of the updated rows
+          ATACOM_UNROLL
+          for (int m = 0; m < k; ++m) g[m] += dg * E[rr][m];
+        } else {
+          status |= ST_COLUMN_DROPPED;
+          S.set(wcell(j), gz);
+        }
+        ++j;
+      }
+      if (!found) status |= ST_RANK_DEFICIENT;     // (ran out of columns: the later stages find j == N)
     }
     ATACOM_UNROLL
     for (int jj = 0; jj < N; ++jj) {
       if (jj < j) {
         w_null[jj] = S.get(wcell(jj));
-      } else {
+      } else {                                     // behind the last pivot
         R acc = R(0);
         ATACOM_UNROLL
         for (int m = 0; m < k; ++m) acc += g[m] * S.get(zcell(jj, m));
