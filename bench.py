@@ -529,9 +529,11 @@ def ours(args):
         return statistics.median(max_over_ranks(reps))
 
     e2e_staged_ms = time_e2e("staged")
-    e2e_auto_ms = e2e_staged_ms if wl == "point_reach" else time_e2e("auto")
-    e2e_api = ("atacom_%s_step_host, pinned host buffers, " % wl) + (
-        "staged copies (CUDA graph of H2D, kernel, D2H per chunk)" if wl == "point_reach" else
+    e2e_zero_copy_ms = None if wl == "point_reach" else time_e2e("zero_copy")
+    auto_path = "staged" if wl == "point_reach" else projection.HostContext.auto_path(fam, params, N_JOINTS)
+    e2e_auto_ms = e2e_staged_ms if auto_path == "staged" else e2e_zero_copy_ms
+    e2e_api = ("atacom_%s_step_host, pinned host buffers, mode auto = " % wl) + (
+        "staged copies (CUDA graph of H2D, kernels, D2H per chunk)" if auto_path == "staged" else
         "zero-copy (kernel loads/stores cross PCIe via cp.async.bulk)")
 
     clocks = sampler.stop() if rank == 0 else None
@@ -582,6 +584,7 @@ def ours(args):
             e2e=dict(value=world * B * K / (e2e_auto_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * bytes_in,
                      d2h_bytes_per_step=B * bytes_out, api=e2e_api,
                      staged_value=world * B * K / (e2e_staged_ms * 1e-3), staged_chunks=args.chunks,
+                     zero_copy_value=(world * B * K / (e2e_zero_copy_ms * 1e-3)) if e2e_zero_copy_ms else None,
                      timing="median of 5 repeats of %d calls, wall clock around the calls, max over ranks" % K),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

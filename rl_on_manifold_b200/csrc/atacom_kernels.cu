@@ -2008,6 +2008,10 @@ struct HostCall {
   // zero-copy launch (one kernel on the mapped aliases of the caller's buffers), or null when the family has none
   int (*zero_copy)(const HostCall& c, void* const* din, void* const* dout, int64_t B, const AtacomParams* p,
                    struct AtacomHostCtx* ctx);
+  // the step takes two launches (ATACOM_BASIS_LAPACK: step kernel + fix-up): the second one reads the rows of the
+  // deferred environments again, over PCIe when the arrays are the caller's — AUTO then stages (measured: 208 against
+  // 177 M env-steps/s at 65 536 IiwaAirHockey-7H environments); ATACOM_HOST_ZERO_COPY still forces the one-copy path
+  bool two_pass;
 };
 
 struct AtacomHostCtx {
@@ -2109,7 +2113,7 @@ static int host_call(AtacomHostCtx* c, const HostCall& call, int64_t B, const At
     for (int i = 0; i < call.n_out && all; ++i)
       if (call.out[i].h) all = (zout[i] = mapped_alias(call.out[i].h)) != nullptr;
     if (!all && c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
-    if (all) {
+    if (all && !(c->mode == ATACOM_HOST_AUTO && call.two_pass)) {
       rc = call.zero_copy(call, zin, zout, B, p, c);
       if (rc != ATACOM_OK) return rc;
       if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
@@ -2225,6 +2229,7 @@ static int step_host(AtacomHostCtx* c, int family_id, const float* q, const floa
   call.key[2] = c->mode;
   call.n_in = 4;
   call.n_out = 3;
+  call.two_pass = p->basis_mode == ATACOM_BASIS_LAPACK && p->variant == ATACOM_VARIANT_ATACOM && D::k > 1;
   call.in[0] = {q, sizeof(float) * D::n};
   call.in[1] = {dq, sizeof(float) * D::n};
   call.in[2] = {D::G > 0 ? s_in : nullptr, sizeof(float) * D::G};
