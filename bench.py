@@ -534,7 +534,8 @@ def ours(args):
     e2e_auto_ms = e2e_staged_ms if auto_path == "staged" else e2e_zero_copy_ms
     e2e_api = ("atacom_%s_step_host, pinned host buffers, mode auto = " % wl) + (
         "staged copies (CUDA graph of H2D, kernels, D2H per chunk)" if auto_path == "staged" else
-        "zero-copy (kernel loads/stores cross PCIe via cp.async.bulk)")
+        "zero-copy (one launch on the caller's buffers, loads/stores cross PCIe via cp.async.bulk; with the LAPACK "
+        "basis both passes run inside that launch)")
 
     clocks = sampler.stop() if rank == 0 else None
     timeouts = _lib.spin_timeouts()

@@ -1,3 +1,6 @@
+"""End-to-end diagnosis on one box: PCIe copy bandwidth, then the host-buffer entry point in every data path, with the
+reference-exact null basis (two launches per step) and the canonical one (a single launch) side by side.
+    python profiles/e2e_diag.py > gpurun_out/e2e_diag.txt"""
 import os, sys, time, torch, subprocess
 sys.path.insert(0, os.getcwd())
 from rl_on_manifold_b200 import _lib, projection, synthetic
@@ -19,15 +22,21 @@ print("D2H 64MB: %.1f GB/s (%.0f us)" % bw(lambda: big_h.copy_(big_d, non_blocki
 sm_h = big_h[:1 << 20]; sm_d = big_d[:1 << 20]
 print("H2D 1MB: %.1f GB/s (%.0f us)" % bw(lambda: sm_d.copy_(sm_h, non_blocking=True), 1 << 20, 100))
 print("D2H 1MB: %.1f GB/s (%.0f us)" % bw(lambda: sm_h.copy_(sm_d, non_blocking=True), 1 << 20, 100))
-for mode, chunks in (("staged", 2), ("zero_copy", 1), ("hybrid", 1), ("hybrid", 2), ("hybrid", 3), ("hybrid", 4),
-                     ("hybrid", 8)):
-    ctx = projection.HostContext(B, chunks=chunks, mode=mode)
-    f = lambda: ctx.iiwa_step(6, *host, ddq_h, s_h, p)
-    for _ in range(5): f()
-    t0 = time.perf_counter()
-    for _ in range(50): f()
-    dt = (time.perf_counter() - t0) / 50
-    print("%s chunks %2d: %.0f us/step -> %.1f M env-steps/s" % (mode, chunks, dt * 1e6, B / dt / 1e6))
-    ctx.close()
+for basis, name in ((_lib.BASIS_LAPACK, "lapack (two launches)"), (_lib.BASIS_CANONICAL, "canonical (one launch)")):
+    p.basis_mode = basis
+    for mode, chunks in (("zero_copy", 1), ("staged", 1), ("staged", 2), ("staged", 4), ("hybrid", 1), ("hybrid", 2)):
+        ctx = projection.HostContext(B, chunks=chunks, mode=mode)
+        f = lambda: ctx.iiwa_step(6, *host, ddq_h, s_h, p)
+        for _ in range(5): f()
+        best = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter()
+            for _ in range(50): f()
+            best = min(best, (time.perf_counter() - t0) / 50)
+        print("%-24s %-9s chunks %d: %.0f us/step -> %.1f M env-steps/s" % (name, mode, chunks, best * 1e6, B / best / 1e6))
+        ctx.close()
+p.basis_mode = _lib.BASIS_LAPACK
+ctx = projection.HostContext(B, chunks=1, mode="zero_copy")
+ctx.iiwa_step(6, *host, ddq_h, s_h, p)
 ref = projection.step("iiwa", q, dq, s, alpha, p)
 print("zero-copy == device path:", torch.equal(ddq_h, ref[0].cpu()), torch.equal(s_h, ref[1].cpu()))

@@ -150,6 +150,13 @@ struct StepArgs {
   // ... and their minimum-norm parts ([B, N] doubles, written for the deferred environments only): the same for every
   // null basis, so the fix-up kernel redoes the null part alone
   double* fix_wmn;
+  // zero-copy launch on the caller's (mapped host) arrays in that mode: every thread also writes the input rows it has
+  // just fetched over PCIe to these device arrays, and the fix-up kernel reads the deferred environments' rows from
+  // there instead of crossing PCIe a second time.  Null: no mirror (the arrays are in HBM already).
+  float* mirror_q;
+  float* mirror_dq;
+  float* mirror_s;
+  float* mirror_alpha;      // [B, k]
 };
 
 // ------------------------------------------------------------------ row access
@@ -412,6 +419,12 @@ __global__ void __maxnreg__(ATACOM_STEP_MAXNREG) atacom_step_kernel(const __grid
     }
   }
 
+  if (BAND && IO == 1 && a.mirror_q != nullptr && valid) {      // (see StepArgs: rows for the fix-up kernel)
+    row_store<n>(a.mirror_q, e, q);
+    row_store<n>(a.mirror_dq, e, dq);
+    if (G > 0) row_store<G1>(a.mirror_s, e, s);
+    if (k > 0) row_store<K1>(a.mirror_alpha, e, al);
+  }
   float* dbg = (a.w_dbg && valid) ? a.w_dbg + e * (2 * N) : nullptr;
 #if ATACOM_STEP_DUAL
   using DU = Dual<double, D, Env::NDIAG>;
@@ -852,6 +865,244 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
     __syncwarp();          // the next round reuses the group's array
   }
 }
+
+// ------------------------------------------------------------------ zero-copy step, both passes in one launch
+// The host-buffer entry points on page-locked arrays (ATACOM_HOST_ZERO_COPY) with the reference-exact null basis.  Run
+// as the two launches above on mapped host memory, the fix-up kernel writes its 20 % of the rows back one by one — 24
+// and 44 byte stores across PCIe — and costs 140 us instead of 30 (324 against 185 us per 65 536-environment step).
+// Here a block of 128 threads takes 128 environments through BOTH passes: bulk loads into shared memory in ticket
+// order (the admission window of the step kernel), the dual path for every environment, then the LAPACK-basis routine
+// for the ones it deferred — their inputs are still in the staging area, their minimum-norm parts next to it — and
+// only then the output slabs leave, whole, through the bulk-copy engine.  No list, no scratch in global memory, no
+// second trip over PCIe.  The launch is PCIe-bound; two such blocks fit an SM (iiwa-6).
+struct ZcArgs {
+  const float* q;
+  const float* dq;
+  const float* s_in;
+  const float* alpha;
+  float* ddq;
+  float* s_out;
+  uint8_t* status;
+  int64_t B;
+  int32_t aligned16;
+  int32_t gate_window;
+  uint32_t* gate;           // { warps loaded, warps finished, next block ticket }, zero between launches
+};
+
+template <class Env>
+struct ZcFused {
+  using D = typename Env::D;
+  using SC = StepScratch<Env>;
+  using LP = Lapack<double, D>;
+  static constexpr int TPB = 128, WARPS = TPB / 32, LPE = 2;
+  static constexpr int SLOTS = 32;                      // deferred environments per round: warps 0 and 1, 2 lanes each
+  static constexpr int STRIDE = SLOTS + 8;              // = 8 (mod 16): see FixShape
+  static constexpr int NA = D::k;
+  static constexpr size_t align128(size_t x) { return (x + 127) / 128 * 128; }
+  static constexpr size_t IN_WARP = align128(sizeof(float) * 32 * (2 * D::n + D::G + NA));
+  static constexpr size_t OUT_WARP = align128(sizeof(float) * 32 * (D::n + D::G));
+  static constexpr size_t HEAD = 128 + align128(sizeof(int32_t) * TPB);       // ticket, count, 4 mbarriers; the list
+  static constexpr size_t IN_OFF = HEAD;
+  static constexpr size_t OUT_OFF = IN_OFF + IN_WARP * WARPS;
+  static constexpr size_t ST_OFF = OUT_OFF + OUT_WARP * WARPS;
+  static constexpr size_t WMN_OFF = ST_OFF + 128;
+  static constexpr size_t WORK_OFF = WMN_OFF + align128(sizeof(double) * TPB * D::N);
+  static constexpr size_t WORK_DUAL = SC::WARP_BYTES * WARPS;
+  static constexpr size_t WORK_LAPACK = sizeof(double) * LP::SIZE * STRIDE;
+  static constexpr size_t BYTES = WORK_OFF + (WORK_DUAL > WORK_LAPACK ? WORK_DUAL : WORK_LAPACK);
+  static_assert(BYTES <= 227 * 1024, "fused zero-copy block does not fit into shared memory");
+};
+
+template <class Env>
+__global__ void __launch_bounds__(ZcFused<Env>::TPB) atacom_zc_fused_kernel(const __grid_constant__ ZcArgs a,
+                                                                           const __grid_constant__ ParamsT<float> P,
+                                                                           const __grid_constant__ DualConsts<double> Kd) {
+  using D = typename Env::D;
+  using Z = ZcFused<Env>;
+  using SC = StepScratch<Env>;
+  constexpr int n = D::n, G = D::G, k = D::k, N = D::N;
+  constexpr int G1 = at_least_1<G>::value, K1 = at_least_1<k>::value;
+  extern __shared__ __align__(128) unsigned char atacom_smem[];
+  volatile uint32_t* tk = reinterpret_cast<volatile uint32_t*>(atacom_smem);
+  uint32_t* fixn = reinterpret_cast<uint32_t*>(atacom_smem + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(atacom_smem + 64);
+  int32_t* list = reinterpret_cast<int32_t*>(atacom_smem + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool gated = a.gate != nullptr;
+  if (threadIdx.x == 0) {
+    *fixn = 0u;
+    *tk = gated ? atomicAdd(a.gate + 2, 1u) : blockIdx.x;
+  }
+  __syncthreads();
+  const unsigned bid = *tk;
+  const int64_t e_raw = static_cast<int64_t>(bid) * Z::TPB + threadIdx.x;
+  const bool valid = e_raw < a.B;
+  const int64_t e = valid ? e_raw : a.B - 1;
+  const int64_t wenv0 = e_raw - lane;
+  float* sq = reinterpret_cast<float*>(atacom_smem + Z::IN_OFF + warp * Z::IN_WARP);
+  float* sdq = sq + 32 * n;
+  float* ss = sdq + 32 * n;
+  float* sa = ss + 32 * G;
+  float* oq = reinterpret_cast<float*>(atacom_smem + Z::OUT_OFF + warp * Z::OUT_WARP);
+  float* os = oq + 32 * n;
+  uint8_t* ost = atacom_smem + Z::ST_OFF;
+  double* wmn = reinterpret_cast<double*>(atacom_smem + Z::WMN_OFF);
+  const bool bulk = a.aligned16 && (wenv0 + 32 <= a.B);
+
+  // ---- inputs: the warp's four slabs, admitted in ticket order (see atacom_step_kernel)
+  float q[n], dq[n], s[G1], al[n], ddq[n], so[G1];
+  if (bulk) {
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+      if (gated) {
+        const unsigned order = bid * Z::WARPS + static_cast<unsigned>(warp);
+        const unsigned window = static_cast<unsigned>(a.gate_window);
+        if (order >= window) {
+          unsigned seen;
+          const long long t0 = clock64();
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gate) : "memory");
+            if (seen + window > order) break;
+            if (clock64() - t0 > ATACOM_SPIN_BUDGET) {   // watchdog: load unrationed rather than hang
+              atomicAdd(&g_spin_timeouts, 1u);
+              break;
+            }
+            __nanosleep(64);
+          }
+        }
+      }
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, 4u * 32u * static_cast<uint32_t>(2 * n + G + k));
+      bulk_g2s(sq, a.q + wenv0 * n, 128u * n, bar);
+      bulk_g2s(sdq, a.dq + wenv0 * n, 128u * n, bar);
+      if (G > 0) bulk_g2s(ss, a.s_in + wenv0 * G, 128u * G, bar);
+      if (k > 0) bulk_g2s(sa, a.alpha + wenv0 * k, 128u * static_cast<uint32_t>(k), bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (gated && lane == 0) atomicAdd(a.gate, 1u);     // this warp's inputs have landed: admit the next one
+  } else {
+    if (gated && lane == 0) atomicAdd(a.gate, 1u);     // direct loads (tail, unaligned views) are not rationed
+    float ak[K1];
+    row_load<n>(a.q, e, q);
+    row_load<n>(a.dq, e, dq);
+    if (G > 0) row_load<G1>(a.s_in, e, s);
+    if (k > 0) row_load<K1>(a.alpha, e, ak);
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      sq[lane * n + j] = q[j];
+      sdq[lane * n + j] = dq[j];
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) ss[lane * G1 + i] = s[i];
+#pragma unroll
+    for (int j = 0; j < k; ++j) sa[lane * k + j] = ak[j];
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    q[j] = sq[lane * n + j];
+    dq[j] = sdq[lane * n + j];
+    al[j] = j < k ? sa[lane * k + (j < k ? j : 0)] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) s[i] = ss[lane * G1 + i];
+
+  // ---- first pass: the dual path; a deferred environment leaves its minimum-norm part in wmn[thread]
+  {
+    unsigned char* region = atacom_smem + Z::WORK_OFF + warp * SC::WARP_BYTES;
+    typename SC::YS Ys = SC::y(region, lane);
+    typename SC::LS Ls = SC::l(region, lane);
+    auto fetch = [&](float* s_row, float* a_row) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) s_row[i] = s[i];
+#pragma unroll
+      for (int j = 0; j < n; ++j) a_row[j] = al[j];
+    };
+    const uint8_t st = step_dual_lazy<Env, float, double, true>(P, Kd, Ys, Ls, q, dq, fetch, ddq, so, nullptr, nullptr, 1, 0,
+                                                                WmnRow<double>{wmn + threadIdx.x * N});
+    if (st & ST_LAPACK_PATH) {
+      if (valid) list[atomicAdd(fixn, 1u)] = static_cast<int32_t>(threadIdx.x);
+    } else {
+#pragma unroll
+      for (int j = 0; j < n; ++j) oq[lane * n + j] = ddq[j];
+#pragma unroll
+      for (int i = 0; i < G; ++i) os[lane * G1 + i] = so[i];
+      ost[threadIdx.x] = st;
+    }
+  }
+  __syncthreads();     // every environment of the block is done or queued; the dual path's scratch is free
+
+  // ---- second pass: the null part of the queued environments with the LAPACK basis, 2 lanes each, warps 0 and 1
+  const int cnt = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(fixn));
+  if (warp < 2 * Z::SLOTS / 32) {
+    const int slot = static_cast<int>(threadIdx.x) / Z::LPE, sub = static_cast<int>(threadIdx.x) % Z::LPE;
+    PlainSharedStore<double, Z::STRIDE> S{reinterpret_cast<double*>(atacom_smem + Z::WORK_OFF) + slot};
+    const int warp_slot0 = warp * (32 / Z::LPE);
+    for (int t0 = 0; t0 < cnt; t0 += Z::SLOTS) {
+      if (t0 + warp_slot0 >= cnt) continue;            // (the whole warp)
+      const bool in_range = t0 + slot < cnt;           // a slot past the end runs along on the last environment
+      const int t = list[in_range ? t0 + slot : cnt - 1];
+      const int tw = t >> 5, tl = t & 31;
+      const float* iq = reinterpret_cast<const float*>(atacom_smem + Z::IN_OFF + tw * Z::IN_WARP);
+      const float* idq = iq + 32 * n;
+      const float* is = idq + 32 * n;
+      const float* ia = is + 32 * G;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        q[j] = iq[tl * n + j];
+        dq[j] = idq[tl * n + j];
+        al[j] = j < k ? ia[tl * k + (j < k ? j : 0)] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < G; ++i) s[i] = is[tl * G1 + i];
+      const WarpLanes grp{sub};
+      const uint8_t st = step_lapack_null<Env, float, double, Z::LPE>(P, Kd, S, q, dq, s, al, wmn + t * N, ddq, so, nullptr,
+                                                                      grp);
+      if (sub == 0 && in_range) {
+        float* tq = reinterpret_cast<float*>(atacom_smem + Z::OUT_OFF + tw * Z::OUT_WARP);
+        float* ts = tq + 32 * n;
+#pragma unroll
+        for (int j = 0; j < n; ++j) tq[tl * n + j] = ddq[j];
+#pragma unroll
+        for (int i = 0; i < G; ++i) ts[tl * G1 + i] = so[i];
+        ost[t] = st;
+      }
+      __syncwarp();        // the next round reuses the group's array
+    }
+  }
+  __syncthreads();
+
+  // ---- outputs: whole slabs through the bulk-copy engine (rows of the tail / unaligned views one by one)
+  if (bulk) {
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (a.ddq) bulk_s2g(a.ddq + wenv0 * n, oq, 128u * n);
+      if (G > 0) bulk_s2g(a.s_out + wenv0 * G, os, 128u * G);
+      if (a.status) bulk_s2g(a.status + wenv0, ost + warp * 32, 32u);
+      bulk_commit_wait_read();
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int j = 0; j < n; ++j) ddq[j] = oq[lane * n + j];
+#pragma unroll
+    for (int i = 0; i < G; ++i) so[i] = os[lane * G1 + i];
+    if (a.ddq) row_store<n>(a.ddq, e, ddq);
+    if (G > 0) row_store<G1>(a.s_out, e, so);
+    if (a.status) a.status[e] = ost[threadIdx.x];
+  }
+  // ordered admission: the last warp of the launch zeroes the counters
+  if (gated && lane == 0) {
+    const unsigned done = atomicAdd(a.gate + 1, 1u);
+    if (done == gridDim.x * Z::WARPS - 1u) {
+      atomicExch(a.gate, 0u);
+      atomicExch(a.gate + 2, 0u);
+      atomicExch(a.gate + 1, 0u);
+    }
+  }
+}
+
 
 template <class Env>
 __global__ void __launch_bounds__(TPB) atacom_slack_init_kernel(const float* __restrict__ q,
@@ -1405,12 +1656,49 @@ bool configure_fix_kernel() {
   return state.load(std::memory_order_acquire) == 1;
 }
 
+template <class Env>
+bool configure_zc_fused_kernel() {
+  static std::atomic<int> states[MAX_DEVICES];
+  std::atomic<int>& state = states[current_device()];
+  if (state.load(std::memory_order_acquire) == 0) {
+    state.store((ZcFused<Env>::BYTES <= 48 * 1024 ||
+                 cudaFuncSetAttribute(atacom_zc_fused_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(ZcFused<Env>::BYTES)) == cudaSuccess) ? 1 : -1,
+                std::memory_order_release);
+  }
+  return state.load(std::memory_order_acquire) == 1;
+}
+
+// Both passes of a step on the caller's page-locked arrays in one launch (atacom_zc_fused_kernel).
+template <class Env>
+int launch_zc_fused(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
+                    uint8_t* status, int64_t B, const AtacomParams* p, void* stream, uint32_t* gate, int gate_window) {
+  using D = typename Env::D;
+  int rc = check_common(B, p);
+  if (rc) return rc;
+  if (B == 0) return ATACOM_OK;
+  if (!q || !dq || !ddq || (D::G > 0 && (!s_in || !s_out)) || (D::k > 0 && !alpha)) return ATACOM_ERR_NULL_POINTER;
+  if (!configure_zc_fused_kernel<Env>()) return ATACOM_ERR_CUDA;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(s_in) |
+                         reinterpret_cast<uintptr_t>(alpha) | reinterpret_cast<uintptr_t>(ddq) |
+                         reinterpret_cast<uintptr_t>(s_out) | reinterpret_cast<uintptr_t>(status);
+  ZcArgs a{q, dq, s_in, alpha, ddq, s_out, status, B, (bits & 15) == 0 ? 1 : 0, gate_window,
+           (gate != nullptr && gate_window > 0) ? gate : nullptr};
+  const ParamsT<float> Pk = as_params(p);
+  const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
+  const unsigned grid = static_cast<unsigned>((B + ZcFused<Env>::TPB - 1) / ZcFused<Env>::TPB);
+  NvtxRange range("atacom_step");
+  atacom_zc_fused_kernel<Env><<<grid, ZcFused<Env>::TPB, ZcFused<Env>::BYTES, static_cast<cudaStream_t>(stream)>>>(a, Pk, Kd);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch();
+}
+
 template <class Env, int IO = (ATACOM_STEP_STAGED_IO == 1 ? 1 : ATACOM_STEP_DEVICE_IO)>
 int launch_step(const float* q, const float* dq, const float* s_in, const float* alpha, float* ddq, float* s_out,
                 uint8_t* status, float* w_dbg, int64_t B, const AtacomParams* p, void* stream,
                 float* const* peers = nullptr, int n_peers = 0, int64_t gather_row0 = 0,
                 uint32_t* const* peer_flags = nullptr, uint32_t* local_sync = nullptr, int rank = 0,
-                uint32_t* gate = nullptr, int gate_window = 0, int tpb_override = 0) {
+                uint32_t* gate = nullptr, int gate_window = 0, int tpb_override = 0, bool mirror_inputs = false) {
   int rc = check_common(B, p);
   if (rc) return rc;
   using D = typename Env::D;
@@ -1460,8 +1748,13 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     keep_scratch_pool_warm();
     // [grid * tpb] indices, [grid] counts, then (8-byte aligned) [grid * tpb, N] minimum-norm parts
     const size_t n_idx = (static_cast<size_t>(grid) * tpb + grid + 1) / 2 * 2;
-    const size_t bytes = sizeof(int32_t) * n_idx +
-                         (ATACOM_FIX_NULL_ONLY ? sizeof(double) * static_cast<size_t>(grid) * tpb * D::N : 0);
+    const size_t rows = static_cast<size_t>(grid) * tpb;
+    const size_t wmn_bytes = ATACOM_FIX_NULL_ONLY ? sizeof(double) * rows * D::N : 0;
+    // ... then, for a launch on mapped host arrays, the mirror of the input rows (sections 16-byte aligned)
+    const bool mirror = mirror_inputs && IO == 1;
+    auto sec = [&](size_t width) { return (sizeof(float) * rows * width + 15) / 16 * 16; };
+    const size_t mirror_bytes = mirror ? 2 * sec(D::n) + sec(D::G) + sec(D::k) : 0;
+    const size_t bytes = sizeof(int32_t) * n_idx + wmn_bytes + mirror_bytes;
     if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
       cudaGetLastError();
       return ATACOM_ERR_CUDA;
@@ -1469,11 +1762,24 @@ int launch_step(const float* q, const float* dq, const float* s_in, const float*
     a.fix_list = scratch;
     a.fix_count = scratch + static_cast<size_t>(grid) * tpb;
     a.fix_wmn = ATACOM_FIX_NULL_ONLY ? reinterpret_cast<double*>(scratch + n_idx) : nullptr;
+    if (mirror) {
+      unsigned char* m = reinterpret_cast<unsigned char*>(scratch + n_idx) + wmn_bytes;
+      a.mirror_q = reinterpret_cast<float*>(m);
+      a.mirror_dq = reinterpret_cast<float*>(m + sec(D::n));
+      a.mirror_s = reinterpret_cast<float*>(m + 2 * sec(D::n));
+      a.mirror_alpha = reinterpret_cast<float*>(m + 2 * sec(D::n) + sec(D::G));
+    }
   }
   auto fix_up = [&]() -> int {      // second launch + release of the scratch, after the step kernel is in the stream
     if (!two_pass) return ATACOM_OK;
     FixArgs f{q, dq, s_in, alpha, ddq, s_out, status, w_dbg, a.fix_list, a.fix_count, a.fix_wmn, tpb, {}, gather_row0,
               n_peers};
+    if (a.mirror_q != nullptr) {      // the rows the step kernel has copied into device memory
+      f.q = a.mirror_q;
+      f.dq = a.mirror_dq;
+      f.s_in = a.mirror_s;
+      f.alpha = a.mirror_alpha;
+    }
     for (int w = 0; w < n_peers; ++w) f.peer[w] = peers[w];
     const ParamsT<float> Pk = as_params(p);
     const DualConsts<double> Kd = make_dual_consts<float, double>(Pk, D::F, D::G);
@@ -2008,10 +2314,6 @@ struct HostCall {
   // zero-copy launch (one kernel on the mapped aliases of the caller's buffers), or null when the family has none
   int (*zero_copy)(const HostCall& c, void* const* din, void* const* dout, int64_t B, const AtacomParams* p,
                    struct AtacomHostCtx* ctx);
-  // the step takes two launches (ATACOM_BASIS_LAPACK: step kernel + fix-up): the second one reads the rows of the
-  // deferred environments again, over PCIe when the arrays are the caller's — AUTO then stages (measured: 208 against
-  // 177 M env-steps/s at 65 536 IiwaAirHockey-7H environments); ATACOM_HOST_ZERO_COPY still forces the one-copy path
-  bool two_pass;
 };
 
 struct AtacomHostCtx {
@@ -2113,7 +2415,7 @@ static int host_call(AtacomHostCtx* c, const HostCall& call, int64_t B, const At
     for (int i = 0; i < call.n_out && all; ++i)
       if (call.out[i].h) all = (zout[i] = mapped_alias(call.out[i].h)) != nullptr;
     if (!all && c->mode == ATACOM_HOST_ZERO_COPY) return ATACOM_ERR_BAD_PARAM;
-    if (all && !(c->mode == ATACOM_HOST_AUTO && call.two_pass)) {
+    if (all) {
       rc = call.zero_copy(call, zin, zout, B, p, c);
       if (rc != ATACOM_OK) return rc;
       if (cudaStreamSynchronize(c->streams[0]) != cudaSuccess) return ATACOM_ERR_CUDA;
@@ -2201,11 +2503,21 @@ template <class Env>
 static int host_zero_copy_step(const HostCall&, void* const* din, void* const* dout, int64_t B, const AtacomParams* p,
                                AtacomHostCtx* ctx) {
   constexpr int HOST_IO = ATACOM_STEP_STAGED_IO != 0 ? 1 : 0;
+  using D = typename Env::D;
+  // the reference-exact null basis takes two passes: both in one launch, so that every row crosses PCIe once each way
+  static const bool fused = getenv("ATACOM_ZC_FUSED") == nullptr || atoi(getenv("ATACOM_ZC_FUSED")) != 0;
+  if constexpr (D::k > 1) {
+    if (fused && p->basis_mode == ATACOM_BASIS_LAPACK && p->variant == ATACOM_VARIANT_ATACOM)
+      return launch_zc_fused<Env>(static_cast<const float*>(din[0]), static_cast<const float*>(din[1]),
+                                  static_cast<const float*>(din[2]), static_cast<const float*>(din[3]),
+                                  static_cast<float*>(dout[0]), static_cast<float*>(dout[1]),
+                                  static_cast<uint8_t*>(dout[2]), B, p, ctx->streams[0], ctx->gate, ctx->zc_window);
+  }
   return launch_step<Env, HOST_IO>(static_cast<const float*>(din[0]), static_cast<const float*>(din[1]),
                                    static_cast<const float*>(din[2]), static_cast<const float*>(din[3]),
                                    static_cast<float*>(dout[0]), static_cast<float*>(dout[1]),
                                    static_cast<uint8_t*>(dout[2]), nullptr, B, p, ctx->streams[0], nullptr, 0, 0, nullptr,
-                                   nullptr, 0, ctx->gate, ctx->zc_window, ctx->zc_tpb);
+                                   nullptr, 0, ctx->gate, ctx->zc_window, ctx->zc_tpb, /*mirror_inputs=*/true);
 }
 
 template <class Env>
@@ -2223,13 +2535,13 @@ static int step_host(AtacomHostCtx* c, int family_id, const float* q, const floa
       !configure_step_kernel<Env, HOST_IO, CB>() || !configure_step_kernel<Env, 2, CB>() || !configure_fix_kernel<Env>())
     return ATACOM_ERR_CUDA;
   step_block_size(1);
+  keep_scratch_pool_warm();      // (touches the device's memory pool: not allowed while a stream is capturing either)
   HostCall call = {};
   call.key[0] = family_id;
   call.key[1] = D::n;
   call.key[2] = c->mode;
   call.n_in = 4;
   call.n_out = 3;
-  call.two_pass = p->basis_mode == ATACOM_BASIS_LAPACK && p->variant == ATACOM_VARIANT_ATACOM && D::k > 1;
   call.in[0] = {q, sizeof(float) * D::n};
   call.in[1] = {dq, sizeof(float) * D::n};
   call.in[2] = {D::G > 0 ? s_in : nullptr, sizeof(float) * D::G};

@@ -348,8 +348,8 @@ class HostContext:
     def __init__(self, max_B, chunks=2, mode="auto"):
         """mode: 'staged' (device staging buffers + copy engines), 'hybrid' (inputs through the copy engines,
         outputs stored by the kernels straight into the caller's page-locked buffers), 'zero_copy' (one kernel
-        works on the caller's page-locked buffers over PCIe) or 'auto' (zero-copy when the buffers are page-locked and
-        the step is a single launch, else staged: see `auto_path`).
+        works on the caller's page-locked buffers over PCIe) or 'auto' (zero-copy when the buffers are page-locked,
+        else staged).
         The pipeline of a call is replayed as a CUDA graph while the same buffers are passed."""
         self._ctx = ctypes.c_void_p()
         _lib.check(_lib.lib.atacom_host_ctx_create(ctypes.byref(self._ctx), max_B, chunks))
@@ -358,12 +358,10 @@ class HostContext:
 
     @staticmethod
     def auto_path(family, params, n_ctrl_joints=6):
-        """The data path mode 'auto' takes for page-locked buffers (the rule of host_step in csrc/atacom_kernels.cu):
-        a step of two launches (ATACOM_BASIS_LAPACK with more than one null-space coordinate: step kernel + fix-up,
-        which reads the deferred environments' rows a second time) is staged, a single launch works zero-copy."""
-        k = {"circle": 1, "planar": 3}.get(family, n_ctrl_joints - 1)      # n - F
-        two_pass = params.basis_mode == _lib.BASIS_LAPACK and params.variant == _lib.VARIANT_ATACOM and k > 1
-        return "staged" if two_pass else "zero_copy"
+        """The data path mode 'auto' takes for page-locked buffers (host_call in csrc/atacom_kernels.cu): zero-copy —
+        one launch on the caller's buffers; with the reference-exact null basis both passes of the step run inside
+        that launch (atacom_zc_fused_kernel), so every row still crosses PCIe once each way."""
+        return "zero_copy"
 
     @staticmethod
     def _hptr(t):

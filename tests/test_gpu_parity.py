@@ -487,3 +487,25 @@ def test_fused_substeps_equal_repeated_steps(cuda_device, nj):
     # sub-step k is an input perturbation of sub-step k + 1
     assert worst < 2e-5, worst
     assert ((status & (_lib.ST_NONFINITE | _lib.ST_DENSE_PATH)) == 0).all()
+
+
+@pytest.mark.gpu
+def test_staged_host_call_first_in_a_fresh_process(cuda_device):
+    """A process whose very first library call is a staged (graph-captured) host step in the default two-launch mode:
+    everything that may not run while a stream captures (kernel attributes, the memory pool's release threshold) has
+    to be set up before the capture starts."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from rl_on_manifold_b200 import _lib, projection, synthetic\n"
+        "p = _lib.default_params('iiwa', 6)\n"
+        "q, dq, s, al = [t.cpu() for t in synthetic.device_batch('iiwa', 4096, 7, torch.device('cuda:0'), 6, p)]\n"
+        "ddq, so = torch.empty(4096, 6), torch.empty(4096, 11)\n"
+        "ctx = projection.HostContext(4096, chunks=2, mode='staged')\n"
+        "ctx.iiwa_step(6, q, dq, s, al, ddq, so, p)\n"
+        "ref = projection.step('iiwa', q.cuda(), dq.cuda(), s.cuda(), al.cuda(), p)\n"
+        "assert torch.equal(ddq, ref[0].cpu()) and torch.equal(so, ref[1].cpu())\n"
+        "print('ok')\n" % helpers.ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
