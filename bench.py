@@ -352,9 +352,13 @@ def ours(args):
     if world > 1 and wl == "iiwa" and args.gather != "nccl":
         try:
             from rl_on_manifold_b200.sharding import SymmetricGather
-            fused = SymmetricGather(B, n_out, deferred=(args.gather == "fused-deferred"))
+            root = 0 if args.gather_to == "root" else None
+            fused = SymmetricGather(B, n_out, deferred=(args.gather == "fused-deferred"), root=root)
             fused_note = fused.describe()
-            fused_other = SymmetricGather(B, n_out, deferred=(args.gather != "fused-deferred"))     # the other schedule, for comparison
+            # for comparison: the all-gather (every rank receives every row) when the default gathers to the learner,
+            # else the other barrier schedule
+            fused_other = (SymmetricGather(B, n_out, deferred=(args.gather == "fused-deferred")) if root is not None else
+                           SymmetricGather(B, n_out, deferred=(args.gather != "fused-deferred")))
         except Exception as exc:
             fused_note = "fused gather unavailable (%s: %s); NCCL all-gather used" % (type(exc).__name__, exc)
 
@@ -487,7 +491,9 @@ def ours(args):
         got = buf.clone()
         step_nccl(0)
         torch.cuda.synchronize()
-        okf = torch.tensor([1.0 if torch.equal(got, gathered) else 0.0], device=dev, dtype=torch.float64)
+        # (gather to the learner: the root's buffer is the one that has to be complete)
+        mine = fused.root is None or fused.root == rank
+        okf = torch.tensor([1.0 if (not mine or torch.equal(got, gathered)) else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(okf, op=dist.ReduceOp.MIN)
         gather_verified = bool(okf.item() == 1.0)
 
@@ -636,6 +642,9 @@ def main():
     ap.add_argument("--replays", type=int, default=7)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gather-to", default="root", choices=["root", "all"],
+                    help="N > 1: the projected actions are gathered on rank 0 (the learner; north_star: one gather per "
+                         "roll-out step) or on every rank (all-gather); the other one is timed beside it")
     ap.add_argument("--gather", default="fused-deferred", choices=["fused", "fused-deferred", "nccl"],
                     help="N > 1: fused peer-store epilogue with the barrier of step t deferred behind kernel t+1 (default), "
                          "with the barrier on the kernel's stream, or a plain NCCL all-gather")

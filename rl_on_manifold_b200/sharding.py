@@ -104,13 +104,19 @@ class SymmetricGather:
         own barrier_{t+1} launch, which is stream-ordered behind whatever consumed step t on the side stream.
     """
 
-    def __init__(self, local_B, n, group=None, buffers=None, in_kernel_barrier=False, deferred=False):
+    def __init__(self, local_B, n, group=None, buffers=None, in_kernel_barrier=False, deferred=False, root=None):
+        """root: None — every rank receives every rank's rows (an all-gather); a rank number — only that rank does (a
+        gather to the learner, what SURVEY.md §8e asks for: "one gather over NVLink per roll-out step").  Every rank
+        then stores its rows into the root's buffer alone: 1/world of the NVLink egress of the all-gather, and the
+        buffer `step` returns is complete on the root only."""
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         if self.world > 8:
             raise ValueError("fused gather supports one NVSwitch domain (<= 8 ranks)")
+        if root is not None and (in_kernel_barrier or not 0 <= root < self.world):
+            raise ValueError("root must be a rank of the group (and the in-kernel barrier gathers to every rank)")
         self.local_B, self.n = local_B, n
         self.deferred = bool(deferred) and not in_kernel_barrier
         buffers = buffers if buffers is not None else (3 if self.deferred else 2)
@@ -124,7 +130,10 @@ class SymmetricGather:
             hdl = symm_mem.rendezvous(t, name)
             self.bufs.append(t)
             self.handles.append(hdl)
-            self.ptrs.append((ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs]))
+            targets = [int(p) for p in hdl.buffer_ptrs] if root is None else [int(hdl.buffer_ptrs[root])]
+            self.ptrs.append((ctypes.c_void_p * len(targets))(*targets))
+        self.root = root
+        self.n_targets = self.world if root is None else 1
         # Optional in-kernel barrier: a flag array [world] per rank in symmetric memory and two local counters; the
         # last block of every launch publishes / awaits the step, so no separate barrier launch is needed.
         # Measured at N = 2 it is slower than the separate barrier kernel (29.5 vs 25.1 us per step: the system-
@@ -144,6 +153,13 @@ class SymmetricGather:
         self._last = None                     # (buffer index, event) of the newest step
 
     def describe(self):
+        what = self._describe()
+        if self.root is not None:
+            what = what.replace("fused peer-store epilogue", "fused store epilogue into rank %d's buffer (gather to the "
+                                "learner)" % self.root)
+        return what
+
+    def _describe(self):
         if self.in_kernel_barrier:
             return "fused peer-store epilogue over NVLink symmetric memory, cross-rank barrier inside the kernel"
         if self.deferred:
@@ -163,7 +179,7 @@ class SymmetricGather:
         main = torch.cuda.current_stream()
         with torch.cuda.nvtx.range("atacom_step_gather"):
             if self.in_kernel_barrier:
-                s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
+                s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.n_targets,
                                                     self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
                                                     status=status, flag_ptrs=self._flag_ptrs,
                                                     local_sync=self._local_sync, rank=self.rank)
@@ -174,7 +190,7 @@ class SymmetricGather:
                 prev = self._bar_done[(t - 2) % nb] if t >= 2 else None
                 if prev is not None:
                     main.wait_event(prev)
-            s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.world,
+            s_out = projection.iiwa_step_gather(q, dq, s, alpha, params, self.ptrs[b], self.n_targets,
                                                 self.rank * self.local_B, n_ctrl_joints=n_ctrl_joints, s_out=s_out,
                                                 status=status)
             if not self.deferred:

@@ -67,6 +67,17 @@ def _worker(rank, world, port, B, out):
     fg.finish()
     torch.cuda.synchronize()
     ok = ok and all(torch.equal(o, full_ddq) for o in outs[-3:])
+    # gather to the learner (rank `root`) instead of to everyone: the root's buffer is complete, nobody else's is written
+    for root in (0, world - 1):
+        fg = SymmetricGather(B, 6, deferred=True, root=root)
+        for it in range(4):
+            gathered, s_f = fg.step(sq, sdq, ss, sal, params)
+            fg.ready()
+            if rank == root:
+                ok = ok and torch.equal(gathered, full_ddq)
+            ok = ok and torch.equal(s_f, full_s[shard.lo:shard.hi])
+        fg.finish()
+        torch.cuda.synchronize()
     ok = ok and _lib.spin_timeouts() == 0
     torch.save(dict(ok=bool(ok)), os.path.join(out, "r%d.pt" % rank))
     dist.barrier()
