@@ -714,7 +714,6 @@ struct WarpLanes {
   __device__ __forceinline__ int sub() const { return s; }
   __device__ __forceinline__ int write_lane() const { return s; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
-  __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p) != 0; }
 };
 
 // Block shape of the fix-up kernel for LPE lanes per environment.  A warp holds EPW = 32 / LPE environments (when 32
@@ -894,9 +893,14 @@ struct ZcFused {
   using D = typename Env::D;
   using SC = StepScratch<Env>;
   using LP = Lapack<double, D>;
-  static constexpr int TPB = 128, WARPS = TPB / 32, LPE = 2;
-  static constexpr int SLOTS = 32;                      // deferred environments per round: warps 0 and 1, 2 lanes each
-  static constexpr int STRIDE = SLOTS + 8;              // = 8 (mod 16): see FixShape
+#ifndef ATACOM_ZC_LPE
+#define ATACOM_ZC_LPE 4
+#endif
+  // lanes per deferred environment: the block has registers to spare (128 threads), so 4 lanes — the whole block on
+  // a round of 32 environments — cost nothing here, unlike in the fix-up kernel, and shorten the tail of the launch
+  static constexpr int TPB = 128, WARPS = TPB / 32, LPE = ATACOM_ZC_LPE;
+  static constexpr int SLOTS = 32;                      // deferred environments per round
+  static constexpr int STRIDE = SLOTS + (LPE == 2 ? 8 : 4);   // = 8 / 4 (mod 16): see FixShape
   static constexpr int NA = D::k;
   static constexpr size_t align128(size_t x) { return (x + 127) / 128 * 128; }
   static constexpr size_t IN_WARP = align128(sizeof(float) * 32 * (2 * D::n + D::G + NA));
@@ -1033,9 +1037,9 @@ __global__ void __launch_bounds__(ZcFused<Env>::TPB) atacom_zc_fused_kernel(cons
   }
   __syncthreads();     // every environment of the block is done or queued; the dual path's scratch is free
 
-  // ---- second pass: the null part of the queued environments with the LAPACK basis, 2 lanes each, warps 0 and 1
+  // ---- second pass: the null part of the queued environments with the LAPACK basis, LPE lanes each
   const int cnt = static_cast<int>(*reinterpret_cast<volatile uint32_t*>(fixn));
-  if (warp < 2 * Z::SLOTS / 32) {
+  if (warp < Z::LPE * Z::SLOTS / 32) {
     const int slot = static_cast<int>(threadIdx.x) / Z::LPE, sub = static_cast<int>(threadIdx.x) % Z::LPE;
     PlainSharedStore<double, Z::STRIDE> S{reinterpret_cast<double*>(atacom_smem + Z::WORK_OFF) + slot};
     const int warp_slot0 = warp * (32 / Z::LPE);

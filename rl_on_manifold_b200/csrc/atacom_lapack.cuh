@@ -1,5 +1,6 @@
 // The reference's null-space basis, restated: what scipy.linalg.svd (LAPACK gesdd) hands to
-// atacom/utils/null_space_coordinate.py:8-26, followed by the reference's tolerance-RREF (:40-79) exactly as written.
+// atacom/utils/null_space_coordinate.py:8-26, followed by the reference's tolerance-RREF (:40-79): its decisions and
+// its result, evaluated lazily (see the comment at the rref below).
 //
 // For a full-row-rank C x N matrix (C < N) gesdd never touches the null vectors with its SVD iteration: with
 // JOBZ = 'A' the trailing N - C rows of VT are [0 I] P^T, where P = G_0 G_1 ... G_{C-1} is the product of the RIGHT
@@ -20,7 +21,8 @@
 // Storage: ONE C x N array (`S`, any store with get / set at a run-time index: a column of a shared-memory array on
 // the device).  It holds Jc, then the reflector vectors (v_i right of the diagonal of row i, u_i below the
 // subdiagonal of column i, the bidiagonal in between), then — in cells that have died by then — the null basis Z
-// (N x k) on which the RREF runs in place.  Cost ~ 4 C^2 (N - C/3) + 4 N C k flops: ~10 kFLOP for 12 x 17.
+// (N x k), which the rref only reads, and the N entries of the result.  Cost ~ 4 C^2 (N - C/3) + 4 N C k flops:
+// ~10 kFLOP for 12 x 17.
 #pragma once
 
 #include "atacom_core.cuh"
@@ -48,7 +50,6 @@ struct ArrayStore {
 struct SoloGroup {
   ATACOM_HD int sub() const { return 0; }
   ATACOM_HD void sync() const {}
-  ATACOM_HD bool all(bool p) const { return p; }      // true when p holds for every environment that syncs along
   ATACOM_HD int write_lane() const { return 0; }      // which rows of Jc this lane fills in: i % LPE == write_lane(); < 0: all
 };
 

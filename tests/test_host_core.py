@@ -81,6 +81,30 @@ def test_full_step_vs_oracle(harness, family, B, dtype, mode):
         assert ((st & _lib.ST_LAPACK_PATH) == 0).all()
 
 
+@pytest.mark.parametrize("family", ["planar", "iiwa6", "iiwa7"])
+def test_null_only_fix_up_equals_the_full_lapack_redo(harness, family):
+    """The fix-up kernel redoes the NULL part only and takes the minimum-norm part from the dual path (it is the same
+    for every basis).  Against redoing both parts with the LAPACK routine — B y = -U^T r through the bidiagonal factor
+    — the outputs of the deferred environments agree to rounding."""
+    B = 600
+    q, dq, s, alpha = helpers.synthetic_cpu(family, B, seed=77)
+    pf = helpers.exact_params_flat(family, _params(family))
+    harness.harness_set_fix_full(0)
+    ddq0, s0, dbg0, st0 = helpers.harness_step(harness, family, pf, q, dq, s, alpha, np.float64)
+    harness.harness_set_fix_full(1)
+    try:
+        ddq1, s1, dbg1, st1 = helpers.harness_step(harness, family, pf, q, dq, s, alpha, np.float64)
+    finally:
+        harness.harness_set_fix_full(0)
+    redone = (st0 & _lib.ST_LAPACK_PATH) != 0
+    ok = redone & ((st0 & _lib.ST_RANK_DEFICIENT) == 0) & ((st1 & _lib.ST_RANK_DEFICIENT) == 0)
+    assert ok.sum() > 20 and np.array_equal(st0 & _lib.ST_LAPACK_PATH, st1 & _lib.ST_LAPACK_PATH)
+    N = dbg0.shape[1] // 2
+    assert helpers.rel_err(dbg0[:, :N], dbg1[:, :N])[ok].max() < 1e-9       # the two minimum-norm parts
+    assert np.array_equal(dbg0[ok][:, N:], dbg1[ok][:, N:])                 # the null part is the same computation
+    assert helpers.rel_err(ddq0, ddq1)[ok].max() < 1e-9 and helpers.rel_err(s0, s1)[ok].max() < 1e-9
+
+
 @pytest.mark.parametrize("family", ["circle", "planar", "iiwa6"])
 def test_stratum_one_equals_reference_svd_basis(harness, family):
     """Where the tolerance branch does not fire the kernels' result equals the reference's own
