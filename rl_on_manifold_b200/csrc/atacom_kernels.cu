@@ -768,13 +768,17 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
   // equal ranges.  Warp 0 sums the counts, then walks them once more and notes the segments that overlap this block's
   // range [lo, hi) (a handful) in a small table; every slot then finds its environment there.
   constexpr int TABN = FixCfg<Env>::ENVS + 2;
-  __shared__ int tab_seg[TABN], tab_beg[TABN];
+  constexpr int CNTS = 1024;                             // counts kept in shared memory (more segments: read again)
+  __shared__ int tab_seg[TABN], tab_beg[TABN], cnts[CNTS];
   __shared__ int tab_n, range_lo, range_hi;
   const int nseg = static_cast<int>(gridDim.x);
+  for (int b = static_cast<int>(threadIdx.x); b < nseg && b < CNTS; b += static_cast<int>(blockDim.x)) cnts[b] = a.fix_count[b];
+  __syncthreads();
   if (threadIdx.x < 32) {
     const int lane = static_cast<int>(threadIdx.x);
+    auto count_of = [&](int b) { return b < CNTS ? cnts[b] : a.fix_count[b]; };
     int sum = 0;
-    for (int b = lane; b < nseg; b += 32) sum += a.fix_count[b];
+    for (int b = lane; b < nseg; b += 32) sum += count_of(b);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const int per = (sum + nseg - 1) / nseg;
@@ -783,7 +787,7 @@ __global__ void __launch_bounds__(FixCfg<Env>::TPB) atacom_fix_kernel(const __gr
     const int hi = lo + per < sum ? lo + per : sum;
     int run = 0, ntab = 0;
     for (int base = 0; base < nseg && run < hi; base += 32) {
-      const int c = base + lane < nseg ? a.fix_count[base + lane] : 0;
+      const int c = base + lane < nseg ? count_of(base + lane) : 0;
       int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {

@@ -379,20 +379,25 @@ struct Lapack {
       for (int m = 0; m < k; ++m) E[i][m] = (i == m) ? R(1) : R(0);
       g[i] = R(0);
     }
+    // Within a stage the walk over the columns only LOOKS for the pivot (a dropped column costs its dot products and
+    // one store); the pivot step itself comes after the loop, where the groups of a warp — which have dropped
+    // different numbers of columns on the way — are together again and execute it once.
     int j = 0;
     ATACOM_UNROLL
     for (int rr = 0; rr < k; ++rr) {
       bool found = false;
+      R z[K1], c[K1];
+      R gz = R(0);
+      int kk = rr;
       ATACOM_ROLLED
-      while (j < N && !found) {
-        R z[K1], c[K1];
+      while (j < N) {
         ATACOM_UNROLL
         for (int m = 0; m < k; ++m) z[m] = S.get(zcell(j, m));
-        R gz = g[0] * z[0];
+        gz = g[0] * z[0];
         ATACOM_UNROLL
         for (int m = 1; m < k; ++m) gz += g[m] * z[m];
         R p = R(-1);
-        int kk = rr;
+        kk = rr;
         ATACOM_UNROLL
         for (int i = rr; i < k; ++i) {
           R acc = E[i][0] * z[0];
@@ -407,53 +412,57 @@ struct Lapack {
         }
         if (p > tol) {
           found = true;
-          if (j >= n) status |= ST_SLACK_PIVOT;
-          S.set(wcell(j), alpha[rr]);
-          // rows rr and kk change places; the pivot row is scaled
-          R ckk = c[rr];
-          ATACOM_UNROLL
-          for (int i = rr + 1; i < k; ++i) {
-            const R ci = c[i];
-            c[i] = (i == kk) ? c[rr] : ci;
-            ckk = (i == kk) ? ci : ckk;
-          }
-          const R inv = rcp(ckk);
-          ATACOM_UNROLL
-          for (int m = 0; m < k; ++m) {
-            R e = E[rr][m];
-            ATACOM_UNROLL
-            for (int i = rr + 1; i < k; ++i) {
-              const R ei = E[i][m];
-              E[i][m] = (i == kk) ? E[rr][m] : ei;
-              e = (i == kk) ? ei : e;
-            }
-            E[rr][m] = e * inv;
-          }
-          // ... and is eliminated from the rows still to come and from the rows used before
-          ATACOM_UNROLL
-          for (int i = 0; i < k; ++i) {
-            if (i == rr) continue;
-            R ci;
-            if (i > rr) {
-              ci = c[i];
-            } else {
-              ci = E[i][0] * z[0];
-              ATACOM_UNROLL
-              for (int m = 1; m < k; ++m) ci += E[i][m] * z[m];
-            }
-            ATACOM_UNROLL
-            for (int m = 0; m < k; ++m) E[i][m] -= ci * E[rr][m];
-          }
-          const R dg = alpha[rr] - gz;             // g = sum_{l <= rr} alpha_l E[l] of the updated rows
-          ATACOM_UNROLL
-          for (int m = 0; m < k; ++m) g[m] += dg * E[rr][m];
-        } else {
-          status |= ST_COLUMN_DROPPED;
-          S.set(wcell(j), gz);
+          break;
         }
+        status |= ST_COLUMN_DROPPED;
+        S.set(wcell(j), gz);
         ++j;
       }
-      if (!found) status |= ST_RANK_DEFICIENT;     // (ran out of columns: the later stages find j == N)
+      if (!found) {
+        status |= ST_RANK_DEFICIENT;               // ran out of columns (the later stages find j == N as well)
+        continue;
+      }
+      if (j >= n) status |= ST_SLACK_PIVOT;
+      S.set(wcell(j), alpha[rr]);
+      // rows rr and kk change places; the pivot row is scaled
+      R ckk = c[rr];
+      ATACOM_UNROLL
+      for (int i = rr + 1; i < k; ++i) {
+        const R ci = c[i];
+        c[i] = (i == kk) ? c[rr] : ci;
+        ckk = (i == kk) ? ci : ckk;
+      }
+      const R inv = rcp(ckk);
+      ATACOM_UNROLL
+      for (int m = 0; m < k; ++m) {
+        R e = E[rr][m];
+        ATACOM_UNROLL
+        for (int i = rr + 1; i < k; ++i) {
+          const R ei = E[i][m];
+          E[i][m] = (i == kk) ? E[rr][m] : ei;
+          e = (i == kk) ? ei : e;
+        }
+        E[rr][m] = e * inv;
+      }
+      // ... and is eliminated from the rows still to come and from the rows used before
+      ATACOM_UNROLL
+      for (int i = 0; i < k; ++i) {
+        if (i == rr) continue;
+        R ci;
+        if (i > rr) {
+          ci = c[i];
+        } else {
+          ci = E[i][0] * z[0];
+          ATACOM_UNROLL
+          for (int m = 1; m < k; ++m) ci += E[i][m] * z[m];
+        }
+        ATACOM_UNROLL
+        for (int m = 0; m < k; ++m) E[i][m] -= ci * E[rr][m];
+      }
+      const R dg = alpha[rr] - gz;                 // g = sum_{l <= rr} alpha_l E[l] of the updated rows
+      ATACOM_UNROLL
+      for (int m = 0; m < k; ++m) g[m] += dg * E[rr][m];
+      ++j;
     }
     ATACOM_UNROLL
     for (int jj = 0; jj < N; ++jj) {
