@@ -713,6 +713,12 @@ struct WarpLanes {
   int s;
   __device__ __forceinline__ int sub() const { return s; }
   __device__ __forceinline__ int write_lane() const { return s; }
+  // sum over the LPE (2 or 4, adjacent) lanes of the group: a butterfly, the same bits in every lane
+  template <int LPE, typename R> __device__ __forceinline__ R sum(R x) const {
+#pragma unroll
+    for (int o = LPE / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+  }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 

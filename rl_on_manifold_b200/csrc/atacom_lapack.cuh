@@ -51,6 +51,7 @@ struct SoloGroup {
   ATACOM_HD int sub() const { return 0; }
   ATACOM_HD void sync() const {}
   ATACOM_HD int write_lane() const { return 0; }      // which rows of Jc this lane fills in: i % LPE == write_lane(); < 0: all
+  template <int LPE, typename R> ATACOM_HD R sum(R x) const { return x; }     // over the lanes of the group
 };
 
 template <typename R, class D>
@@ -171,10 +172,126 @@ struct Lapack {
     R tau_s[WITH_MN ? C1 : 1];
     R bmax = R(0), bmin = R(1e300);                // largest and smallest |diagonal entry| of the bidiagonal / L factor
 
-    // ---- reflectors (dgebd2 / dgelq2), left reflectors applied to the right-hand side as they are formed.
-    // The loop over i is unrolled: every range below is static, nothing is predicated.
+    // ---- reflectors (dgebd2 / dgelq2).
+    // (a) Null part only, bidiagonal path: ONE pass over the trailing rows per reflector pair.  What bounds the sweeps
+    // on the device is shared-memory bandwidth — every trailing entry read and written once per reflector — so the
+    // left reflector H_i is not applied in a column sweep of its own: a lane that has a row in registers applies the
+    // PENDING left reflector H_{i-1} to it (row_l -= u_l y^T, u_l = A[l][i-1] scq the row's own entry of column i-1),
+    // then G_i, and adds the row's share to what H_i needs — P_j = sum_l A[l][i] A[l][j] over the rows below the
+    // subdiagonal and the squared norm of column i; the column dot products of H_i are y_j = tauq (A[i+1][j] +
+    // scq P_j), a scaling away.  The lanes' partial sums meet in a butterfly (Grp.sum), row i+1 is read by every lane,
+    // H_i and, from that row with H_i applied, G_{i+1} are formed by every lane alike.  Half the shared-memory
+    // traffic of (b), the same arithmetic up to the order of two roundings.
+    constexpr bool FUSED_PAIRS = !WITH_MN && !LQ_PATH && (LPE == 1 || LPE == 2 || LPE == 4) && C >= 2;
+    if constexpr (FUSED_PAIRS) {
+      R v[N], y[N];
+      R tau, scq_prev = R(0);
+      {
+        Grp.sync();
+        R xs[NACC];
+        ATACOM_UNROLL
+        for (int t = 0; t < NACC; ++t) xs[t] = R(0);
+        const R x0 = S.get(a(0, 0));
+        ATACOM_UNROLL
+        for (int j = 1; j < N; ++j) {
+          v[j] = S.get(a(0, j));
+          xs[(j - 1) % NACC] += v[j] * v[j];
+        }
+        R xn2 = xs[0];
+        ATACOM_UNROLL
+        for (int t = 1; t < NACC; ++t) xn2 += xs[t];
+        R beta, sc;
+        larfg(x0, xn2, &beta, &tau, &sc);
+        const R ab = num<R>::abs(beta);
+        bmax = ab > bmax ? ab : bmax;
+        bmin = ab < bmin ? ab : bmin;
+        ATACOM_UNROLL
+        for (int j = 1; j < N; ++j) v[j] *= sc;
+        Grp.sync();                                // every lane has read row 0
+        if (sub == 0) {
+          S.set(a(0, 0), tau);
+          ATACOM_UNROLL
+          for (int j = 1; j < N; ++j) S.set(a(0, j), v[j]);
+        }
+      }
+      ATACOM_UNROLL
+      for (int i = 0; i < C - 1; ++i) {
+        R Pj[N];
+        R cn2 = R(0);
+        ATACOM_UNROLL
+        for (int j = i + 1; j < N; ++j) Pj[j] = R(0);
+        ATACOM_ROLLED
+        for (int l = i + 1 + sub; l < C; l += LPE) {
+          R row[N];
+          ATACOM_UNROLL
+          for (int j = i; j < N; ++j) row[j] = S.get(a(l, j));
+          if (i >= 1) {                            // H_{i-1}, pending from the step before
+            const R ul = S.get(a(l, i >= 1 ? i - 1 : 0)) * scq_prev;
+            ATACOM_UNROLL
+            for (int j = i; j < N; ++j) row[j] -= ul * y[j];
+          }
+          R ws[NACC];                              // G_i
+          ATACOM_UNROLL
+          for (int t = 0; t < NACC; ++t) ws[t] = (t == 0) ? row[i] : R(0);
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) ws[(j - i) % NACC] += row[j] * v[j];
+          R wsum = ws[0];
+          ATACOM_UNROLL
+          for (int t = 1; t < NACC; ++t) wsum += ws[t];
+          const R w = wsum * tau;
+          row[i] -= w;
+          ATACOM_UNROLL
+          for (int j = i + 1; j < N; ++j) row[j] -= w * v[j];
+          if (l != i + 1) {                        // below the subdiagonal: the row's share of H_i
+            cn2 += row[i] * row[i];
+            ATACOM_UNROLL
+            for (int j = i + 1; j < N; ++j) Pj[j] += row[i] * row[j];
+          }
+          ATACOM_UNROLL
+          for (int j = i; j < N; ++j) S.set(a(l, j), row[j]);
+        }
+        Grp.sync();                                // the rows are final up to H_i
+        cn2 = Grp.template sum<LPE>(cn2);
+        ATACOM_UNROLL
+        for (int j = i + 1; j < N; ++j) Pj[j] = Grp.template sum<LPE>(Pj[j]);
+        R pr[N];                                   // row i + 1: the row H_i pivots on, then the one G_{i+1} is made of
+        ATACOM_UNROLL
+        for (int j = i; j < N; ++j) pr[j] = S.get(a(i + 1, j));
+        R betaq, tauq, scq;
+        larfg(pr[i], cn2, &betaq, &tauq, &scq);
+        ATACOM_UNROLL
+        for (int j = i + 1; j < N; ++j) {
+          y[j] = (pr[j] + scq * Pj[j]) * tauq;
+          pr[j] -= y[j];
+        }
+        R xs[NACC];
+        ATACOM_UNROLL
+        for (int t = 0; t < NACC; ++t) xs[t] = R(0);
+        ATACOM_UNROLL
+        for (int j = i + 2; j < N; ++j) xs[(j - i) % NACC] += pr[j] * pr[j];
+        R xn2 = xs[0];
+        ATACOM_UNROLL
+        for (int t = 1; t < NACC; ++t) xn2 += xs[t];
+        R beta, sc;
+        larfg(pr[i + 1], xn2, &beta, &tau, &sc);
+        const R ab = num<R>::abs(beta);
+        bmax = ab > bmax ? ab : bmax;
+        bmin = ab < bmin ? ab : bmin;
+        ATACOM_UNROLL
+        for (int j = i + 2; j < N; ++j) v[j] = pr[j] * sc;
+        scq_prev = scq;
+        Grp.sync();                                // every lane has read row i + 1
+        if (sub == 0) {
+          S.set(a(i + 1, i + 1), tau);
+          ATACOM_UNROLL
+          for (int j = i + 2; j < N; ++j) S.set(a(i + 1, j), v[j]);
+        }
+      }
+    }
+    // (b) Everything else: left reflectors applied in a sweep over the columns, and to the right-hand side as they are
+    // formed.  The loop over i is unrolled: every range below is static, nothing is predicated.
     ATACOM_UNROLL
-    for (int i = 0; i < C; ++i) {
+    for (int i = 0; i < (FUSED_PAIRS ? 0 : C); ++i) {
       Grp.sync();                                  // row i is final: the previous reflectors have been applied to it
       R v[N];                                      // row i right of the diagonal, then the reflector vector
       R xs[NACC];                                  // NACC partial sums: the dependent chains are what bounds a warp here

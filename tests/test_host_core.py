@@ -101,7 +101,8 @@ def test_null_only_fix_up_equals_the_full_lapack_redo(harness, family):
     assert ok.sum() > 20 and np.array_equal(st0 & _lib.ST_LAPACK_PATH, st1 & _lib.ST_LAPACK_PATH)
     N = dbg0.shape[1] // 2
     assert helpers.rel_err(dbg0[:, :N], dbg1[:, :N])[ok].max() < 1e-9       # the two minimum-norm parts
-    assert np.array_equal(dbg0[ok][:, N:], dbg1[ok][:, N:])                 # the null part is the same computation
+    # the null parts: the same reflectors, applied pairwise in one pass (null-only) or one by one (full redo)
+    assert helpers.rel_err(dbg0[:, N:], dbg1[:, N:])[ok].max() < 1e-9
     assert helpers.rel_err(ddq0, ddq1)[ok].max() < 1e-9 and helpers.rel_err(s0, s1)[ok].max() < 1e-9
 
 
