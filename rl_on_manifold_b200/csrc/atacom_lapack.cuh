@@ -487,8 +487,8 @@ struct Lapack {
     // g = sum over the rows used so far of alpha_l E[l].
     // One stage per pivot, unrolled: in stage r only the rows r.. are candidates, so a column costs (k - r) dot
     // products, and the stages that walk through many dropped columns (the last pivot of an environment with an
-    // active constraint is a slack column) are the cheap ones.  Every lane of a group runs this redundantly — no
-    // shared-memory writes but its own results, no synchronisation.
+    // active constraint is a slack column) are the cheap ones.  Every lane of a group runs this redundantly; lane 0
+    // notes the per-column results in shared memory (w_null is indexed at run time), one synchronisation at the end.
     R E[K1][K1], g[K1];
     ATACOM_UNROLL
     for (int i = 0; i < k; ++i) {
@@ -532,7 +532,7 @@ struct Lapack {
           break;
         }
         status |= ST_COLUMN_DROPPED;
-        S.set(wcell(j), gz);
+        if (sub == 0) S.set(wcell(j), gz);
         ++j;
       }
       if (!found) {
@@ -540,7 +540,7 @@ struct Lapack {
         continue;
       }
       if (j >= n) status |= ST_SLACK_PIVOT;
-      S.set(wcell(j), alpha[rr]);
+      if (sub == 0) S.set(wcell(j), alpha[rr]);
       // rows rr and kk change places; the pivot row is scaled
       R ckk = c[rr];
       ATACOM_UNROLL
@@ -581,6 +581,7 @@ struct Lapack {
       for (int m = 0; m < k; ++m) g[m] += dg * E[rr][m];
       ++j;
     }
+    Grp.sync();                                    // lane 0's per-column results are visible to the group
     ATACOM_UNROLL
     for (int jj = 0; jj < N; ++jj) {
       if (jj < j) {
