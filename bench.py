@@ -442,7 +442,10 @@ def ours(args):
                                                    "one NCCL all-gather of the projected action per step")
     launches0 = _lib.launch_count()
     eager_ms = timed_eager(default_step)
-    launches_eager = _lib.launch_count() - launches0 - args.warmup
+    # kernels of this library per step (2 in the default mode of the step families: step kernel + fix-up), counted by
+    # the library itself over the eager leg's warm-up + K steps
+    kernels_per_step = max(1, round((_lib.launch_count() - launches0) / float(args.warmup + K)))
+    launches_eager = kernels_per_step * K
     if default_finish:
         default_finish()
     if args.no_graph:
@@ -453,7 +456,7 @@ def ours(args):
         if world == 1 and wl != "point_reach" and os.environ.get("ATACOM_PDL", "1") != "0":
             launch_mode += "; programmatic dependent launch"
     total_ms, min_ms = statistics.median(replay_ms), min(replay_ms)
-    launches = K * len(replay_ms) if not args.no_graph else launches_eager
+    launches = kernels_per_step * K * len(replay_ms) if not args.no_graph else launches_eager
 
     # ---- comparison paths at N > 1 (reported in config, never substituted for the default path)
     nccl_ms = kernel_ms_list = other_ms = None
